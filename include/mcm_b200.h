@@ -1,0 +1,122 @@
+/* motioncraft_b200 -- C ABI of the B200-native MotionCraft (configs/mcm/*) denoising hot path.
+ *
+ * The reference has NO native boundary: its seam is the mmcv registry + nn.Module call convention
+ * (SURVEY.md section 8b).  This header is the boundary a maintainer would bind instead; every entry
+ * names the reference code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain C, no torch types: device pointers are raw CUDA pointers (fp32, row-major, contiguous),
+ *     `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - every function returns 0 on success, non-zero on error; mcm_last_error() returns the message of
+ *     the calling thread's last failure.  Nothing throws, nothing calls exit().
+ *   - one context per (device, stream); a context is NOT re-entrant.  The caller keeps OWNERSHIP of all
+ *     parameter and activation memory; the context borrows parameter pointers only during
+ *     mcm_finalize_params() (it keeps its own packed 16-bit copies; call it again after load_state_dict).
+ *   - requires an sm_100a device.  There is no CPU or non-tcgen05 fallback: creation fails loudly.
+ */
+#ifndef MCM_B200_H_
+#define MCM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcm_ctx mcm_ctx;
+
+/* Architecture of the denoiser, as configs/mcm/mcm_t2m_smplx.py:26-58 spells it. */
+typedef struct mcm_config {
+  int input_feats;      /* 322                       (input_feats)                               */
+  int seq_len;          /* T = max_seq_len; also the SA feature dim (sa_block_cfg.latent_dim)    */
+  int latent_dim;       /* 512                                                                   */
+  int time_embed_dim;   /* 2048                                                                  */
+  int ffn_dim;          /* 1024 (ff_size)                                                        */
+  int text_latent_dim;  /* 256                                                                   */
+  int num_heads;        /* 4                                                                     */
+  int num_layers;       /* 8                                                                     */
+  int num_ctrl_blocks;  /* copy_blocks_num of ControlT2MHalf_MCM, 0 = no control branch          */
+  int ctrl_cond_feats;  /* in_features of control_cond_input (2048 pre-encoded audio, 35 music)   */
+  int max_batch;        /* workspace is sized for this many samples                              */
+  int max_text_tokens;  /* 77                                                                    */
+  int precise_all;      /* debug: run EVERY GEMM in the 3-pass bf16-split mode (~fp32 accuracy)   */
+} mcm_config;
+
+/* Sampler description: float32 copies of the float64 tables of GaussianDiffusion.__init__
+ * (mogen/models/utils/gaussian_diffusion.py:354-387), already respaced (SpacedDiffusion.__init__
+ * :1416-1431), each of length n_steps, plus timestep_map (:1421-1429).  The float32 cast is the one
+ * _extract_into_tensor (:1340) applies. */
+typedef struct mcm_sampler {
+  int mode;                                   /* 0 = DDIM (ddim_sample :799-852), 1 = DDPM (p_sample :634-696) */
+  int n_steps;
+  float eta;                                  /* DDIM eta (MotionDiffusion passes 0)                 */
+  const int* timestep_map;                    /* host, [n_steps]                                      */
+  const float* alphas_cumprod;                /* host, [n_steps]                                      */
+  const float* alphas_cumprod_prev;
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_log_variance_clipped;
+} mcm_sampler;
+
+/* replaces: MCMTransformer.__init__ / DiffusionTransformer.__init__
+ * (mogen/models/transformers/diffusion_transformer.py:56-99) -- allocates workspace, no weights yet. */
+int mcm_create(const mcm_config* cfg, mcm_ctx** out);
+void mcm_destroy(mcm_ctx* ctx);
+
+/* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key
+ * (SURVEY.md section 8b), e.g. "temporal_decoder_blocks.3.ca_block.query.weight"; ControlNet keys are
+ * "controlnet.{j}.copied_block.*", "controlnet.{j}.before_proj.*", "controlnet.{j}.after_proj.*",
+ * "control_cond_input.*" (controlnet_mcm.py:34-53,138-153).  dev_ptr: fp32 device memory. */
+int mcm_set_param(mcm_ctx* ctx, const char* name, const float* dev_ptr, long long numel);
+/* Pack all parameters into tensor-core operand form.  Fails if a required key is missing. */
+int mcm_finalize_params(mcm_ctx* ctx, void* stream);
+
+/* replaces: the step-INVARIANT part of the per-step forward -- the key/value/softmax/K^T V half of every
+ * EfficientCrossAttention (efficient_attention.py:74-88), which depends only on xf_out, and
+ * ControlT2MHalf_MCM.forward_c (controlnet_mcm.py:155-166), which depends only on c.
+ *   xf_out [B, n_tokens, text_latent_dim], xf_proj [B, time_embed_dim]   (get_precompute_condition, mcm.py:58-67)
+ *   c      [B, c_len, ctrl_cond_feats] pre-encoded condition or NULL */
+int mcm_prepare_conditions(mcm_ctx* ctx, int batch, const float* xf_out, int n_tokens, const float* xf_proj,
+                           const float* c, int c_len, void* stream);
+
+/* replaces: DiffusionTransformer.forward + MCMTransformer.forward_test (diffusion_transformer.py:186-238,
+ * mcm.py:93-102) or ControlT2MHalf_MCM.forward/forward_test (controlnet_mcm.py:168-233, 306-361) when the
+ * context has control blocks and a condition was prepared.
+ *   x [B, T, input_feats]; timesteps: device int64 [B] (ORIGINAL 0..999 timesteps) or NULL to use
+ *   t_uniform for every sample; eps_out [B, T, input_feats]. */
+int mcm_denoise(mcm_ctx* ctx, int batch, const float* x, const long long* timesteps, int t_uniform,
+                float* eps_out, void* stream);
+
+/* replaces: one DecoderLayer.forward (mcm.py:25-41) -- the per-block entry ControlT2MHalf_MCM and
+ * block-level parity tests use.  kind 0 = temporal_decoder_blocks[index], 1 = controlnet[index].copied_block.
+ *   x_inout [B, T, latent_dim] (updated in place), emb [B, time_embed_dim]. */
+int mcm_block_forward(mcm_ctx* ctx, int kind, int index, int batch, float* x_inout, const float* emb,
+                      void* stream);
+
+/* replaces: GaussianDiffusion.ddim_sample_loop / p_sample_loop (gaussian_diffusion.py:698-797, 925-1049)
+ * with clip_denoised=False, epsilon prediction, fixed_small variance.
+ *   x_T [B,T,F] device; step_noise: device [n_steps, B, T, F] (index i = retained step i) or NULL
+ *   (required for DDPM and for DDIM with eta != 0); x0_out [B,T,F] device. */
+int mcm_sample(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* x_T, const float* step_noise,
+               float* x0_out, void* stream);
+/* Same through HOST buffers (pinned or pageable): host->device copy of x_T, the loop, device->host copy
+ * of x_0, all on `stream`, synchronised before returning.  This is the end-to-end call bench.py times. */
+int mcm_sample_host(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* x_T_host,
+                    const float* step_noise_host, float* x0_out_host, void* stream);
+
+/* Raw tensor-core GEMM, exposed for unit tests of the kernel itself:
+ *   C[M,N] (fp32) = A[M,K] * W[N,K]^T + bias[N]   with A, W fp32 device tensors quantised to
+ *   fmt 0 = fp16 (1 pass) or 1 = bf16 hi/lo (3 passes). */
+int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
+                    int fmt, void* stream);
+
+const char* mcm_last_error(void);
+/* kernels launched by this library since process start (tcgen05 GEMMs, all kernels) */
+unsigned long long mcm_gemm_launches(void);
+unsigned long long mcm_kernel_launches(void);
+const char* mcm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCM_B200_H_ */

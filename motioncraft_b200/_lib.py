@@ -1,0 +1,87 @@
+"""ctypes binding of the C-ABI CUDA library (include/mcm_b200.h).
+
+There is deliberately no fallback: if `libmcm_b200.so` is missing or cannot be loaded the import of
+the product path raises, and every entry point raises `McmError` with the library's own message on
+a non-zero status.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcm_b200.so")
+
+
+class McmError(RuntimeError):
+    pass
+
+
+class McmConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "input_feats", "seq_len", "latent_dim", "time_embed_dim", "ffn_dim", "text_latent_dim", "num_heads",
+        "num_layers", "num_ctrl_blocks", "ctrl_cond_feats", "max_batch", "max_text_tokens", "precise_all")]
+
+
+_FP = ctypes.POINTER(ctypes.c_float)
+_IP = ctypes.POINTER(ctypes.c_int)
+
+
+class McmSampler(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int), ("n_steps", ctypes.c_int), ("eta", ctypes.c_float),
+                ("timestep_map", _IP), ("alphas_cumprod", _FP), ("alphas_cumprod_prev", _FP),
+                ("sqrt_recip_alphas_cumprod", _FP), ("sqrt_recipm1_alphas_cumprod", _FP),
+                ("posterior_mean_coef1", _FP), ("posterior_mean_coef2", _FP),
+                ("posterior_log_variance_clipped", _FP)]
+
+
+# name -> (restype, argtypes); exactly the symbols include/mcm_b200.h declares
+_VP, _I, _LL = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+SIGNATURES = {
+    "mcm_create": (_I, [ctypes.POINTER(McmConfig), ctypes.POINTER(_VP)]),
+    "mcm_destroy": (None, [_VP]),
+    "mcm_set_param": (_I, [_VP, ctypes.c_char_p, _VP, _LL]),
+    "mcm_finalize_params": (_I, [_VP, _VP]),
+    "mcm_prepare_conditions": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
+    "mcm_denoise": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP]),
+    "mcm_block_forward": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
+    "mcm_sample": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
+    "mcm_sample_host": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
+    "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
+    "mcm_last_error": (ctypes.c_char_p, []),
+    "mcm_gemm_launches": (ctypes.c_ulonglong, []),
+    "mcm_kernel_launches": (ctypes.c_ulonglong, []),
+    "mcm_version": (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raises McmError if it is absent (run `python -c 'import
+    __graft_entry__ as g; g.build()'` or ./build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McmError(f"{LIB_PATH} not found: the CUDA extension is not built (./build.sh). "
+                       "motioncraft_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the library ever diverge
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().mcm_last_error()
+        raise McmError(msg.decode() if msg else f"mcm status {status}")
+
+
+def kernel_launches():
+    return int(load().mcm_kernel_launches())
+
+
+def gemm_launches():
+    return int(load().mcm_gemm_launches())

@@ -1,0 +1,747 @@
+// motioncraft_b200 -- the denoiser context: parameter packing, HBM workspace, the per-step schedule of
+// kernels for the MCM transformer (+ ControlNet branch) and the DDIM / DDPM sampler loop; plus the
+// extern "C" surface declared in include/mcm_b200.h.
+//
+// Data layout in HBM (B samples, T frames, D = latent 512):
+//   x      [B*T, 322]  fp32   sampler state                     xop  [B*T, 328] bf16 hi/lo (joint_embed operand)
+//   h      [B*T, D]    fp32   residual stream (never rounded)    hop  [B*T, D]   16-bit copy where a GEMM reads h raw
+//   mod    [B, sum 2d] fp32   every block's AdaLN (scale|shift), one GEMM per step
+//   16-bit GEMM operands are K-major rows with a pitch that is a multiple of 8 elements, pad columns 0.
+// The channel-attention ("SA") works on h^T without ever materialising a transposed fp32 tensor: the
+// transposing LayerNorm writes the operand (B*D rows x T), and GEMM epilogues write back transposed.
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mcm_b200.h"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+namespace mcm {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+inline size_t smax(size_t a, size_t b) { return a > b ? a : b; }
+
+struct Block {
+  float *sa_ln_w, *sa_ln_b, *sa_bqkv, *sa_pn_w, *sa_pn_b, *sa_bo;
+  OpPtr sa_wqkv, sa_wo;
+  float *ca_ln_w, *ca_ln_b, *ca_bq, *ca_tn_w, *ca_tn_b, *ca_bkv, *ca_pn_w, *ca_pn_b, *ca_bo;
+  OpPtr ca_wq, ca_wkv, ca_wo;
+  OpPtr ca_ctxT;  // [B*H, hdD, hdD] step-invariant per-head context, transposed (B operand of q*ctx)
+  float *f_b1, *f_b2, *f_pn_w, *f_pn_b, *f_bo;
+  OpPtr f_w1, f_w2, f_wo;
+  int mod_off;    // [sa scale T | sa shift T | ca scale D | ca shift D | ffn scale D | ffn shift D]
+};
+
+struct Ctrl {
+  OpPtr before_w, after_w;
+  float *before_b, *after_b;
+};
+}  // namespace mcm
+
+using namespace mcm;
+
+struct mcm_ctx {
+  mcm_config cfg;
+  int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
+  bool finalized = false;
+  bool cond_ready = false;
+  int cond_batch = 0;
+  bool have_c = false;
+  std::map<std::string, std::pair<const float*, long long>> params;
+  std::vector<void*> allocs;
+
+  // packed parameters
+  std::vector<Block> blocks;      // nL base blocks followed by nC control copies
+  std::vector<Ctrl> ctrls;
+  OpPtr w_joint, w_te0, w_te2, w_mod, w_out, w_cci;
+  float *b_joint, *b_te0, *b_te2, *b_mod, *b_out, *b_cci, *seq_emb;
+
+  // workspace
+  float *h32, *f32A, *f32B, *mod32, *emb32, *xfproj32, *eps32, *x32, *cc32, *c32;
+  OpPtr opA, opB, opC, opD, hop, ctxT_sa, xop, te_op, t1_op, emb_op, cc_op, c_op;
+
+  int fmt_fast() const { return cfg.precise_all ? OP_BF16X2 : OP_F16; }
+  int fmt_prec() const { return OP_BF16X2; }
+
+  ~mcm_ctx() {
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+namespace {
+
+int dev_alloc(mcm_ctx* c, void** out, size_t bytes) {
+  void* p = nullptr;
+  bytes = smax(bytes, 256);
+  MCM_CUDA(cudaMalloc(&p, bytes));
+  MCM_CUDA(cudaMemset(p, 0, bytes));
+  c->allocs.push_back(p);
+  *out = p;
+  return 0;
+}
+int alloc_f32(mcm_ctx* c, float** out, size_t n) { return dev_alloc(c, reinterpret_cast<void**>(out), n * 4); }
+int alloc_op(mcm_ctx* c, OpPtr* o, size_t elems, int ld, bool with_lo) {
+  o->ld = ld;
+  o->lo = nullptr;
+  MCM_TRY(dev_alloc(c, &o->hi, elems * 2));
+  if (with_lo) MCM_TRY(dev_alloc(c, &o->lo, elems * 2));
+  return 0;
+}
+inline OpPtr view(const OpPtr& o, int ld) { return OpPtr{o.hi, o.lo, ld}; }
+
+int get_param(mcm_ctx* c, const std::string& name, long long numel, const float** out) {
+  auto it = c->params.find(name);
+  if (it == c->params.end()) {
+    set_error("missing parameter: " + name);
+    return 1;
+  }
+  if (it->second.second != numel) {
+    set_error("parameter " + name + " has " + std::to_string(it->second.second) + " elements, expected " + std::to_string(numel));
+    return 1;
+  }
+  *out = it->second.first;
+  return 0;
+}
+
+// copy an fp32 parameter (or a concatenation of parameters) into context-owned memory
+int own_f32(mcm_ctx* c, const std::vector<std::pair<std::string, long long>>& pieces, float** out, cudaStream_t st) {
+  long long total = 0;
+  for (auto& p : pieces) total += p.second;
+  MCM_TRY(alloc_f32(c, out, (size_t)total));
+  long long off = 0;
+  for (auto& p : pieces) {
+    const float* src;
+    MCM_TRY(get_param(c, p.first, p.second, &src));
+    MCM_CUDA(cudaMemcpyAsync(*out + off, src, (size_t)p.second * 4, cudaMemcpyDeviceToDevice, st));
+    off += p.second;
+  }
+  return 0;
+}
+
+// pack (a row-concatenation of) Linear weights [rows_i, in] into one K-major operand [sum rows, in_p]
+int pack_weight(mcm_ctx* c, const std::vector<std::pair<std::string, int>>& pieces, int in, int fmt, OpPtr* out,
+                cudaStream_t st) {
+  int rows = 0;
+  for (auto& p : pieces) rows += p.second;
+  const int in_p = rup(in, 8);
+  MCM_TRY(alloc_op(c, out, (size_t)rows * in_p, in_p, fmt == OP_BF16X2));
+  int r0 = 0;
+  for (auto& p : pieces) {
+    const float* src;
+    MCM_TRY(get_param(c, p.first, (long long)p.second * in, &src));
+    OpPtr dst{reinterpret_cast<uint16_t*>(out->hi) + (size_t)r0 * in_p,
+              out->lo ? reinterpret_cast<uint16_t*>(out->lo) + (size_t)r0 * in_p : nullptr, in_p};
+    MCM_TRY(pack_op_launch(src, p.second, in, in, false, dst, fmt, st));
+    r0 += p.second;
+  }
+  return 0;
+}
+
+EpiSeg seg_default(int n, int w_row0 = 0) {
+  EpiSeg s;
+  std::memset(&s, 0, sizeof(s));
+  s.n = n;
+  s.w_row0 = w_row0;
+  return s;
+}
+
+// shared-weight Linear over `rows` rows: out = act(A W^T + bias + addend)
+GemmProblem linear_problem(const OpPtr& a, int rows, const OpPtr& w, int w_rows, int K, int fmt) {
+  GemmProblem g;
+  std::memset(&g, 0, sizeof(g));
+  g.a = a; g.a_rows = rows; g.a_k = a.ld; g.a_batches = 1;
+  g.b = w; g.b_rows = w_rows; g.b_k = w.ld; g.b_batches = 1;
+  g.fmt = fmt;
+  g.M = rows; g.K = K; g.batches = 1; g.inner = 1;
+  g.out_rows_per_outer = rows;
+  g.nseg = 1;
+  return g;
+}
+
+int build_block(mcm_ctx* c, const std::string& pfx, Block* b, int mod_off, cudaStream_t st) {
+  const int T = c->T, D = c->D, F = c->F, L = c->L;
+  const int ff = c->fmt_fast();
+  const std::string sa = pfx + ".sa_block.", ca = pfx + ".ca_block.", fn = pfx + ".ffn_temporal.";
+  MCM_TRY(own_f32(c, {{sa + "norm.weight", T}}, &b->sa_ln_w, st));
+  MCM_TRY(own_f32(c, {{sa + "norm.bias", T}}, &b->sa_ln_b, st));
+  MCM_TRY(own_f32(c, {{sa + "query.bias", T}, {sa + "key.bias", T}, {sa + "value.bias", T}}, &b->sa_bqkv, st));
+  MCM_TRY(pack_weight(c, {{sa + "query.weight", T}, {sa + "key.weight", T}, {sa + "value.weight", T}}, T, ff, &b->sa_wqkv, st));
+  MCM_TRY(own_f32(c, {{sa + "proj_out.norm.weight", T}}, &b->sa_pn_w, st));
+  MCM_TRY(own_f32(c, {{sa + "proj_out.norm.bias", T}}, &b->sa_pn_b, st));
+  MCM_TRY(pack_weight(c, {{sa + "proj_out.out_layers.2.weight", T}}, T, ff, &b->sa_wo, st));
+  MCM_TRY(own_f32(c, {{sa + "proj_out.out_layers.2.bias", T}}, &b->sa_bo, st));
+
+  MCM_TRY(own_f32(c, {{ca + "norm.weight", D}}, &b->ca_ln_w, st));
+  MCM_TRY(own_f32(c, {{ca + "norm.bias", D}}, &b->ca_ln_b, st));
+  MCM_TRY(own_f32(c, {{ca + "text_norm.weight", L}}, &b->ca_tn_w, st));
+  MCM_TRY(own_f32(c, {{ca + "text_norm.bias", L}}, &b->ca_tn_b, st));
+  MCM_TRY(pack_weight(c, {{ca + "query.weight", D}}, D, ff, &b->ca_wq, st));
+  MCM_TRY(own_f32(c, {{ca + "query.bias", D}}, &b->ca_bq, st));
+  MCM_TRY(pack_weight(c, {{ca + "key.weight", D}, {ca + "value.weight", D}}, L, ff, &b->ca_wkv, st));
+  MCM_TRY(own_f32(c, {{ca + "key.bias", D}, {ca + "value.bias", D}}, &b->ca_bkv, st));
+  MCM_TRY(own_f32(c, {{ca + "proj_out.norm.weight", D}}, &b->ca_pn_w, st));
+  MCM_TRY(own_f32(c, {{ca + "proj_out.norm.bias", D}}, &b->ca_pn_b, st));
+  MCM_TRY(pack_weight(c, {{ca + "proj_out.out_layers.2.weight", D}}, D, ff, &b->ca_wo, st));
+  MCM_TRY(own_f32(c, {{ca + "proj_out.out_layers.2.bias", D}}, &b->ca_bo, st));
+  MCM_TRY(alloc_op(c, &b->ca_ctxT, (size_t)c->Bmax * c->H * c->hdD * c->hdD, c->hdD, ff == OP_BF16X2));
+
+  MCM_TRY(pack_weight(c, {{fn + "linear1.weight", F}}, D, ff, &b->f_w1, st));
+  MCM_TRY(own_f32(c, {{fn + "linear1.bias", F}}, &b->f_b1, st));
+  MCM_TRY(pack_weight(c, {{fn + "linear2.weight", D}}, F, ff, &b->f_w2, st));
+  MCM_TRY(own_f32(c, {{fn + "linear2.bias", D}}, &b->f_b2, st));
+  MCM_TRY(own_f32(c, {{fn + "proj_out.norm.weight", D}}, &b->f_pn_w, st));
+  MCM_TRY(own_f32(c, {{fn + "proj_out.norm.bias", D}}, &b->f_pn_b, st));
+  MCM_TRY(pack_weight(c, {{fn + "proj_out.out_layers.2.weight", D}}, D, ff, &b->f_wo, st));
+  MCM_TRY(own_f32(c, {{fn + "proj_out.out_layers.2.bias", D}}, &b->f_bo, st));
+  b->mod_off = mod_off;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one DecoderLayer (mcm.py:25-41) on the fp32 residual stream `h` [B*T, D], in place.
+// `mod` points at this block's modulation vectors (pitch mod_ld).  If hop_out_fmt >= 0 the block's
+// final GEMM also emits the 16-bit copy of the new h into c->hop in that format.
+// ---------------------------------------------------------------------------------------------
+int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int mod_ld, OpPtr final_op,
+              int final_op_fmt, cudaStream_t st) {
+  const int T = c->T, Tp = c->Tp, D = c->D, F = c->F, H = c->H, hdT = c->hdT, hdD = c->hdD;
+  const int ff = c->fmt_fast();
+  const OpPtr opA_t = view(c->opA, Tp), opC_t = view(c->opC, Tp);
+  const OpPtr opA_d = view(c->opA, D), opB_d = view(c->opB, D), opC_d = view(c->opC, D), opD_d = view(c->opD, D);
+  const OpPtr opB_f = view(c->opB, F);
+  const OpPtr hop = view(c->hop, D);
+
+  // ---- channel attention (EfficientSelfAttention on x^T, efficient_attention.py:25-46) ----
+  // xn^T = LayerNorm_T(h^T)                                   -> opA [B*D, Tp]
+  MCM_TRY(ln_transpose_launch(h, B, T, D, k.sa_ln_w, k.sa_ln_b, opA_t, ff, st));
+  {  // q | k | v = xn^T W^T + b ; q stays row-major fp32, k and v go back to the [B, T', D] layout
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opA_t; g.a_rows = D; g.a_k = Tp; g.a_batches = B;
+    g.b = k.sa_wqkv; g.b_rows = 3 * T; g.b_k = Tp; g.b_batches = 1;
+    g.fmt = ff; g.M = D; g.K = T; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = D; g.trans_rows = T;
+    g.nseg = 3;
+    g.seg[0] = seg_default(T, 0);
+    g.seg[0].bias = k.sa_bqkv; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = T;
+    g.seg[1] = seg_default(T, T);
+    g.seg[1].bias = k.sa_bqkv + T; g.seg[1].out32 = c->f32B; g.seg[1].ld32 = D; g.seg[1].flags = EPI_TRANSPOSED;
+    g.seg[2] = seg_default(T, 2 * T);
+    g.seg[2].bias = k.sa_bqkv + 2 * T; g.seg[2].op = opB_d; g.seg[2].op_fmt = ff; g.seg[2].flags = EPI_TRANSPOSED;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  // q: softmax over each head's T/H features; k: softmax over the D channel-tokens (a row in [B,T',D])
+  MCM_TRY(softmax_seg_launch(c->f32A, B * D, T, T, hdT, opC_t, ff, st));
+  MCM_TRY(softmax_seg_launch(c->f32B, B * T, D, D, D, opD_d, ff, st));
+  {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, stored transposed: ctxT[b][l][dk]
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opD_d; g.a_rows = T; g.a_k = D; g.a_batches = B;
+    g.b = opB_d; g.b_rows = T; g.b_k = D; g.b_batches = B; g.b_batched = 1;
+    g.fmt = ff; g.M = T; g.K = D; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = T; g.trans_rows = T; g.head_dim = hdT;
+    g.nseg = 1;
+    g.seg[0] = seg_default(T, 0);
+    g.seg[0].op = view(c->ctxT_sa, Tp); g.seg[0].op_fmt = ff;
+    g.seg[0].flags = EPI_TRANSPOSED | EPI_MASK_BLOCKDIAG;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  {  // y^T[b] = softmax(q) ctx                                 -> f32A [B*D, T]
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opC_t; g.a_rows = D; g.a_k = Tp; g.a_batches = B;
+    g.b = view(c->ctxT_sa, Tp); g.b_rows = T; g.b_k = Tp; g.b_batches = B; g.b_batched = 1;
+    g.fmt = ff; g.M = D; g.K = T; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = D;
+    g.nseg = 1;
+    g.seg[0] = seg_default(T, 0);
+    g.seg[0].out32 = c->f32A; g.seg[0].ld32 = T;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  // StylizationBlock over T: SiLU(LN(y) (1 + scale) + shift)    -> opA [B*D, Tp]
+  MCM_TRY(ln_rows_launch(c->f32A, B * D, T, T, k.sa_pn_w, k.sa_pn_b, mod + k.mod_off, mod + k.mod_off + T, mod_ld, D,
+                         true, opA_t, ff, st));
+  {  // h[b, t', d] += (. W_o^T + b_o)[(b,d), t']
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opA_t; g.a_rows = D; g.a_k = Tp; g.a_batches = B;
+    g.b = k.sa_wo; g.b_rows = T; g.b_k = Tp; g.b_batches = 1;
+    g.fmt = ff; g.M = D; g.K = T; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = D; g.trans_rows = T;
+    g.nseg = 1;
+    g.seg[0] = seg_default(T, 0);
+    g.seg[0].bias = k.sa_bo; g.seg[0].addend = h; g.seg[0].out32 = h; g.seg[0].ld32 = D;
+    g.seg[0].flags = EPI_TRANSPOSED;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+
+  // ---- text cross attention (EfficientCrossAttention, efficient_attention.py:64-92) ----
+  MCM_TRY(ln_rows_launch(h, B * T, D, D, k.ca_ln_w, k.ca_ln_b, nullptr, nullptr, 4, T, false, opA_d, ff, st));
+  {
+    GemmProblem g = linear_problem(opA_d, B * T, k.ca_wq, D, D, ff);
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = k.ca_bq; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = D;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  MCM_TRY(softmax_seg_launch(c->f32A, B * T, D, D, hdD, opC_d, ff, st));
+  {  // y[b, :, head] = softmax(q)[b, :, head] ctx[b, head]     (context precomputed per run)
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opC_d; g.a_rows = T; g.a_k = D; g.a_batches = B;
+    g.b = k.ca_ctxT; g.b_rows = hdD; g.b_k = hdD; g.b_batches = B * H; g.b_batched = 1;
+    g.fmt = ff; g.M = T; g.K = hdD; g.batches = B * H; g.inner = H; g.a_k_inner = hdD;
+    g.out_col_inner = hdD; g.out_rows_per_outer = T;
+    g.nseg = 1;
+    g.seg[0] = seg_default(hdD, 0);
+    g.seg[0].out32 = c->f32A; g.seg[0].ld32 = D;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  MCM_TRY(ln_rows_launch(c->f32A, B * T, D, D, k.ca_pn_w, k.ca_pn_b, mod + k.mod_off + 2 * T,
+                         mod + k.mod_off + 2 * T + D, mod_ld, T, true, opA_d, ff, st));
+  {  // h += . W_o^T + b_o ; also emit the 16-bit copy of h that linear1 reads
+    GemmProblem g = linear_problem(opA_d, B * T, k.ca_wo, D, D, ff);
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = k.ca_bo; g.seg[0].addend = h; g.seg[0].out32 = h; g.seg[0].ld32 = D;
+    g.seg[0].op = hop; g.seg[0].op_fmt = ff;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+
+  // ---- FFN (diffusion_transformer.py:25-28) ----
+  {
+    GemmProblem g = linear_problem(hop, B * T, k.f_w1, F, D, ff);
+    g.seg[0] = seg_default(F, 0);
+    g.seg[0].bias = k.f_b1; g.seg[0].flags = EPI_GELU; g.seg[0].op = opB_f; g.seg[0].op_fmt = ff;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  {
+    GemmProblem g = linear_problem(opB_f, B * T, k.f_w2, D, F, ff);
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = k.f_b2; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = D;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  MCM_TRY(ln_rows_launch(c->f32A, B * T, D, D, k.f_pn_w, k.f_pn_b, mod + k.mod_off + 2 * T + 2 * D,
+                         mod + k.mod_off + 2 * T + 3 * D, mod_ld, T, true, opA_d, ff, st));
+  {
+    GemmProblem g = linear_problem(opA_d, B * T, k.f_wo, D, D, ff);
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = k.f_bo; g.seg[0].addend = h; g.seg[0].out32 = h; g.seg[0].ld32 = D;
+    if (final_op.hi) { g.seg[0].op = final_op; g.seg[0].op_fmt = final_op_fmt; }
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  return 0;
+}
+
+// AdaLN modulation vectors of blocks [blk0, blk0 + nblk) from emb [B, E] (fp32): one GEMM
+//   mod[b, :] = SiLU(emb[b]) W_mod^T + b_mod          (StylizationBlock.emb_layers, stylization_block.py:17-20,35)
+int run_mod(mcm_ctx* c, int B, const float* emb, int blk0, int nblk, cudaStream_t st) {
+  const int per = 2 * c->T + 4 * c->D;
+  MCM_TRY(pack_op_launch(emb, B, c->E, c->E, true, c->emb_op, c->fmt_prec(), st));
+  GemmProblem g = linear_problem(c->emb_op, B, c->w_mod, c->mod_total, c->E, c->fmt_prec());
+  g.seg[0] = seg_default(nblk * per, blk0 * per);
+  g.seg[0].bias = c->b_mod + (size_t)blk0 * per;
+  g.seg[0].out32 = c->mod32; g.seg[0].ld32 = c->mod_total; g.seg[0].col0 = blk0 * per;
+  return gemm_tc_launch(g, st);
+}
+
+int check_batch(mcm_ctx* c, int B) {
+  MCM_CHECK(c != nullptr, "null context");
+  MCM_CHECK(c->finalized, "mcm_finalize_params has not been called");
+  MCM_CHECK(B >= 1 && B <= c->Bmax, "batch exceeds max_batch of the context");
+  return 0;
+}
+
+// the whole denoiser on x32/xop already in place: writes eps32
+int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float* eps_out, cudaStream_t st) {
+  const int T = c->T, D = c->D, E = c->E, IN = c->IN;
+  const int fp = c->fmt_prec();
+  MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first (for at least this batch)");
+  // emb = time_embed(sinusoid(t)) + xf_proj                      (diffusion_transformer.py:206-213)
+  MCM_TRY(timestep_embedding_launch(t_dev, t_uniform, B, D, c->te_op, fp, st));
+  {
+    GemmProblem g = linear_problem(c->te_op, B, c->w_te0, E, D, fp);
+    g.seg[0] = seg_default(E, 0);
+    g.seg[0].bias = c->b_te0; g.seg[0].flags = EPI_SILU; g.seg[0].op = c->t1_op; g.seg[0].op_fmt = fp;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  {
+    GemmProblem g = linear_problem(c->t1_op, B, c->w_te2, E, E, fp);
+    g.seg[0] = seg_default(E, 0);
+    g.seg[0].bias = c->b_te2; g.seg[0].addend = c->xfproj32; g.seg[0].out32 = c->emb32; g.seg[0].ld32 = E;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  MCM_TRY(run_mod(c, B, c->emb32, 0, (int)c->blocks.size(), st));
+  {  // h = joint_embed(x) + sequence_embedding[:T]               (:215-218)
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = c->xop; g.a_rows = T; g.a_k = c->INp; g.a_batches = B;
+    g.b = c->w_joint; g.b_rows = D; g.b_k = c->INp; g.b_batches = 1;
+    g.fmt = fp; g.M = T; g.K = IN; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = T;
+    g.nseg = 1;
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = c->b_joint; g.seg[0].addend = c->seq_emb; g.seg[0].flags = EPI_ADDEND_BCAST;
+    g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  const OpPtr none{nullptr, nullptr, 0};
+  const OpPtr hop_out = view(c->hop, D);
+  const int nL = c->nL, nC = (c->have_c ? c->nC : 0);
+  const float* mod = c->mod32;
+  const int mld = c->mod_total;
+  // MCMTransformer.forward_test (mcm.py:93-102) / ControlT2MHalf_MCM.forward_test (controlnet_mcm.py:306-361)
+  MCM_TRY(run_block(c, c->blocks[0], B, c->h32, mod, mld, (nL == 1) ? hop_out : none, fp, st));
+  for (int i = 1; i < nL; ++i) {
+    if (i <= nC) {
+      const int j = i - 1;
+      const Block& cb = c->blocks[nL + j];
+      const Ctrl& ct = c->ctrls[j];
+      if (j == 0) {  // c = copied_block(x = h + before_proj(c))      (controlnet_mcm.py:65-75)
+        GemmProblem g = linear_problem(view(c->cc_op, D), B * T, ct.before_w, D, D, c->fmt_fast());
+        g.seg[0] = seg_default(D, 0);
+        g.seg[0].bias = ct.before_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->c32; g.seg[0].ld32 = D;
+        MCM_TRY(gemm_tc_launch(g, st));
+      }
+      MCM_TRY(run_block(c, cb, B, c->c32, mod, mld, view(c->c_op, D), c->fmt_fast(), st));
+      {  // h = h + after_proj(c)                                       (:75,85 ; :341-349)
+        GemmProblem g = linear_problem(view(c->c_op, D), B * T, ct.after_w, D, D, c->fmt_fast());
+        g.seg[0] = seg_default(D, 0);
+        g.seg[0].bias = ct.after_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
+        MCM_TRY(gemm_tc_launch(g, st));
+      }
+    }
+    MCM_TRY(run_block(c, c->blocks[i], B, c->h32, mod, mld, (i == nL - 1) ? hop_out : none, fp, st));
+  }
+  {  // eps = out(h)                                                (mcm.py:102)
+    GemmProblem g = linear_problem(hop_out, B * T, c->w_out, IN, D, fp);
+    g.seg[0] = seg_default(IN, 0);
+    g.seg[0].bias = c->b_out; g.seg[0].out32 = eps_out; g.seg[0].ld32 = IN;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  return 0;
+}
+
+int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const float* step_noise, float* x_io, cudaStream_t st) {
+  const size_t rows = (size_t)B * c->T;
+  const size_t n = rows * c->IN;
+  // x_io holds x_T on entry and x_0 on exit; xop must already hold the operand copy of x_T
+  for (int i = s->n_steps - 1; i >= 0; --i) {
+    MCM_TRY(run_denoiser(c, B, nullptr, s->timestep_map[i], c->eps32, st));
+    const float* noise = step_noise ? step_noise + (size_t)i * n : nullptr;
+    if (s->mode == 0) {
+      DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
+                  s->alphas_cumprod_prev[i], s->eta, (s->eta != 0.f && i != 0) ? 1 : 0};
+      MCM_TRY(ddim_update_launch(x_io, c->eps32, noise, x_io, rows, c->IN, k, c->xop, c->fmt_prec(), st));
+    } else {
+      DdpmCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->posterior_mean_coef1[i],
+                  s->posterior_mean_coef2[i], s->posterior_log_variance_clipped[i], i != 0 ? 1 : 0};
+      MCM_TRY(ddpm_update_launch(x_io, c->eps32, noise, x_io, rows, c->IN, k, c->xop, c->fmt_prec(), st));
+    }
+  }
+  return 0;
+}
+
+int check_sampler(const mcm_sampler* s, const float* step_noise) {
+  MCM_CHECK(s != nullptr && s->n_steps > 0 && s->timestep_map != nullptr, "bad sampler description");
+  MCM_CHECK(s->mode == 0 || s->mode == 1, "sampler mode must be 0 (DDIM) or 1 (DDPM)");
+  MCM_CHECK(s->sqrt_recip_alphas_cumprod && s->sqrt_recipm1_alphas_cumprod, "missing sampler tables");
+  if (s->mode == 0) {
+    MCM_CHECK(s->alphas_cumprod && s->alphas_cumprod_prev, "DDIM needs alphas_cumprod(_prev)");
+    MCM_CHECK(s->eta == 0.f || step_noise != nullptr, "DDIM with eta != 0 needs step noise");
+  } else {
+    MCM_CHECK(s->posterior_mean_coef1 && s->posterior_mean_coef2 && s->posterior_log_variance_clipped, "DDPM needs posterior tables");
+    MCM_CHECK(step_noise != nullptr || s->n_steps == 1, "DDPM needs step noise");
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+const char* mcm_last_error(void) { return g_last_error.c_str(); }
+const char* mcm_version(void) { return "motioncraft_b200 0.1.0 (sm_100a, tcgen05)"; }
+unsigned long long mcm_gemm_launches(void) { return gemm_tc_launch_count(); }
+unsigned long long mcm_kernel_launches(void) { return gemm_tc_launch_count() + elementwise_launch_count(); }
+
+int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
+  MCM_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  MCM_TRY(gemm_tc_init());
+  MCM_TRY(elementwise_init());
+  MCM_CHECK(cfg->seq_len % cfg->num_heads == 0 && cfg->latent_dim % cfg->num_heads == 0, "heads must divide seq_len and latent_dim");
+  MCM_CHECK(cfg->seq_len % 4 == 0 && cfg->seq_len <= 1024, "seq_len must be a multiple of 4 and <= 1024");
+  MCM_CHECK(cfg->latent_dim % 32 == 0 && cfg->latent_dim <= 1024, "latent_dim must be a multiple of 32 and <= 1024");
+  MCM_CHECK(cfg->text_latent_dim % 8 == 0 && cfg->text_latent_dim <= 1024, "text_latent_dim must be a multiple of 8");
+  MCM_CHECK(cfg->time_embed_dim % 8 == 0 && cfg->ffn_dim % 8 == 0, "time_embed_dim / ffn_dim must be multiples of 8");
+  MCM_CHECK((cfg->latent_dim / cfg->num_heads) % 8 == 0, "latent head dim must be a multiple of 8");
+  MCM_CHECK(cfg->max_batch >= 1 && cfg->num_layers >= 1 && cfg->num_ctrl_blocks >= 0 && cfg->num_ctrl_blocks < cfg->num_layers, "bad sizes");
+  mcm_ctx* c = new mcm_ctx();
+  c->cfg = *cfg;
+  c->T = cfg->seq_len; c->Tp = rup(c->T, 8); c->D = cfg->latent_dim; c->E = cfg->time_embed_dim; c->F = cfg->ffn_dim;
+  c->L = cfg->text_latent_dim; c->H = cfg->num_heads; c->IN = cfg->input_feats; c->INp = rup(c->IN, 8);
+  c->NTmax = cfg->max_text_tokens > 0 ? cfg->max_text_tokens : 77; c->NTp = rup(c->NTmax, 8);
+  c->nL = cfg->num_layers; c->nC = cfg->num_ctrl_blocks; c->Cin = cfg->ctrl_cond_feats; c->Cinp = rup(c->Cin > 0 ? c->Cin : 8, 8);
+  c->hdT = c->T / c->H; c->hdD = c->D / c->H; c->Bmax = cfg->max_batch;
+  c->mod_total = (c->nL + c->nC) * (2 * c->T + 4 * c->D);
+
+  const size_t B = c->Bmax, R1 = B * c->T, R2 = B * c->D;
+  const bool lo = cfg->precise_all != 0;
+  auto fail = [&](int) { delete c; return 1; };
+  size_t szA = smax(smax(R2 * c->Tp, R1 * c->D), smax(B * c->NTmax * c->L, R2 * c->NTp));
+  size_t szB = smax(smax(R1 * c->D, R1 * c->F), R2 * c->NTp);
+  if (c->nC > 0) szB = smax(szB, R1 * c->Cinp);
+  size_t szC = smax(smax(R2 * c->Tp, R1 * c->D), R2 * c->NTp);
+  if (alloc_f32(c, &c->h32, R1 * c->D)) return fail(0);
+  if (alloc_f32(c, &c->f32A, smax(smax(R2 * c->T, R1 * c->D), R2 * c->NTp))) return fail(0);
+  if (alloc_f32(c, &c->f32B, R1 * c->D)) return fail(0);
+  if (alloc_f32(c, &c->mod32, B * c->mod_total)) return fail(0);
+  if (alloc_f32(c, &c->emb32, B * c->E)) return fail(0);
+  if (alloc_f32(c, &c->xfproj32, B * c->E)) return fail(0);
+  if (alloc_f32(c, &c->eps32, R1 * c->IN)) return fail(0);
+  if (alloc_f32(c, &c->x32, R1 * c->IN)) return fail(0);
+  if (alloc_op(c, &c->opA, szA, 8, lo)) return fail(0);
+  if (alloc_op(c, &c->opB, szB, 8, true)) return fail(0);      // lo: also stages the bf16x2 control condition
+  if (alloc_op(c, &c->opC, szC, 8, lo)) return fail(0);
+  if (alloc_op(c, &c->opD, R1 * c->D, 8, lo)) return fail(0);
+  if (alloc_op(c, &c->hop, R1 * c->D, c->D, true)) return fail(0);
+  if (alloc_op(c, &c->ctxT_sa, B * c->T * c->Tp, c->Tp, lo)) return fail(0);
+  if (alloc_op(c, &c->xop, R1 * c->INp, c->INp, true)) return fail(0);
+  if (alloc_op(c, &c->te_op, B * c->D, c->D, true)) return fail(0);
+  if (alloc_op(c, &c->t1_op, B * c->E, c->E, true)) return fail(0);
+  if (alloc_op(c, &c->emb_op, B * c->E, c->E, true)) return fail(0);
+  if (c->nC > 0) {
+    if (alloc_f32(c, &c->cc32, R1 * c->D)) return fail(0);
+    if (alloc_f32(c, &c->c32, R1 * c->D)) return fail(0);
+    if (alloc_op(c, &c->cc_op, R1 * c->D, c->D, lo)) return fail(0);
+    if (alloc_op(c, &c->c_op, R1 * c->D, c->D, lo)) return fail(0);
+  }
+  *out = c;
+  return 0;
+}
+
+void mcm_destroy(mcm_ctx* ctx) { delete ctx; }
+
+int mcm_set_param(mcm_ctx* ctx, const char* name, const float* dev_ptr, long long numel) {
+  MCM_CHECK(ctx && name && dev_ptr && numel > 0, "bad argument");
+  ctx->params[name] = {dev_ptr, numel};
+  return 0;
+}
+
+int mcm_finalize_params(mcm_ctx* c, void* stream) {
+  MCM_CHECK(c != nullptr, "null context");
+  MCM_CHECK(!c->finalized, "parameters were already finalized (create a new context to reload weights)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int T = c->T, D = c->D, E = c->E, IN = c->IN;
+  const int fp = c->fmt_prec();
+  MCM_TRY(pack_weight(c, {{"joint_embed.weight", D}}, IN, fp, &c->w_joint, st));
+  MCM_TRY(own_f32(c, {{"joint_embed.bias", D}}, &c->b_joint, st));
+  MCM_TRY(pack_weight(c, {{"time_embed.0.weight", E}}, D, fp, &c->w_te0, st));
+  MCM_TRY(own_f32(c, {{"time_embed.0.bias", E}}, &c->b_te0, st));
+  MCM_TRY(pack_weight(c, {{"time_embed.2.weight", E}}, E, fp, &c->w_te2, st));
+  MCM_TRY(own_f32(c, {{"time_embed.2.bias", E}}, &c->b_te2, st));
+  MCM_TRY(pack_weight(c, {{"out.weight", IN}}, D, fp, &c->w_out, st));
+  MCM_TRY(own_f32(c, {{"out.bias", IN}}, &c->b_out, st));
+  MCM_TRY(own_f32(c, {{"sequence_embedding", (long long)T * D}}, &c->seq_emb, st));
+
+  const int per = 2 * T + 4 * D;
+  c->blocks.resize(c->nL + c->nC);
+  std::vector<std::pair<std::string, int>> mod_w;
+  std::vector<std::pair<std::string, long long>> mod_b;
+  for (int i = 0; i < c->nL + c->nC; ++i) {
+    const std::string pfx = i < c->nL ? "temporal_decoder_blocks." + std::to_string(i)
+                                      : "controlnet." + std::to_string(i - c->nL) + ".copied_block";
+    MCM_TRY(build_block(c, pfx, &c->blocks[i], i * per, st));
+    mod_w.push_back({pfx + ".sa_block.proj_out.emb_layers.1.weight", 2 * T});
+    mod_w.push_back({pfx + ".ca_block.proj_out.emb_layers.1.weight", 2 * D});
+    mod_w.push_back({pfx + ".ffn_temporal.proj_out.emb_layers.1.weight", 2 * D});
+    mod_b.push_back({pfx + ".sa_block.proj_out.emb_layers.1.bias", 2 * T});
+    mod_b.push_back({pfx + ".ca_block.proj_out.emb_layers.1.bias", 2 * D});
+    mod_b.push_back({pfx + ".ffn_temporal.proj_out.emb_layers.1.bias", 2 * D});
+  }
+  MCM_TRY(pack_weight(c, mod_w, E, fp, &c->w_mod, st));
+  MCM_TRY(own_f32(c, mod_b, &c->b_mod, st));
+  c->ctrls.resize(c->nC);
+  for (int j = 0; j < c->nC; ++j) {
+    const std::string pfx = "controlnet." + std::to_string(j);
+    Ctrl& ct = c->ctrls[j];
+    ct.before_w = OpPtr{nullptr, nullptr, 0};
+    ct.before_b = nullptr;
+    if (j == 0) {
+      MCM_TRY(pack_weight(c, {{pfx + ".before_proj.weight", D}}, D, c->fmt_fast(), &ct.before_w, st));
+      MCM_TRY(own_f32(c, {{pfx + ".before_proj.bias", D}}, &ct.before_b, st));
+    }
+    MCM_TRY(pack_weight(c, {{pfx + ".after_proj.weight", D}}, D, c->fmt_fast(), &ct.after_w, st));
+    MCM_TRY(own_f32(c, {{pfx + ".after_proj.bias", D}}, &ct.after_b, st));
+  }
+  if (c->nC > 0) {
+    MCM_TRY(pack_weight(c, {{"control_cond_input.weight", D}}, c->Cin, fp, &c->w_cci, st));
+    MCM_TRY(own_f32(c, {{"control_cond_input.bias", D}}, &c->b_cci, st));
+  }
+  MCM_CUDA(cudaStreamSynchronize(st));
+  c->params.clear();   // borrowed pointers are not used after this point
+  c->finalized = true;
+  return 0;
+}
+
+int mcm_prepare_conditions(mcm_ctx* c, int B, const float* xf_out, int n_tokens, const float* xf_proj, const float* cond,
+                           int c_len, void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_CHECK(xf_out && xf_proj, "xf_out / xf_proj are required (the text encoder stays outside this library)");
+  MCM_CHECK(n_tokens >= 1 && n_tokens <= c->NTmax, "n_tokens exceeds max_text_tokens");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = c->D, L = c->L, H = c->H, hdD = c->hdD, T = c->T;
+  const int N = n_tokens, Np = rup(N, 8);
+  const int ff = c->fmt_fast();
+  MCM_CUDA(cudaMemcpyAsync(c->xfproj32, xf_proj, (size_t)B * c->E * 4, cudaMemcpyDeviceToDevice, st));
+  for (size_t i = 0; i < c->blocks.size(); ++i) {
+    const Block& k = c->blocks[i];
+    const OpPtr xfn = view(c->opA, L), vT = view(c->opB, Np), pT = view(c->opC, Np);
+    // LN_L(xf) -> [B*N, L]
+    MCM_TRY(ln_rows_launch(xf_out, B * N, L, L, k.ca_tn_w, k.ca_tn_b, nullptr, nullptr, 4, N, false, xfn, ff, st));
+    {  // key | value = LN(xf) W^T + b, both written transposed: [B, D, Np] (tokens contiguous)
+      GemmProblem g;
+      std::memset(&g, 0, sizeof(g));
+      g.a = xfn; g.a_rows = N; g.a_k = L; g.a_batches = B;
+      g.b = k.ca_wkv; g.b_rows = 2 * D; g.b_k = L; g.b_batches = 1;
+      g.fmt = ff; g.M = N; g.K = L; g.batches = B; g.inner = 1;
+      g.out_rows_per_outer = N; g.trans_rows = D;
+      g.nseg = 2;
+      g.seg[0] = seg_default(D, 0);
+      g.seg[0].bias = k.ca_bkv; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = Np; g.seg[0].flags = EPI_TRANSPOSED;
+      g.seg[1] = seg_default(D, D);
+      g.seg[1].bias = k.ca_bkv + D; g.seg[1].op = vT; g.seg[1].op_fmt = ff; g.seg[1].flags = EPI_TRANSPOSED;
+      MCM_TRY(gemm_tc_launch(g, st));
+    }
+    // softmax over the N text tokens (dim=1 of [B, N, H, hd], efficient_attention.py:78)
+    MCM_TRY(softmax_seg_launch(c->f32A, B * D, N, Np, N, pT, ff, st));
+    {  // ctx[b, h] = softmax(key)_h^T value_h  (hd x hd), stored transposed for the per-step q * ctx GEMM
+      GemmProblem g;
+      std::memset(&g, 0, sizeof(g));
+      g.a = pT; g.a_rows = hdD; g.a_k = Np; g.a_batches = B * H;
+      g.b = vT; g.b_rows = hdD; g.b_k = Np; g.b_batches = B * H; g.b_batched = 1;
+      g.fmt = ff; g.M = hdD; g.K = N; g.batches = B * H; g.inner = 1;
+      g.out_rows_per_outer = hdD; g.trans_rows = hdD;
+      g.nseg = 1;
+      g.seg[0] = seg_default(hdD, 0);
+      g.seg[0].op = k.ca_ctxT; g.seg[0].op_fmt = ff; g.seg[0].flags = EPI_TRANSPOSED;
+      MCM_TRY(gemm_tc_launch(g, st));
+    }
+  }
+  c->have_c = false;
+  if (cond != nullptr) {
+    MCM_CHECK(c->nC > 0, "a control condition was given but the context has no control blocks");
+    MCM_CHECK(c_len >= 1 && c_len <= T, "control condition longer than seq_len");
+    // forward_c (controlnet_mcm.py:155-166): control_cond_input(c), zero-pad to T, + sequence_embedding[:len_c]
+    const int fp = c->fmt_prec();
+    const OpPtr cin = view(c->opB, c->Cinp);
+    MCM_TRY(pack_op_launch(cond, B * c_len, c->Cin, c->Cin, false, cin, fp, st));
+    MCM_CUDA(cudaMemsetAsync(c->cc32, 0, (size_t)B * T * D * 4, st));
+    MCM_CUDA(cudaMemsetAsync(c->cc_op.hi, 0, (size_t)B * T * D * 2, st));
+    if (c->cc_op.lo) MCM_CUDA(cudaMemsetAsync(c->cc_op.lo, 0, (size_t)B * T * D * 2, st));
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = cin; g.a_rows = c_len; g.a_k = c->Cinp; g.a_batches = B;
+    g.b = c->w_cci; g.b_rows = D; g.b_k = c->Cinp; g.b_batches = 1;
+    g.fmt = fp; g.M = c_len; g.K = c->Cin; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = T;
+    g.nseg = 1;
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = c->b_cci; g.seg[0].addend = c->seq_emb; g.seg[0].flags = EPI_ADDEND_BCAST;
+    g.seg[0].out32 = c->cc32; g.seg[0].ld32 = D;
+    g.seg[0].op = view(c->cc_op, D); g.seg[0].op_fmt = c->fmt_fast();
+    MCM_TRY(gemm_tc_launch(g, st));
+    c->have_c = true;
+  }
+  c->cond_ready = true;
+  c->cond_batch = B;
+  return 0;
+}
+
+int mcm_denoise(mcm_ctx* c, int B, const float* x, const long long* timesteps, int t_uniform, float* eps_out,
+                void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_CHECK(x && eps_out, "null tensor");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MCM_TRY(pack_op_launch(x, B * c->T, c->IN, c->IN, false, c->xop, c->fmt_prec(), st));
+  return run_denoiser(c, B, timesteps, t_uniform, eps_out, st);
+}
+
+int mcm_block_forward(mcm_ctx* c, int kind, int index, int B, float* x_inout, const float* emb, void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_CHECK(x_inout && emb, "null tensor");
+  MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first");
+  MCM_CHECK((kind == 0 && index >= 0 && index < c->nL) || (kind == 1 && index >= 0 && index < c->nC), "no such block");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int bi = kind == 0 ? index : c->nL + index;
+  MCM_TRY(run_mod(c, B, emb, bi, 1, st));
+  const OpPtr none{nullptr, nullptr, 0};
+  return run_block(c, c->blocks[bi], B, x_inout, c->mod32, c->mod_total, none, 0, st);
+}
+
+int mcm_sample(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T, const float* step_noise, float* x0_out,
+               void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_TRY(check_sampler(s, step_noise));
+  MCM_CHECK(x_T && x0_out, "null tensor");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * c->T * c->IN;
+  if (x0_out != x_T) MCM_CUDA(cudaMemcpyAsync(x0_out, x_T, n * 4, cudaMemcpyDeviceToDevice, st));
+  MCM_TRY(pack_op_launch(x0_out, B * c->T, c->IN, c->IN, false, c->xop, c->fmt_prec(), st));
+  return run_sampler(c, s, B, step_noise, x0_out, st);
+}
+
+int mcm_sample_host(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T_host, const float* step_noise_host,
+                    float* x0_out_host, void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_CHECK(x_T_host && x0_out_host, "null tensor");
+  MCM_CHECK(step_noise_host == nullptr, "mcm_sample_host: per-step noise must be staged on the device (use mcm_sample)");
+  MCM_TRY(check_sampler(s, nullptr));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * c->T * c->IN;
+  MCM_CUDA(cudaMemcpyAsync(c->x32, x_T_host, n * 4, cudaMemcpyHostToDevice, st));
+  MCM_TRY(pack_op_launch(c->x32, B * c->T, c->IN, c->IN, false, c->xop, c->fmt_prec(), st));
+  MCM_TRY(run_sampler(c, s, B, nullptr, c->x32, st));
+  MCM_CUDA(cudaMemcpyAsync(x0_out_host, c->x32, n * 4, cudaMemcpyDeviceToHost, st));
+  MCM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const float* bias, float* C, int fmt,
+                    void* stream) {
+  MCM_CHECK(M > 0 && N > 0 && K > 0 && A && W && C, "bad argument");
+  MCM_CHECK(fmt == OP_F16 || fmt == OP_BF16X2, "fmt must be 0 (fp16) or 1 (bf16x2)");
+  MCM_TRY(gemm_tc_init());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int Kp = rup(K, 8);
+  void *ah = nullptr, *al = nullptr, *wh = nullptr, *wl = nullptr;
+  MCM_CUDA(cudaMalloc(&ah, (size_t)M * Kp * 2));
+  MCM_CUDA(cudaMalloc(&al, (size_t)M * Kp * 2));
+  MCM_CUDA(cudaMalloc(&wh, (size_t)N * Kp * 2));
+  MCM_CUDA(cudaMalloc(&wl, (size_t)N * Kp * 2));
+  OpPtr a{ah, al, Kp}, w{wh, wl, Kp};
+  int rc = pack_op_launch(A, M, K, K, false, a, fmt, st);
+  if (!rc) rc = pack_op_launch(W, N, K, K, false, w, fmt, st);
+  if (!rc) {
+    GemmProblem g = linear_problem(a, M, w, N, K, fmt);
+    g.seg[0] = seg_default(N, 0);
+    g.seg[0].bias = bias; g.seg[0].out32 = C; g.seg[0].ld32 = N;
+    rc = gemm_tc_launch(g, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+  if (!rc && e != cudaSuccess) {
+    set_error(std::string("mcm_test_linear: ") + cudaGetErrorString(e));
+    rc = 1;
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// motioncraft_b200 -- row kernels (see elementwise.cuh).  One warp per row, float4 loads, warp-shuffle
+// reductions, 8-byte packed 16-bit stores; the transposing LayerNorm stages a [T x 32] tile in shared
+// memory so both its reads (along d) and its writes (along t) are coalesced.
+#include "elementwise.cuh"
+
+#include <atomic>
+
+namespace mcm {
+namespace {
+std::atomic<unsigned long long> g_ew_launches{0};
+constexpr int MAXV = 8;   // float4 per lane -> rows of up to 1024 elements
+
+__device__ __forceinline__ void op_store4(const OpPtr& o, int fmt, size_t idx, float a, float b, float c, float d) {
+  if (fmt == OP_F16) {
+    uint2 w;
+    w.x = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(b) << 16);
+    w.y = (uint32_t)f32_to_f16_bits(c) | ((uint32_t)f32_to_f16_bits(d) << 16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.hi) + idx) = w;
+  } else {
+    uint16_t h[4], l[4];
+    f32_to_bf16x2_bits(a, h[0], l[0]);
+    f32_to_bf16x2_bits(b, h[1], l[1]);
+    f32_to_bf16x2_bits(c, h[2], l[2]);
+    f32_to_bf16x2_bits(d, h[3], l[3]);
+    uint2 wh, wl;
+    wh.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+    wh.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+    wl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
+    wl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.hi) + idx) = wh;
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.lo) + idx) = wl;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ln_rows
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const float* __restrict__ w,
+               const float* __restrict__ b, const float* __restrict__ scale, const float* __restrict__ shift,
+               int mod_ld, int rows_per_batch, int act_silu, OpPtr out, int out_fmt) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = in + (size_t)row * ld_in;
+  const int nv = d >> 2;                       // float4 count (d % 4 == 0)
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = i * 32 + lane;
+    if (q < nv) {
+      v[i] = *reinterpret_cast<const float4*>(x + 4 * q);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = i * 32 + lane;
+    if (q < nv) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      ss += (a * a + bb * bb) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)d + 1e-5f);
+  const int batch = row / rows_per_batch;
+  const float* sc = scale ? scale + (size_t)batch * mod_ld : nullptr;
+  const float* sh = shift ? shift + (size_t)batch * mod_ld : nullptr;
+  const int nvo = out.ld >> 2;
+  const size_t obase = (size_t)row * out.ld;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = i * 32 + lane;
+    if (q < nv) {
+      const float4 ww = *reinterpret_cast<const float4*>(w + 4 * q);
+      const float4 bb = *reinterpret_cast<const float4*>(b + 4 * q);
+      float y[4] = {(v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y,
+                    (v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w};
+      if (sc) {
+        const float4 s4 = *reinterpret_cast<const float4*>(sc + 4 * q);
+        const float4 h4 = *reinterpret_cast<const float4*>(sh + 4 * q);
+        y[0] = y[0] * (1.f + s4.x) + h4.x;
+        y[1] = y[1] * (1.f + s4.y) + h4.y;
+        y[2] = y[2] * (1.f + s4.z) + h4.z;
+        y[3] = y[3] * (1.f + s4.w) + h4.w;
+      }
+      if (act_silu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = silu(y[j]);
+      }
+      op_store4(out, out_fmt, obase + 4 * q, y[0], y[1], y[2], y[3]);
+    } else if (q < nvo) {
+      op_store4(out, out_fmt, obase + 4 * q, 0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ softmax_seg
+// one warp per (row, segment); seg <= 32 * MAXE
+constexpr int MAXE = 32;
+__global__ void __launch_bounds__(256)
+softmax_seg_kernel(const float* __restrict__ in, int rows, int ncols, int ld_in, int seg, int nseg, OpPtr out,
+                   int out_fmt) {
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)rows * nseg) return;
+  const int row = (int)(gw / nseg);
+  const int sidx = (int)(gw - (long long)row * nseg);
+  const float* x = in + (size_t)row * ld_in + (size_t)sidx * seg;
+  float v[MAXE];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < seg) ? x[c] : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < seg) ? expf(v[i] - m) : 0.f;
+    s += v[i];
+  }
+  const float inv = 1.f / warp_sum(s);
+  const size_t obase = (size_t)row * out.ld + (size_t)sidx * seg;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = i * 32 + lane;
+    if (c < seg) op_store1(out, out_fmt, obase + c, v[i] * inv);
+  }
+  if (sidx == nseg - 1) {
+    for (int c = ncols + lane; c < out.ld; c += 32) op_store1(out, out_fmt, (size_t)row * out.ld + c, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ln_transpose
+// grid (D/32, B), block (32, 8).  tile[t][dx] (+1 pad) holds h[b, t, d0 + dx].
+__global__ void __launch_bounds__(256)
+ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __restrict__ w,
+                    const float* __restrict__ b, OpPtr out, int out_fmt) {
+  extern __shared__ float tile[];            // T * 33
+  __shared__ float red[8][33];
+  __shared__ float mean_s[32], rstd_s[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int d0 = blockIdx.x * 32;
+  const int bidx = blockIdx.y;
+  const float* src = h + (size_t)bidx * T * D + d0;
+  float s = 0.f;
+  for (int t = ty; t < T; t += 8) {
+    const float val = src[(size_t)t * D + tx];
+    tile[t * 33 + tx] = val;
+    s += val;
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][tx];
+    mean_s[tx] = tot / (float)T;
+  }
+  __syncthreads();
+  const float mean = mean_s[tx];
+  float ss = 0.f;
+  for (int t = ty; t < T; t += 8) {
+    const float dlt = tile[t * 33 + tx] - mean;
+    ss += dlt * dlt;
+  }
+  red[ty][tx] = ss;
+  __syncthreads();
+  if (ty == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][tx];
+    rstd_s[tx] = rsqrtf(tot / (float)T + 1e-5f);
+  }
+  __syncthreads();
+  // write: warp ty handles columns dl = ty, ty+8, ...; lanes run along t (contiguous in the output)
+  for (int dl = ty; dl < 32; dl += 8) {
+    const float mu = mean_s[dl], rs = rstd_s[dl];
+    const size_t obase = ((size_t)bidx * D + d0 + dl) * out.ld;
+    for (int t = tx; t < out.ld; t += 32) {
+      const float y = (t < T) ? (tile[t * 33 + dl] - mu) * rs * w[t] + b[t] : 0.f;
+      op_store1(out, out_fmt, obase + t, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ pack_op
+__global__ void __launch_bounds__(256)
+pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, int act_silu, OpPtr out, int out_fmt) {
+  const size_t total = rows * (size_t)out.ld;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / out.ld;
+    const int c = (int)(i - r * out.ld);
+    float v = 0.f;
+    if (c < cols) {
+      v = in[r * ld_in + c];
+      if (act_silu) v = silu(v);
+    }
+    op_store1(out, out_fmt, i, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ timestep embedding
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t_dev, int t_uniform, int B, int dim,
+                                          OpPtr out, int out_fmt) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * out.ld) return;
+  const int bidx = i / out.ld;
+  const int c = i - bidx * out.ld;
+  float v = 0.f;
+  if (c < 2 * half) {
+    const float t = (float)(t_dev ? t_dev[bidx] : (long long)t_uniform);
+    const int k = c < half ? c : c - half;
+    // freqs = exp(-ln(1e4) * k / half) in fp32, exactly as position_encoding.py:53-55
+    const float freq = expf(-9.210340371976184f * (float)k / (float)half);
+    const float arg = t * freq;
+    v = c < half ? cosf(arg) : sinf(arg);
+  }
+  op_store1(out, out_fmt, (size_t)i, v);
+}
+
+// ------------------------------------------------------------------------------------------ sampler updates
+__global__ void __launch_bounds__(256)
+ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_model, const float* __restrict__ noise,
+                   float* __restrict__ x_out, size_t rows, int cols, DdimCoefs k, OpPtr xop, int op_fmt) {
+  // gaussian_diffusion.py:572-577 (x0 from eps), :587-591 (eps re-derived), :839-852 (Equation 12);
+  // same fp32 operation order as the reference, no fused multiply-adds
+  const float one_m_abp = __fsub_rn(1.f, k.alpha_bar_prev);
+  const float sigma = __fmul_rn(__fmul_rn(k.eta, sqrtf(__fdiv_rn(one_m_abp, __fsub_rn(1.f, k.alpha_bar)))),
+                                sqrtf(__fsub_rn(1.f, __fdiv_rn(k.alpha_bar, k.alpha_bar_prev))));
+  const float s_abp = sqrtf(k.alpha_bar_prev);
+  const float s_dir = sqrtf(__fsub_rn(one_m_abp, __fmul_rn(sigma, sigma)));
+  const int ldo = xop.hi ? xop.ld : cols;
+  const size_t total = rows * (size_t)ldo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ldo;
+    const int c = (int)(i - r * ldo);
+    float xn = 0.f;
+    if (c < cols) {
+      const size_t j = r * cols + c;
+      const float c1x = __fmul_rn(k.c1, x[j]);
+      const float x0 = __fsub_rn(c1x, __fmul_rn(k.c2, eps_model[j]));
+      const float eps = __fdiv_rn(__fsub_rn(c1x, x0), k.c2);
+      xn = __fadd_rn(__fmul_rn(x0, s_abp), __fmul_rn(s_dir, eps));
+      if (k.add_noise) xn = __fadd_rn(xn, __fmul_rn(sigma, noise[j]));
+      x_out[j] = xn;
+    }
+    if (xop.hi) op_store1(xop, op_fmt, i, xn);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_model, const float* __restrict__ noise,
+                   float* __restrict__ x_out, size_t rows, int cols, DdpmCoefs k, OpPtr xop, int op_fmt) {
+  // gaussian_diffusion.py:572-577, :445-449 (posterior mean), :694 (mean + exp(0.5 logvar) * noise)
+  const float sd = expf(__fmul_rn(0.5f, k.log_var));
+  const int ldo = xop.hi ? xop.ld : cols;
+  const size_t total = rows * (size_t)ldo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ldo;
+    const int c = (int)(i - r * ldo);
+    float xn = 0.f;
+    if (c < cols) {
+      const size_t j = r * cols + c;
+      const float x0 = __fsub_rn(__fmul_rn(k.c1, x[j]), __fmul_rn(k.c2, eps_model[j]));
+      xn = __fadd_rn(__fmul_rn(k.pm1, x0), __fmul_rn(k.pm2, x[j]));
+      if (k.add_noise) xn = __fadd_rn(xn, __fmul_rn(sd, noise[j]));
+      x_out[j] = xn;
+    }
+    if (xop.hi) op_store1(xop, op_fmt, i, xn);
+  }
+}
+
+inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  return (int)std::min<size_t>(g, 148 * 16);
+}
+}  // namespace
+
+int elementwise_init() {
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  return 0;
+}
+unsigned long long elementwise_launch_count() { return g_ew_launches.load(); }
+
+int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, const float* b, const float* scale,
+                   const float* shift, int mod_ld, int rows_per_batch, bool act_silu, OpPtr out, int out_fmt,
+                   cudaStream_t stream) {
+  MCM_CHECK(d % 4 == 0 && d <= 32 * 4 * MAXV, "ln_rows: row length must be a multiple of 4 and <= 1024");
+  MCM_CHECK(ld_in % 4 == 0 && out.ld % 4 == 0 && out.ld >= d && out.ld <= 32 * 4 * MAXV, "ln_rows: bad pitch");
+  MCM_CHECK(mod_ld % 4 == 0, "ln_rows: modulation pitch must be a multiple of 4");
+  const int wpb = 8;
+  ln_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld,
+                                                                  rows_per_batch > 0 ? rows_per_batch : 1,
+                                                                  act_silu ? 1 : 0, out, out_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg, OpPtr out, int out_fmt,
+                       cudaStream_t stream) {
+  MCM_CHECK(seg > 0 && ncols % seg == 0 && seg <= 32 * MAXE, "softmax_seg: segment must divide ncols and be <= 1024");
+  MCM_CHECK(out.ld >= ncols, "softmax_seg: output pitch too small");
+  const int nseg = ncols / seg;
+  const long long warps = (long long)rows * nseg;
+  const int wpb = 8;
+  softmax_seg_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(in, rows, ncols, ld_in, seg, nseg,
+                                                                                 out, out_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, const float* b, OpPtr out, int out_fmt,
+                        cudaStream_t stream) {
+  MCM_CHECK(D % 32 == 0 && T <= 1024 && out.ld >= T, "ln_transpose: need D % 32 == 0, T <= 1024");
+  dim3 grid(D / 32, B), block(32, 8);
+  ln_transpose_kernel<<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, out, out_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu, OpPtr out, int out_fmt,
+                   cudaStream_t stream) {
+  MCM_CHECK(out.ld >= cols, "pack_op: output pitch too small");
+  const size_t total = (size_t)rows * out.ld;
+  pack_op_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, (size_t)rows, cols, ld_in, act_silu ? 1 : 0, out, out_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int timestep_embedding_launch(const long long* t_dev, int t_uniform, int B, int dim, OpPtr out, int out_fmt,
+                              cudaStream_t stream) {
+  const int total = B * out.ld;
+  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t_dev, t_uniform, B, dim, out, out_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int ddim_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
+                       DdimCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream) {
+  MCM_CHECK(!c.add_noise || noise != nullptr, "ddim_update: eta != 0 needs step noise");
+  const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
+  ddim_update_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, eps, noise, x_out, rows, cols, c, xop, op_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int ddpm_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
+                       DdpmCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream) {
+  MCM_CHECK(!c.add_noise || noise != nullptr, "ddpm_update: needs step noise");
+  const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
+  ddpm_update_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, eps, noise, x_out, rows, cols, c, xop, op_fmt);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+}  // namespace mcm

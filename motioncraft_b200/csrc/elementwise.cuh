@@ -1,0 +1,47 @@
+// motioncraft_b200 -- HBM-bound row kernels between the GEMMs: LayerNorm (+AdaLN modulation +SiLU),
+// segment softmax, the transposing LayerNorm of the channel-attention, operand packing, timestep
+// embedding and the DDIM / DDPM update.  All statistics in fp32; outputs are 16-bit GEMM operands.
+#pragma once
+#include "common.cuh"
+
+namespace mcm {
+
+// LayerNorm over the last dim of in[rows, d] (pitch ld_in), eps 1e-5, affine (w, b), then optionally
+//   y = y * (1 + scale[batch, :]) + shift[batch, :]    (StylizationBlock, stylization_block.py:38)
+//   y = SiLU(y)                                          (out_layers[0], :21)
+// batch = row / rows_per_batch; scale/shift have pitch mod_ld.  Output: operand (rows x out.ld), pad 0.
+int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, const float* b,
+                   const float* scale, const float* shift, int mod_ld, int rows_per_batch, bool act_silu,
+                   OpPtr out, int out_fmt, cudaStream_t stream);
+
+// softmax over contiguous segments of length `seg` of every row of in[rows, ncols] (ncols % seg == 0);
+// output operand (rows x out.ld), pad columns zero.
+int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg, OpPtr out, int out_fmt,
+                       cudaStream_t stream);
+
+// h[B, T, D] fp32 -> LayerNorm over T (per (b, d) column, affine w[T], b[T]) written TRANSPOSED as an
+// operand of shape (B*D rows, T cols): row b*D+d.   (EfficientSelfAttention.norm on x^T, mcm.py:28-32)
+int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, const float* b, OpPtr out,
+                        int out_fmt, cudaStream_t stream);
+
+// plain fp32 [rows, cols] -> operand (optionally SiLU first), pad columns zero
+int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu, OpPtr out, int out_fmt,
+                   cudaStream_t stream);
+
+// sinusoidal timestep embedding (position_encoding.py:42-60) -> operand [B, dim]
+int timestep_embedding_launch(const long long* t_dev, int t_uniform, int B, int dim, OpPtr out, int out_fmt,
+                              cudaStream_t stream);
+
+struct DdimCoefs { float c1, c2, alpha_bar, alpha_bar_prev, eta; int add_noise; };
+struct DdpmCoefs { float c1, c2, pm1, pm2, log_var; int add_noise; };
+// x <- DDIM / DDPM update from eps (fp32, n elements); writes x_out (may alias x) and, if xop.hi, the
+// operand copy [rows, cols -> xop.ld] the next step's joint_embed GEMM reads.
+int ddim_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
+                       DdimCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream);
+int ddpm_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
+                       DdpmCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream);
+
+int elementwise_init();
+unsigned long long elementwise_launch_count();
+
+}  // namespace mcm

@@ -1,0 +1,436 @@
+// motioncraft_b200 -- tcgen05 / TMEM / TMA GEMM (sm_100a).  See gemm_tc.cuh for the problem model.
+//
+// One persistent CTA per SM, 6 warps, warp-specialised:
+//   warp 0      TMA producer   : cp.async.bulk.tensor (128B-swizzled boxes) -> smem ring, mbarrier tx
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM);
+//                                tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..5  epilogue       : tcgen05.ld (one TMEM lane = one output row per thread), bias / addend /
+//                                activation / mask, fp32 and/or 16-bit operand stores
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "gemm_tc.cuh"
+
+#include <atomic>
+#include <mutex>
+
+namespace mcm {
+
+namespace {
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;    // 64 x 16-bit = 128 B = one swizzle-128B atom row
+constexpr int UMMA_K = 16;
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+constexpr int SMEM_BUDGET = 220 * 1024;
+
+struct KParams {
+  int M, M_pad, K, batches, inner, a_k_inner, b_batched, out_col_inner, out_rows_per_outer,
+      trans_rows, head_dim;
+  int block_n, m_tiles, n_tiles, num_kb, stages, split, total_tiles;
+  uint32_t idesc, stage_bytes, a_bytes, b_bytes;
+  int nseg;
+  EpiSeg seg[3];
+};
+
+__device__ __forceinline__ float apply_act(float v, int flags) {
+  if (flags & EPI_GELU) return gelu_erf(v);
+  if (flags & EPI_SILU) return silu(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.split) {
+      tma_prefetch_desc(&tmAlo);
+      tma_prefetch_desc(&tmBlo);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&tfull_bar[s]), 1);
+        mbar_init(smem_u32(&tempty_bar[s]), 4);   // one arrive per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = p.stage_bytes;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int t2 = tile / p.n_tiles;
+        const int m_blk = t2 % p.m_tiles;
+        const int batch = t2 / p.m_tiles;
+        const int outer = batch / p.inner;
+        const int inner = batch - outer * p.inner;
+        int si = 0;
+        while (si + 1 < p.nseg && n_tile >= p.seg[si + 1].tile0) ++si;
+        const int b_row = p.seg[si].w_row0 + (n_tile - p.seg[si].tile0) * p.block_n;
+        const int a_k0 = inner * p.a_k_inner;
+        const int a_z = outer;
+        const int b_z = p.b_batched ? batch : 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          mbar_expect_tx(bar, tx);
+          if (!p.split) {
+            tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
+            tma_load_3d(&tmB, bar, sa + p.a_bytes, kb * BLOCK_K, b_row, b_z);
+          } else {
+            tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
+            tma_load_3d(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
+            tma_load_3d(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_row, b_z);
+            tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_row, b_z);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const int kleft = p.K - kb * BLOCK_K;
+          const int nk = kleft >= BLOCK_K ? BLOCK_K / UMMA_K : (kleft + UMMA_K - 1) / UMMA_K;
+          if (!p.split) {
+            const uint32_t sb = sa + p.a_bytes;
+            for (int k = 0; k < nk; ++k) {
+              umma_f16(taddr, make_smem_desc_sw128(sa + k * UMMA_K * 2), make_smem_desc_sw128(sb + k * UMMA_K * 2),
+                       p.idesc, (uint32_t)((kb | k) != 0));
+            }
+          } else {
+            const uint32_t sal = sa + p.a_bytes, sb = sa + 2 * p.a_bytes, sbl = sb + p.b_bytes;
+            for (int k = 0; k < nk; ++k) {
+              const uint32_t o = k * UMMA_K * 2;
+              const uint64_t ah = make_smem_desc_sw128(sa + o), al = make_smem_desc_sw128(sal + o);
+              const uint64_t bh = make_smem_desc_sw128(sb + o), bl = make_smem_desc_sw128(sbl + o);
+              umma_f16(taddr, al, bh, p.idesc, (uint32_t)((kb | k) != 0));   // small terms first
+              umma_f16(taddr, ah, bl, p.idesc, 1u);
+              umma_f16(taddr, ah, bh, p.idesc, 1u);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));   // smem stage reusable once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      const int t2 = tile / p.n_tiles;
+      const int m_blk = t2 % p.m_tiles;
+      const int batch = t2 / p.m_tiles;
+      const int outer = batch / p.inner;
+      const int inner = batch - outer * p.inner;
+      int si = 0;
+      while (si + 1 < p.nseg && n_tile >= p.seg[si + 1].tile0) ++si;
+      const EpiSeg& sg = p.seg[si];
+      const int nbase = (n_tile - sg.tile0) * p.block_n;
+      const int r = m_blk * BLOCK_M + quad * 32 + lane;         // row within the batch
+      const bool row_valid = r < p.M;
+      const bool has_op = sg.op.hi != nullptr;
+      const int flags = sg.flags;
+
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int cbase = nbase + c0;                 // column within the segment of v[0]
+        if (cbase >= sg.n_pad) break;                 // warp-uniform
+        float v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int nvalid = min(32, sg.n - cbase);     // may be <= 0 (pad-only chunk)
+        if (sg.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __ldg(sg.bias + cbase + j);
+        }
+        const int colg0 = sg.col0 + inner * p.out_col_inner + cbase;
+        if (!(flags & EPI_TRANSPOSED)) {
+          if (row_valid) {
+            const size_t row_g = (size_t)outer * p.out_rows_per_outer + r;
+            const size_t off32 = row_g * (size_t)sg.ld32 + colg0;
+            if (sg.addend != nullptr) {
+              const size_t arow = (flags & EPI_ADDEND_BCAST) ? (size_t)r : row_g;
+              const float* ap = sg.addend + arow * (size_t)sg.ld32 + colg0;
+              if (sg.vec32 == 4 && nvalid == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(ap + j);
+                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) v[j] += ap[j];
+              }
+            }
+            if (flags & (EPI_GELU | EPI_SILU)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], flags);
+            }
+            if (flags & EPI_MASK_BLOCKDIAG) {
+              const int rh = r / p.head_dim;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((cbase + j) / p.head_dim != rh) v[j] = 0.f;
+            }
+            if (sg.out32 != nullptr) {
+              float* op32 = sg.out32 + off32;
+              if (sg.vec32 == 4 && nvalid == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(op32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) op32[j] = v[j];
+              }
+            }
+            if (has_op) {
+              const size_t offop = row_g * (size_t)sg.op.ld + colg0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j >= nvalid) v[j] = 0.f;            // pad columns of an operand are zero
+              if ((colg0 & 7) == 0) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (cbase + g * 8 < sg.n_pad) op_store8(sg.op, sg.op_fmt, offop + g * 8, v + g * 8);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (cbase + j < sg.n_pad) op_store1(sg.op, sg.op_fmt, offop + j, v[j]);
+              }
+            }
+          }
+        } else {
+          // transposed destination: lanes (= consecutive r) are contiguous in memory
+          const bool row_pad = !row_valid && r < p.M_pad;
+          if (row_valid || (row_pad && has_op)) {
+            const int rh = (flags & EPI_MASK_BLOCKDIAG) ? r / p.head_dim : 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                const size_t trow = (size_t)outer * p.trans_rows + (size_t)(colg0 + j);
+                float val = v[j];
+                if (row_valid) {
+                  if (sg.addend != nullptr) val += sg.addend[trow * (size_t)sg.ld32 + r];
+                  val = apply_act(val, flags);
+                  if ((flags & EPI_MASK_BLOCKDIAG) && (cbase + j) / p.head_dim != rh) val = 0.f;
+                  if (sg.out32 != nullptr) sg.out32[trow * (size_t)sg.ld32 + r] = val;
+                } else {
+                  val = 0.f;
+                }
+                if (has_op) op_store1(sg.op, sg.op_fmt, trow * (size_t)sg.op.ld + r, val);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+std::once_flag g_init_once;
+int g_init_status = 0;
+std::atomic<unsigned long long> g_launches{0};
+
+int do_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  MCM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  MCM_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  MCM_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MCM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  MCM_CHECK(prop.major == 10, "motioncraft_b200 needs an sm_100a (B200) device; there is no fallback path");
+  g_num_sms = prop.multiProcessorCount;
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
+  return 0;
+}
+
+int make_map(CUtensorMap* m, const void* ptr, int fmt, int k_dim, int rows, int batches, int ld, int box_rows) {
+  MCM_CHECK(ptr != nullptr, "null operand pointer");
+  MCM_CHECK((ld % 8) == 0, "operand pitch must be a multiple of 8 elements (TMA 16-byte rule)");
+  MCM_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "operand base must be 16-byte aligned");
+  cuuint64_t gdim[3] = {(cuuint64_t)k_dim, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, fmt == OP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                        const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (k=" + std::to_string(k_dim) +
+              " rows=" + std::to_string(rows) + " batches=" + std::to_string(batches) + " ld=" + std::to_string(ld) +
+              " box_rows=" + std::to_string(box_rows) + ")");
+    return 1;
+  }
+  return 0;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+}  // namespace
+
+int gemm_tc_init() {
+  std::call_once(g_init_once, [] { g_init_status = do_init(); });
+  if (g_init_status != 0) set_error("gemm_tc_init failed earlier (not an sm_100a device or no TMA driver entry point)");
+  return g_init_status;
+}
+
+unsigned long long gemm_tc_launch_count() { return g_launches.load(); }
+
+int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
+  MCM_TRY(gemm_tc_init());
+  MCM_CHECK(q.nseg >= 1 && q.nseg <= 3, "1..3 output segments");
+  MCM_CHECK(q.M > 0 && q.K > 0 && q.batches > 0 && q.inner > 0 && q.batches % q.inner == 0, "bad GEMM iteration space");
+  MCM_CHECK(q.a.hi && q.b.hi, "missing operand");
+  const int split = q.fmt == OP_BF16X2 ? 1 : 0;
+  if (split) MCM_CHECK(q.a.lo && q.b.lo, "bf16x2 operands need their lo halves");
+
+  KParams p{};
+  p.M = q.M;
+  p.M_pad = round_up(q.M, 8);
+  p.K = q.K;
+  p.batches = q.batches;
+  p.inner = q.inner;
+  p.a_k_inner = q.a_k_inner;
+  p.b_batched = q.b_batched;
+  p.out_col_inner = q.out_col_inner;
+  p.out_rows_per_outer = q.out_rows_per_outer;
+  p.trans_rows = q.trans_rows;
+  p.head_dim = q.head_dim > 0 ? q.head_dim : 1;
+  p.split = split;
+  p.nseg = q.nseg;
+
+  int nmax = 0;
+  for (int s = 0; s < q.nseg; ++s) {
+    p.seg[s] = q.seg[s];
+    EpiSeg& sg = p.seg[s];
+    MCM_CHECK(sg.n > 0, "empty segment");
+    const bool transposed = (sg.flags & EPI_TRANSPOSED) != 0;
+    sg.n_pad = (sg.op.hi != nullptr && !transposed) ? round_up(sg.n, 8) : sg.n;
+    if (sg.op.hi != nullptr) {
+      MCM_CHECK(sg.op_fmt == OP_F16 || sg.op.lo != nullptr, "bf16x2 operand output needs a lo buffer");
+      if (!transposed) MCM_CHECK(sg.op.ld >= sg.col0 + (q.inner - 1) * q.out_col_inner + sg.n_pad, "operand output pitch too small");
+    }
+    sg.vec32 = ((sg.ld32 % 4) == 0 && ((sg.col0 + 0) % 4) == 0 && (q.out_col_inner % 4) == 0 &&
+                (sg.out32 == nullptr || (reinterpret_cast<uintptr_t>(sg.out32) & 15) == 0) &&
+                (sg.addend == nullptr || (reinterpret_cast<uintptr_t>(sg.addend) & 15) == 0))
+                   ? 4 : 1;
+    nmax = std::max(nmax, sg.n_pad);
+  }
+  const int bn_cap = split ? 128 : 256;
+  const int tiles_for_max = (nmax + bn_cap - 1) / bn_cap;
+  p.block_n = std::min(bn_cap, round_up((nmax + tiles_for_max - 1) / tiles_for_max, 16));
+  int tile0 = 0;
+  for (int s = 0; s < q.nseg; ++s) {
+    p.seg[s].tile0 = tile0;
+    p.seg[s].n_tiles = (p.seg[s].n_pad + p.block_n - 1) / p.block_n;
+    tile0 += p.seg[s].n_tiles;
+  }
+  p.n_tiles = tile0;
+  p.m_tiles = (q.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_kb = (q.K + BLOCK_K - 1) / BLOCK_K;
+  p.total_tiles = p.n_tiles * p.m_tiles * q.batches;
+  p.a_bytes = BLOCK_M * BLOCK_K * 2;
+  p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  p.stage_bytes = (split ? 2u : 1u) * (p.a_bytes + p.b_bytes);
+  p.stages = std::min(MAX_STAGES, (int)(SMEM_BUDGET / p.stage_bytes));
+  MCM_CHECK(p.stages >= 2, "tile does not fit a 2-stage pipeline");
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a/b format, K-major both, N>>3, M>>4
+  const uint32_t ab = split ? 1u : 0u;   // 0 = F16, 1 = BF16
+  p.idesc = (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  MCM_TRY(make_map(&tmA, q.a.hi, q.fmt, q.a_k, q.a_rows, q.a_batches, q.a.ld, BLOCK_M));
+  MCM_TRY(make_map(&tmB, q.b.hi, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n));
+  if (split) {
+    MCM_TRY(make_map(&tmAlo, q.a.lo, q.fmt, q.a_k, q.a_rows, q.a_batches, q.a.ld, BLOCK_M));
+    MCM_TRY(make_map(&tmBlo, q.b.lo, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n));
+  } else {
+    tmAlo = tmA;
+    tmBlo = tmB;
+  }
+  const int grid = std::min(p.total_tiles, g_num_sms);
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BUDGET + 1024, stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  MCM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // namespace mcm

@@ -1,0 +1,336 @@
+"""nn.Module shells with the reference's registry names, constructor signatures and state_dict layout
+(SURVEY.md section 8b), whose forward passes run inside the C-ABI CUDA library.
+
+The modules hold parameters (so reference checkpoints load unchanged and `ControlT2MHalf_MCM`-style
+attribute access keeps working) but contain NO arithmetic: `MCMTransformer.forward` and
+`DecoderLayer.forward` hand device pointers to `libmcm_b200.so`.  There is no PyTorch fallback; a CPU
+tensor or a missing library raises.
+
+Reference classes mirrored (paths relative to the reference root):
+  StylizationBlock          mogen/models/utils/stylization_block.py:14-40
+  FFN                       mogen/models/transformers/diffusion_transformer.py:15-28
+  EfficientSelfAttention    mogen/models/attentions/efficient_attention.py:9-46
+  EfficientCrossAttention   mogen/models/attentions/efficient_attention.py:49-92
+  DecoderLayer              mogen/models/transformers/mcm.py:12-41
+  MCMTransformer            mogen/models/transformers/mcm.py:44-102 (+ DiffusionTransformer base)
+  ControlT2MBlock / ControlT2MHalf_MCM   mogen/models/transformers/controlnet_mcm.py:29-87, 107-403
+"""
+import re
+
+import numpy as np
+import torch
+from torch import nn
+
+from ._lib import McmError
+from .engine import DenoiserEngine
+from .registry import ATTENTIONS, SUBMODULES, build_attention
+
+
+def _zero_(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+class _EngineOnly(nn.Module):
+    """A parameter container whose arithmetic lives in the CUDA library."""
+
+    def forward(self, *a, **k):  # pragma: no cover - never a compute path
+        raise McmError(f"{type(self).__name__} has no stand-alone PyTorch forward in motioncraft_b200; it runs as "
+                       "part of DecoderLayer / MCMTransformer inside libmcm_b200.so")
+
+
+class StylizationBlock(_EngineOnly):
+    def __init__(self, latent_dim, time_embed_dim, dropout):
+        super().__init__()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(time_embed_dim, 2 * latent_dim))
+        self.norm = nn.LayerNorm(latent_dim)
+        self.out_layers = nn.Sequential(nn.SiLU(), nn.Dropout(p=dropout),
+                                        _zero_(nn.Linear(latent_dim, latent_dim)))
+
+
+class FFN(_EngineOnly):
+    def __init__(self, latent_dim, ffn_dim, dropout, time_embed_dim):
+        super().__init__()
+        _check_dropout(dropout)
+        self.linear1 = nn.Linear(latent_dim, ffn_dim)
+        self.linear2 = _zero_(nn.Linear(ffn_dim, latent_dim))
+        self.activation = nn.GELU()
+        self.dropout = nn.Dropout(dropout)
+        self.proj_out = StylizationBlock(latent_dim, time_embed_dim, dropout)
+
+
+def _check_dropout(p):
+    if p:
+        raise McmError("motioncraft_b200 is an inference path: dropout must be 0 (configs/mcm/* set dropout = 0)")
+
+
+@ATTENTIONS.register_module()
+class EfficientSelfAttention(_EngineOnly):
+    def __init__(self, latent_dim, num_heads, dropout, time_embed_dim=None):
+        super().__init__()
+        _check_dropout(dropout)
+        if time_embed_dim is None:
+            raise McmError("EfficientSelfAttention without time_embed_dim (the stmogen STMA use) is out of scope")
+        self.num_heads = num_heads
+        self.latent_dim = latent_dim
+        self.norm = nn.LayerNorm(latent_dim)
+        self.query = nn.Linear(latent_dim, latent_dim)
+        self.key = nn.Linear(latent_dim, latent_dim)
+        self.value = nn.Linear(latent_dim, latent_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.time_embed_dim = time_embed_dim
+        self.proj_out = StylizationBlock(latent_dim, time_embed_dim, dropout)
+
+
+@ATTENTIONS.register_module()
+class EfficientCrossAttention(_EngineOnly):
+    def __init__(self, latent_dim, text_latent_dim, num_heads, dropout, time_embed_dim):
+        super().__init__()
+        _check_dropout(dropout)
+        self.num_heads = num_heads
+        self.latent_dim = latent_dim
+        self.text_latent_dim = text_latent_dim
+        self.norm = nn.LayerNorm(latent_dim)
+        self.text_norm = nn.LayerNorm(text_latent_dim)
+        self.query = nn.Linear(latent_dim, latent_dim)
+        self.key = nn.Linear(text_latent_dim, latent_dim)
+        self.value = nn.Linear(text_latent_dim, latent_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.proj_out = StylizationBlock(latent_dim, time_embed_dim, dropout)
+
+
+class DecoderLayer(nn.Module):
+    """mcm.py:12-41.  `ffn_channel` is kept as a parameter container (checkpoints carry its weights)
+    but never evaluated: the reference computes it and discards the result (mcm.py:33-34)."""
+
+    def __init__(self, sa_block_cfg=None, ca_block_cfg=None, ffn_cfg=None):
+        super().__init__()
+        if sa_block_cfg is None or ca_block_cfg is None or ffn_cfg is None:
+            raise McmError("the MCM DecoderLayer needs sa_block_cfg, ca_block_cfg and ffn_cfg (configs/mcm/*)")
+        self.sa_block = build_attention(sa_block_cfg)
+        self.ca_block = build_attention(ca_block_cfg)
+        self.ffn_channel = FFN(**ffn_cfg)
+        self.ffn_temporal = FFN(**ffn_cfg)
+        self._owner = None   # (weakref-free) set by the owning transformer: (owner, kind, index)
+
+    def _bind(self, owner, kind, index):
+        object.__setattr__(self, "_owner", (owner, kind, index))
+
+    def forward(self, x=None, xf=None, emb=None, src_mask=None, **kwargs):
+        if self._owner is None:
+            raise McmError("DecoderLayer is not attached to an MCMTransformer / ControlT2MHalf_MCM engine")
+        if kwargs.get("cond_type") is not None:
+            raise McmError("cond_type (classifier-free training masks) is a training feature; out of scope")
+        owner, kind, index = self._owner
+        return owner._block_forward(kind, index, x, xf, emb)
+
+
+def _shape_cfg(model):
+    blk = model.temporal_decoder_blocks[0]
+    return dict(seq_len=model.max_seq_len, input_feats=model.input_feats, latent_dim=model.latent_dim,
+                time_embed_dim=model.time_embed_dim, ffn_dim=blk.ffn_temporal.linear1.out_features,
+                text_latent_dim=blk.ca_block.text_latent_dim, num_heads=blk.ca_block.num_heads,
+                num_layers=len(model.temporal_decoder_blocks))
+
+
+def timestep_embedding_table():
+    raise NotImplementedError
+
+
+@SUBMODULES.register_module()
+class MCMTransformer(nn.Module):
+    """DiffusionTransformer (diffusion_transformer.py:54-238) + MCMTransformer (mcm.py:44-102)."""
+
+    def __init__(self, input_feats, max_seq_len=240, latent_dim=512, time_embed_dim=2048, num_layers=8,
+                 sa_block_cfg=None, ca_block_cfg=None, ffn_cfg=None, text_encoder=None, use_pos_embedding=True,
+                 use_residual_connection=False, time_embedding_type="sinusoidal", post_process_cfg=None,
+                 init_cfg=None, max_batch=None, precise_all=False):
+        super().__init__()
+        self.init_cfg = init_cfg
+        self.input_feats = input_feats
+        self.max_seq_len = max_seq_len
+        self.latent_dim = latent_dim
+        self.num_layers = num_layers
+        self.time_embed_dim = time_embed_dim
+        self.use_pos_embedding = use_pos_embedding
+        if not use_pos_embedding:
+            raise McmError("use_pos_embedding=False is not used by configs/mcm/*; out of scope")
+        if time_embedding_type != "sinusoidal":
+            raise McmError("only the sinusoidal time embedding (configs/mcm/*) is implemented")
+        if use_residual_connection:
+            raise McmError("use_residual_connection=True is not used by configs/mcm/*; out of scope")
+        if sa_block_cfg is not None and sa_block_cfg.get("latent_dim") != max_seq_len:
+            raise McmError("MCM applies self-attention on the transposed tensor: sa_block_cfg.latent_dim must "
+                           "equal max_seq_len (configs/mcm/mcm_t2m_smplx.py:44-45)")
+        self.sequence_embedding = nn.Parameter(torch.randn(max_seq_len, latent_dim))
+        self._build_text_encoder(text_encoder)
+        self.joint_embed = nn.Linear(input_feats, latent_dim)
+        self.time_embedding_type = time_embedding_type
+        self.time_embed = nn.Sequential(nn.Linear(latent_dim, time_embed_dim), nn.SiLU(),
+                                        nn.Linear(time_embed_dim, time_embed_dim))
+        self.temporal_decoder_blocks = nn.ModuleList(
+            DecoderLayer(sa_block_cfg=sa_block_cfg, ca_block_cfg=ca_block_cfg, ffn_cfg=ffn_cfg)
+            for _ in range(num_layers))
+        self.out = _zero_(nn.Linear(latent_dim, input_feats))
+        self.use_residual_connection = use_residual_connection
+        self.post_process_cfg = post_process_cfg
+        self._max_batch_hint = max_batch
+        self._precise_all = precise_all
+        self._engine = None
+        self._engine_key = None
+        for i, blk in enumerate(self.temporal_decoder_blocks):
+            blk._bind(self, 0, i)
+        self._register_load_state_dict_pre_hook(self._drop_engine_hook)
+
+    # ------------------------------------------------------------------ text encoder (outside the hot path)
+    def _build_text_encoder(self, text_encoder):
+        # diffusion_transformer.py:109-145.  CLIP is not available offline; the modules that hold
+        # trainable text-side weights are created so checkpoints load, CLIP itself is resolved lazily.
+        self.use_text_proj = False
+        self._text_cfg = text_encoder
+        self.clip = None
+        if text_encoder is None:
+            return
+        tl = text_encoder["latent_dim"]
+        self.use_text_proj = text_encoder.get("use_text_proj", False)
+        if text_encoder["pretrained_model"] != "clip":
+            raise NotImplementedError(text_encoder["pretrained_model"])
+        self.text_pre_proj = nn.Linear(512, tl) if tl != 512 else nn.Identity()
+        n_layers = text_encoder.get("num_layers", 0)
+        self.use_text_finetune = n_layers > 0
+        if n_layers > 0:
+            layer = nn.TransformerEncoderLayer(d_model=tl, nhead=text_encoder.get("num_heads", 4),
+                                               dim_feedforward=text_encoder.get("ff_size", 2048),
+                                               dropout=text_encoder.get("dropout", 0),
+                                               activation=text_encoder.get("activation", "gelu"))
+            self.textTransEncoder = nn.TransformerEncoder(layer, num_layers=n_layers)
+        self.text_ln = nn.LayerNorm(tl)
+        if self.use_text_proj:
+            self.text_proj = nn.Sequential(nn.Linear(tl, self.time_embed_dim))
+
+    def encode_text(self, text, clip_feat, device):
+        # diffusion_transformer.py:147-172 -- once per batch, not part of the per-step hot path.
+        if self.clip is None:
+            try:
+                import clip  # noqa: F401
+            except ImportError as e:
+                raise McmError("text conditioning needs the `clip` package and its ViT-B/32 weights, which are not "
+                               "available offline; pass precomputed xf_proj / xf_out (mcm.py:65)") from e
+            self.clip, _ = clip.load("ViT-B/32", "cpu")
+            for p in self.clip.parameters():
+                p.requires_grad = False
+        import clip
+        tokens = clip.tokenize(text, truncate=True).to(device)
+        if clip_feat is None:
+            with torch.no_grad():
+                x = self.clip.token_embedding(tokens).type(self.clip.dtype)
+                x = x + self.clip.positional_embedding.type(self.clip.dtype)
+                x = self.clip.ln_final(self.clip.transformer(x.permute(1, 0, 2))).type(self.clip.dtype)
+        else:
+            x = clip_feat.type(self.clip.dtype).to(device).permute(1, 0, 2)
+        xf_out = self.text_ln(self.textTransEncoder(self.text_pre_proj(x)))
+        xf_proj = self.text_proj(xf_out[tokens.argmax(dim=-1), torch.arange(xf_out.shape[1])])
+        return xf_proj, xf_out.permute(1, 0, 2)
+
+    def get_precompute_condition(self, text=None, xf_proj=None, xf_out=None, device=None, clip_feat=None, **kwargs):
+        if xf_proj is None or xf_out is None:
+            xf_proj, xf_out = self.encode_text(text, clip_feat, device)
+        return {"xf_proj": xf_proj, "xf_out": xf_out}
+
+    def post_process(self, motion):
+        if self.post_process_cfg is not None:
+            if self.post_process_cfg.get("unnormalized_infer", False):
+                mean = torch.from_numpy(np.load(self.post_process_cfg["mean_path"])).type_as(motion)
+                std = torch.from_numpy(np.load(self.post_process_cfg["std_path"])).type_as(motion)
+            motion = motion * std + mean
+        return motion
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _drop_engine_hook(self, *args, **kwargs):
+        self._drop_engine()
+
+    def _drop_engine(self):
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_key = None
+
+    def _hot_state_dict(self):
+        skip = ("clip.", "text_pre_proj.", "textTransEncoder.", "text_ln.", "text_proj.")
+        return {k: v for k, v in self.state_dict().items() if not k.startswith(skip) and ".ffn_channel." not in k}
+
+    def _engine_extra(self):
+        return {}, {}
+
+    def engine(self, batch):
+        dev = self.sequence_embedding.device
+        if dev.type != "cuda":
+            raise McmError("motioncraft_b200 modules compute on an sm_100a CUDA device only: move the model with "
+                           ".cuda() (there is no CPU / PyTorch fallback path)")
+        want = max(batch, self._max_batch_hint or 0)
+        if self._engine is None or self._engine_key[0] != dev or self._engine.max_batch < batch:
+            self._drop_engine()
+            extra_sd, extra_cfg = self._engine_extra()
+            sd = self._hot_state_dict()
+            sd.update(extra_sd)
+            self._engine = DenoiserEngine(sd, max_batch=want, precise_all=self._precise_all, device=dev,
+                                          **_shape_cfg(self), **extra_cfg)
+            self._engine_key = (dev,)
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        self._drop_engine()
+        return super()._apply(fn, *a, **k)
+
+    def _block_forward(self, kind, index, x, xf, emb):
+        eng = self.engine(x.shape[0])
+        eng.prepare_conditions_cached(xf, torch.zeros(x.shape[0], self.time_embed_dim, device=x.device))
+        return eng.block_forward(kind, index, x, emb)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, motion, timesteps, motion_mask=None, motion_length=None, num_intervals=1, patch_size=1,
+                **kwargs):
+        """diffusion_transformer.py:186-238 (eval).  motion_mask / motion_length / num_intervals are accepted
+        for signature parity; the MCM decoder layers replace the mask by ones (mcm.py:28) so it has no effect."""
+        if self.training:
+            raise McmError("motioncraft_b200 implements the inference path only: call .eval() first")
+        if patch_size != 1:
+            raise McmError("patch_size != 1 is not used by configs/mcm/*")
+        cond = self.get_precompute_condition(device=motion.device, **kwargs)
+        xf_proj = cond["xf_proj"] if self.use_text_proj else torch.zeros(
+            motion.shape[0], self.time_embed_dim, device=motion.device)
+        eng = self.engine(motion.shape[0])
+        eng.prepare_conditions_cached(cond["xf_out"], xf_proj, self._control_condition(kwargs))
+        return eng.denoise(motion, timesteps)
+
+    def _control_condition(self, kwargs):
+        return None
+
+    def forward_test(self, h=None, src_mask=None, emb=None, xf_out=None, **kwargs):
+        """mcm.py:93-102, from an already embedded h: runs the per-block entry for every layer, then `out`."""
+        raise McmError("forward_test(h=..., emb=...) on pre-embedded activations is not exposed; call the module "
+                       "(forward) or the DecoderLayer blocks")
+
+
+def state_shapes(seq_len=196, input_feats=322, latent_dim=512, time_embed_dim=2048, ffn_dim=1024,
+                 text_latent_dim=256, num_heads=4, num_layers=8):
+    """name -> shape of the hot-path parameters of an MCMTransformer (text encoder excluded)."""
+    with torch.device("meta"):
+        m = MCMTransformer(**mcm_config(seq_len, input_feats, latent_dim, time_embed_dim, ffn_dim, text_latent_dim,
+                                        num_heads, num_layers))
+    return {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+
+def mcm_config(seq_len=196, input_feats=322, latent_dim=512, time_embed_dim=2048, ffn_dim=1024, text_latent_dim=256,
+               num_heads=4, num_layers=8, text_encoder=None):
+    """The `model=dict(...)` section of configs/mcm/mcm_t2m_smplx.py:37-66 as keyword arguments."""
+    return dict(input_feats=input_feats, max_seq_len=seq_len, latent_dim=latent_dim, time_embed_dim=time_embed_dim,
+                num_layers=num_layers,
+                sa_block_cfg=dict(type="EfficientSelfAttention", latent_dim=seq_len, num_heads=num_heads, dropout=0,
+                                  time_embed_dim=time_embed_dim),
+                ca_block_cfg=dict(type="EfficientCrossAttention", latent_dim=latent_dim,
+                                  text_latent_dim=text_latent_dim, num_heads=num_heads, dropout=0,
+                                  time_embed_dim=time_embed_dim),
+                ffn_cfg=dict(latent_dim=latent_dim, ffn_dim=ffn_dim, dropout=0, time_embed_dim=time_embed_dim),
+                text_encoder=text_encoder)
