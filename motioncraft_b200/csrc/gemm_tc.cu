@@ -192,7 +192,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
         tmem_ld_32x32(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
-        const int nvalid = min(32, sg.n - cbase);     // may be <= 0 (pad-only chunk)
+        const int ncover = min(32, p.block_n - c0);   // columns of this chunk that belong to this tile
+        const int nvalid = min(ncover, sg.n - cbase); // may be <= 0 (pad-only chunk)
         if (sg.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -248,11 +249,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if ((colg0 & 7) == 0) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
-                  if (cbase + g * 8 < sg.n_pad) op_store8(sg.op, sg.op_fmt, offop + g * 8, v + g * 8);
+                  if (g * 8 < ncover && cbase + g * 8 < sg.n_pad) op_store8(sg.op, sg.op_fmt, offop + g * 8, v + g * 8);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (cbase + j < sg.n_pad) op_store1(sg.op, sg.op_fmt, offop + j, v[j]);
+                  if (j < ncover && cbase + j < sg.n_pad) op_store1(sg.op, sg.op_fmt, offop + j, v[j]);
               }
             }
           }
