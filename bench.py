@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- sampled motion frames/sec, 50-step DDIM (eta=0, respace '15,15,8,6,6'), (B x T x 322).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload t2m|s2g|m2d] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU arithmetic (oracle port) on the host cores
+
+One "step" = ONE complete 50-step DDIM sampling run producing B x T frames per GPU (BASELINE.json
+configs[1]: t2m, B=256, T=196, D=322; weak scaling: every rank samples its own 256 rows of the global
+batch, one all-gather of the results at the end, configs[4]).  Prints ONE JSON line (rank 0).
+
+  value : whole-job frames/s with x_T already resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e   : the same through the host-buffer C-ABI call (mcm_sample_host): pinned x_T H2D + loop + x_0 D2H
+  roofline     : tcgen05 GEMM kernel class -- algorithmic FLOPs / summed kernel time (CUDA events around every
+                 launch, separate instrumented pass) against the measured bf16 peak
+  cpu_baseline : the oracle (bit-identical restatement of the reference's CPU path) on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, T, control blocks, control feats, control length)   [BASELINE.json configs 1..3]
+    "t2m": dict(B=256, T=196, n_ctrl=0, c_feats=0, c_len=0),
+    "s2g": dict(B=128, T=300, n_ctrl=2, c_feats=2048, c_len=297),
+    "m2d": dict(B=64, T=1024, n_ctrl=4, c_feats=35, c_len=1024),
+}
+RESPACE = "15,15,8,6,6"
+N_STEPS = 50
+
+
+def algorithmic_flops(T, n_ctrl, n_tokens=77, D=512, E=2048, F=1024, H=4, IN=322, Lt=256, L=8, c_feats=0, c_len=0):
+    """live graph only, per sample; returns (per denoise step, one-off per run)."""
+    layers = L + n_ctrl
+    sa = 8 * D * T * T + 4 * D * T * T / H + 4 * E * T
+    ffn = 4 * T * D * F + 4 * E * D + 2 * T * D * D
+    ca = 4 * T * D * D + 2 * T * D * D / H + 4 * E * D
+    per_step = layers * (sa + ffn + ca) + 4 * T * IN * D + 2 * D * E + 2 * E * E
+    if n_ctrl:
+        per_step += (n_ctrl + 1) * 2 * T * D * D
+    once = layers * (4 * n_tokens * Lt * D + 2 * n_tokens * D * D / H) + 2 * c_len * c_feats * D
+    return per_step, once
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1421.6))), hbm=float(d["hbm_gbs"]),
+                    source="measured (MEASURED_PEAKS.json, bf16 sustained)")
+    return dict(tflops=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_CPU_SETUP = {}
+
+
+def oracle_cpu_setup(T, n_ctrl, c_feats, c_len, B_cpu):
+    """Synthetic weights / inputs for the CPU arm (built once, outside any timed region)."""
+    key = (T, n_ctrl, c_feats, c_len, B_cpu)
+    if key in _CPU_SETUP:
+        return _CPU_SETUP[key]
+    import torch
+    from motioncraft_b200 import modules, synth
+    from oracle import mcm_oracle as O
+    shapes = modules.ctrl_state_shapes(T, n_ctrl, c_feats) if n_ctrl else modules.state_shapes(seq_len=T)
+    sd = synth.synth_state_dict(shapes)
+    x = synth.synth_rows("x_T", (T, 322), synth.SEED_XT, 0, B_cpu)
+    xf_out = synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, 0, B_cpu)
+    xf_proj = synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, 0, B_cpu)
+    c = synth.synth_rows("c", (c_len, c_feats), synth.SEED_C_EMB, 0, B_cpu) if n_ctrl else None
+    if n_ctrl:
+        fn = lambda xx, tt: O.control_forward(sd, xx, tt, xf_proj, xf_out, c)  # noqa: E731
+    else:
+        fn = lambda xx, tt: O.mcm_forward(sd, xx, tt, xf_proj, xf_out)  # noqa: E731
+    with torch.no_grad():
+        fn(x, torch.full((B_cpu,), 999, dtype=torch.long))          # warm-up (thread pool, allocator)
+    _CPU_SETUP[key] = (fn, x)
+    return _CPU_SETUP[key]
+
+
+def oracle_cpu_rate(T, n_ctrl, c_feats, c_len, B_cpu, n_denoise):
+    """frames/s of the reference's CPU arithmetic (oracle port) on a bounded sample: B_cpu samples,
+    n_denoise of the 50 denoise steps + sampler updates, extrapolated to the 50-step run.
+    This is the ONLY place outside tests/ and smoke() where oracle/ is executed, and only as the thing
+    measured in the baseline / reference arm -- never on the product path."""
+    import torch
+    from oracle import mcm_oracle as O
+    fn, x = oracle_cpu_setup(T, n_ctrl, c_feats, c_len, B_cpu)
+    tables, tmap = O.spaced_tables(1000, RESPACE)
+    sub_tables = {k: v[-n_denoise:] for k, v in tables.items()}
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.ddim_sample_loop(fn, x, sub_tables, tmap[-n_denoise:])
+        dt = time.perf_counter() - t0
+    return B_cpu * T / (N_STEPS * dt / n_denoise), dt, torch.get_num_threads()
+
+
+def run_reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    B_cpu = args.cpu_batch or 8
+    oracle_cpu_setup(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu)
+    for _ in range(args.warmup):
+        oracle_cpu_rate(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 1)
+    vals, wall, cores = [], 0.0, None
+    for _ in range(args.steps):
+        v, dt, cores = oracle_cpu_rate(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 2)
+        vals.append(v)
+        wall += dt
+    value = sum(vals) / len(vals)
+    sample = (f"reference CPU arithmetic (oracle port, bit-identical to mogen's PyTorch path on CPU): B={B_cpu} samples x "
+              f"2 of 50 DDIM steps per bench step, fp32, {cores} threads, frames/s = B*T/(50*t_denoise_step)")
+    line = {"impl": "reference", "metric": "sampled motion frames/sec (50-step DDIM)", "value": value, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, wl, world),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl, world):
+    return {"workload": f"{args.workload}: synthetic (B={wl['B']}/GPU x T={wl['T']} x 322), 50-step DDIM eta=0 respace "
+                        f"'{RESPACE}', MCMTransformer 8 layers" + (f" + {wl['n_ctrl']} control blocks" if wl["n_ctrl"] else ""),
+            "global_batch": wl["B"] * world, "seq_len": wl["T"], "parallelism": f"dp{world} (batch shards, one all-gather)",
+            "l2": "per-step working set (>1 GB activations + 124 MB weights) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="t2m", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precise", action="store_true", help="debug: every GEMM in bf16x2-split mode")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["B"] = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from motioncraft_b200 import _lib, modules, synth
+    from motioncraft_b200 import dist as mdist
+    from motioncraft_b200.diffusion import build_diffusion
+    from motioncraft_b200.engine import DenoiserEngine, SamplerTables
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: motioncraft_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = wl["B"], wl["T"]
+    n_total = B * world
+    lo, hi = mdist.shard_range(n_total, rank, world)
+
+    # ---- synthetic weights (replicated) and this rank's rows of the globally seeded inputs
+    if wl["n_ctrl"]:
+        sd = modules.engine_state_from_ctrl(synth.synth_state_dict(modules.ctrl_state_shapes(T, wl["n_ctrl"], wl["c_feats"])))
+    else:
+        sd = {k: v for k, v in synth.synth_state_dict(modules.state_shapes(seq_len=T)).items() if ".ffn_channel." not in k}
+    x_T = synth.synth_rows("x_T", (T, 322), synth.SEED_XT, lo, hi)
+    xf_out = synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, lo, hi)
+    xf_proj = synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, lo, hi)
+    c = synth.synth_rows("c", (wl["c_len"], wl["c_feats"]), synth.SEED_C_EMB, lo, hi) if wl["n_ctrl"] else None
+
+    eng = DenoiserEngine(sd, seq_len=T, max_batch=B, num_ctrl_blocks=wl["n_ctrl"], ctrl_cond_feats=wl["c_feats"],
+                         precise_all=args.precise, device=dev)
+    del sd
+    d = build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                             model_var_type="fixed_small", respace=RESPACE))
+    tables = SamplerTables(d._tables(), d.timestep_map, "ddim", 0.0)
+    x_dev = x_T.to(dev)
+    x_pin = x_T.pin_memory()
+    out_pin = torch.empty_like(x_pin).pin_memory()
+    cond = (xf_out.to(dev), xf_proj.to(dev), c.to(dev) if c is not None else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_run_device():
+        # the step-invariant condition work is part of every sampling run (counted in the algorithmic FLOPs)
+        eng.prepare_conditions(*cond)
+        x0 = eng.sample(tables, x_dev)
+        return mdist.gather_rows(x0, n_total) if world > 1 else x0
+
+    def one_run_host():
+        eng.prepare_conditions(*cond)
+        out = eng.sample_host(tables, x_pin, out_pin)
+        return out
+
+    for _ in range(args.warmup):
+        one_run_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        one_run_device()
+    ev1.record()
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    launches = _lib.kernel_launches() - launches0
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end through the host-buffer C-ABI call (H2D + loop + D2H inside the timed region)
+    one_run_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_run_host()
+        if world > 1:
+            pass  # results stay per-rank on the host; the reference's collect_results is outside this path
+    torch.cuda.synchronize(dev)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+
+    # ---- roofline leg: separate instrumented run (events around every launch), not part of the numbers above
+    _lib.timing_enable(True)
+    one_run_device()
+    tm = _lib.timing_collect()
+    _lib.timing_enable(False)
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        frames = n_total * T * args.steps
+        value = frames / (ms_dev * 1e-3)
+        e2e = frames / (ms_e2e * 1e-3)
+        per_step, once = algorithmic_flops(T, wl["n_ctrl"], c_feats=wl["c_feats"], c_len=wl["c_len"])
+        flops_run = B * (N_STEPS * per_step + once)            # per GPU per sampling run
+        peaks = measured_peaks()
+        gemm_ms = tm["gemm"]["ms"]
+        achieved = flops_run / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        whole = flops_run / (ms_dev / args.steps * 1e-3) / 1e12
+        line = {
+            "metric": "sampled motion frames/sec (50-step DDIM)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands (bf16x2-split for embed/out/AdaLN), f32 accumulate/residual",
+            "data": "synthetic", "config": workload_config(args, wl, world),
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(out_pin.numel() * 4), "api": "mcm_sample_host (pinned host x_T -> x_0)"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one sampling run)",
+                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                         "peak_source": peaks["source"], "algorithmic_gflop_per_frame": flops_run / (B * T) / 1e9,
+                         "gemm_ms_per_run": gemm_ms, "gemm_launches_per_run": tm["gemm"]["launches"],
+                         "row_kernel_ms_per_run": tm["row"]["ms"], "row_kernel_launches_per_run": tm["row"]["launches"],
+                         "whole_step_achieved": whole, "whole_step_frac": whole / peaks["tflops"]},
+        }
+        if not args.no_cpu_baseline:
+            B_cpu = args.cpu_batch or 8
+            torch.set_num_threads(os.cpu_count() or 1)
+            v, dt, cores = oracle_cpu_rate(T, wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 3)
+            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle (bit-identical restatement of mogen's CPU path): B={B_cpu} x 3 of 50 "
+                                              f"DDIM steps, fp32, {dt:.1f} s of CPU work, extrapolated B*T/(50*t_step)"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,4 @@
-/* motioncraft_b200 -- C ABI of the B200-native MotionCraft (configs/mcm/*) denoising hot path.
+/* motioncraft_b200 -- C ABI of the B200-native MotionCraft (configs/mcm) denoising hot path.
  *
  * The reference has NO native boundary: its seam is the mmcv registry + nn.Module call convention
  * (SURVEY.md section 8b).  This header is the boundary a maintainer would bind instead; every entry
@@ -109,6 +109,13 @@ int mcm_sample_host(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* 
  *   fmt 0 = fp16 (1 pass) or 1 = bf16 hi/lo (3 passes). */
 int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
                     int fmt, void* stream);
+
+/* Measurement aid for bench.py's roofline leg: when enabled, every kernel launch of the library is
+ * bracketed by CUDA events on its stream; collect() synchronises the device and returns, for class 0
+ * (tcgen05 GEMM) and class 1 (row kernels), the summed device time [ms], launch count and algorithmic
+ * flops, then clears the record.  Arrays have 2 entries. */
+void mcm_timing_enable(int on);
+int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops);
 
 const char* mcm_last_error(void);
 /* kernels launched by this library since process start (tcgen05 GEMMs, all kernels) */

@@ -46,6 +46,9 @@ SIGNATURES = {
     "mcm_sample": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
     "mcm_sample_host": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
     "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
+    "mcm_timing_enable": (None, [_I]),
+    "mcm_timing_collect": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong),
+                                ctypes.POINTER(ctypes.c_double)]),
     "mcm_last_error": (ctypes.c_char_p, []),
     "mcm_gemm_launches": (ctypes.c_ulonglong, []),
     "mcm_kernel_launches": (ctypes.c_ulonglong, []),
@@ -85,3 +88,17 @@ def kernel_launches():
 
 def gemm_launches():
     return int(load().mcm_gemm_launches())
+
+
+def timing_enable(on):
+    load().mcm_timing_enable(1 if on else 0)
+
+
+def timing_collect():
+    """-> dict(gemm=dict(ms, launches, flops), row=dict(...)); clears the record."""
+    ms = (ctypes.c_double * 2)()
+    n = (ctypes.c_ulonglong * 2)()
+    fl = (ctypes.c_double * 2)()
+    check(load().mcm_timing_collect(ms, n, fl))
+    return {"gemm": dict(ms=ms[0], launches=int(n[0]), flops=fl[0]),
+            "row": dict(ms=ms[1], launches=int(n[1]), flops=fl[1])}

@@ -17,6 +17,7 @@
 #include "../../include/mcm_b200.h"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
+#include "timing.cuh"
 
 namespace mcm {
 
@@ -249,6 +250,7 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     g.seg[0] = seg_default(T, 0);
     g.seg[0].op = view(c->ctxT_sa, Tp); g.seg[0].op_fmt = ff;
     g.seg[0].flags = EPI_TRANSPOSED | EPI_MASK_BLOCKDIAG;
+    g.algo_flops = 2.0 * T * hdT * D * B;      // only the per-head diagonal blocks are algorithmic work
     MCM_TRY(gemm_tc_launch(g, st));
   }
   {  // y^T[b] = softmax(q) ctx                                 -> f32A [B*D, T]
@@ -261,6 +263,7 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     g.nseg = 1;
     g.seg[0] = seg_default(T, 0);
     g.seg[0].out32 = c->f32A; g.seg[0].ld32 = T;
+    g.algo_flops = 2.0 * D * T * hdT * B;
     MCM_TRY(gemm_tc_launch(g, st));
   }
   // StylizationBlock over T: SiLU(LN(y) (1 + scale) + shift)    -> opA [B*D, Tp]
@@ -470,6 +473,12 @@ const char* mcm_last_error(void) { return g_last_error.c_str(); }
 const char* mcm_version(void) { return "motioncraft_b200 0.1.0 (sm_100a, tcgen05)"; }
 unsigned long long mcm_gemm_launches(void) { return gemm_tc_launch_count(); }
 unsigned long long mcm_kernel_launches(void) { return gemm_tc_launch_count() + elementwise_launch_count(); }
+
+void mcm_timing_enable(int on) { timing_enable(on != 0); }
+int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops) {
+  MCM_CHECK(ms && launches && flops, "null argument");
+  return timing_collect(ms, launches, flops);
+}
 
 int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   MCM_CHECK(cfg != nullptr && out != nullptr, "null argument");

@@ -2,6 +2,7 @@
 // reductions, 8-byte packed 16-bit stores; the transposing LayerNorm stages a [T x 32] tile in shared
 // memory so both its reads (along d) and its writes (along t) are coalesced.
 #include "elementwise.cuh"
+#include "timing.cuh"
 
 #include <atomic>
 
@@ -297,6 +298,7 @@ int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, 
   MCM_CHECK(ld_in % 4 == 0 && out.ld % 4 == 0 && out.ld >= d && out.ld <= 32 * 4 * MAXV, "ln_rows: bad pitch");
   MCM_CHECK(mod_ld % 4 == 0, "ln_rows: modulation pitch must be a multiple of 4");
   const int wpb = 8;
+  LaunchTimer lt(LK_ROW, stream);
   ln_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld,
                                                                   rows_per_batch > 0 ? rows_per_batch : 1,
                                                                   act_silu ? 1 : 0, out, out_fmt);
@@ -312,6 +314,7 @@ int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg,
   const int nseg = ncols / seg;
   const long long warps = (long long)rows * nseg;
   const int wpb = 8;
+  LaunchTimer lt(LK_ROW, stream);
   softmax_seg_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(in, rows, ncols, ld_in, seg, nseg,
                                                                                  out, out_fmt);
   MCM_CUDA(cudaGetLastError());
@@ -323,6 +326,7 @@ int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, con
                         cudaStream_t stream) {
   MCM_CHECK(D % 32 == 0 && T <= 1024 && out.ld >= T, "ln_transpose: need D % 32 == 0, T <= 1024");
   dim3 grid(D / 32, B), block(32, 8);
+  LaunchTimer lt(LK_ROW, stream);
   ln_transpose_kernel<<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, out, out_fmt);
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
@@ -333,6 +337,7 @@ int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu
                    cudaStream_t stream) {
   MCM_CHECK(out.ld >= cols, "pack_op: output pitch too small");
   const size_t total = (size_t)rows * out.ld;
+  LaunchTimer lt(LK_ROW, stream);
   pack_op_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, (size_t)rows, cols, ld_in, act_silu ? 1 : 0, out, out_fmt);
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
@@ -342,6 +347,7 @@ int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu
 int timestep_embedding_launch(const long long* t_dev, int t_uniform, int B, int dim, OpPtr out, int out_fmt,
                               cudaStream_t stream) {
   const int total = B * out.ld;
+  LaunchTimer lt(LK_ROW, stream);
   timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t_dev, t_uniform, B, dim, out, out_fmt);
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
@@ -352,6 +358,7 @@ int ddim_update_launch(const float* x, const float* eps, const float* noise, flo
                        DdimCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream) {
   MCM_CHECK(!c.add_noise || noise != nullptr, "ddim_update: eta != 0 needs step noise");
   const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
+  LaunchTimer lt(LK_ROW, stream);
   ddim_update_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, eps, noise, x_out, rows, cols, c, xop, op_fmt);
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
@@ -362,6 +369,7 @@ int ddpm_update_launch(const float* x, const float* eps, const float* noise, flo
                        DdpmCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream) {
   MCM_CHECK(!c.add_noise || noise != nullptr, "ddpm_update: needs step noise");
   const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
+  LaunchTimer lt(LK_ROW, stream);
   ddpm_update_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, eps, noise, x_out, rows, cols, c, xop, op_fmt);
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);

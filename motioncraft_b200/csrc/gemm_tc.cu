@@ -8,6 +8,7 @@
 //                                activation / mask, fp32 and/or 16-bit operand stores
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "gemm_tc.cuh"
+#include "timing.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -428,7 +429,16 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     tmBlo = tmB;
   }
   const int grid = std::min(p.total_tiles, g_num_sms);
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BUDGET + 1024, stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  double flops = q.algo_flops;
+  if (flops <= 0.0) {
+    long long ncols = 0;
+    for (int s = 0; s < q.nseg; ++s) ncols += q.seg[s].n;
+    flops = 2.0 * (double)q.M * (double)ncols * (double)q.K * (double)q.batches;
+  }
+  {
+    LaunchTimer lt(LK_GEMM, stream, flops);
+    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BUDGET + 1024, stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  }
   MCM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -54,6 +54,7 @@ struct GemmProblem {
   int head_dim;          // see EPI_MASK_BLOCKDIAG
   int nseg;
   EpiSeg seg[3];
+  double algo_flops;     // ALGORITHMIC flops of this launch for the roofline record; 0 = 2*M*N*K*batches
 };
 
 // Launch on `stream`.  Returns 0 or an error status (message via mcm_last_error()).

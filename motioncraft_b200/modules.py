@@ -134,10 +134,6 @@ def _shape_cfg(model):
                 num_layers=len(model.temporal_decoder_blocks))
 
 
-def timestep_embedding_table():
-    raise NotImplementedError
-
-
 @SUBMODULES.register_module()
 class MCMTransformer(nn.Module):
     """DiffusionTransformer (diffusion_transformer.py:54-238) + MCMTransformer (mcm.py:44-102)."""
@@ -307,6 +303,17 @@ class MCMTransformer(nn.Module):
     def _control_condition(self, kwargs):
         return None
 
+    def bind_for_sampling(self, batch, model_kwargs, device):
+        """Used by GaussianDiffusion.{p,ddim}_sample_loop: resolve the conditions once, stage the
+        step-invariant work in the engine, return the engine that runs the whole loop."""
+        if self.training:
+            raise McmError("motioncraft_b200 implements the inference path only: call .eval() first")
+        cond = self.get_precompute_condition(device=device, **model_kwargs)
+        xf_proj = cond["xf_proj"] if self.use_text_proj else torch.zeros(batch, self.time_embed_dim, device=device)
+        eng = self.engine(batch)
+        eng.prepare_conditions_cached(cond["xf_out"], xf_proj, self._control_condition(model_kwargs))
+        return eng
+
     def forward_test(self, h=None, src_mask=None, emb=None, xf_out=None, **kwargs):
         """mcm.py:93-102, from an already embedded h: runs the per-block entry for every layer, then `out`."""
         raise McmError("forward_test(h=..., emb=...) on pre-embedded activations is not exposed; call the module "
@@ -334,3 +341,174 @@ def mcm_config(seq_len=196, input_feats=322, latent_dim=512, time_embed_dim=2048
                                   time_embed_dim=time_embed_dim),
                 ffn_cfg=dict(latent_dim=latent_dim, ffn_dim=ffn_dim, dropout=0, time_embed_dim=time_embed_dim),
                 text_encoder=text_encoder)
+
+
+# =================================================================================================
+# ControlNet branch (speech-to-gesture / music-to-dance), controlnet_mcm.py
+# =================================================================================================
+def _cfg_get(cfg, *path):
+    cur = cfg
+    for key in path:
+        cur = cur[key] if isinstance(cur, dict) else getattr(cur, key)
+    return cur
+
+
+class ControlT2MBlock(nn.Module):
+    """controlnet_mcm.py:29-87: a trainable copy of base block `block_index` with zero-initialised
+    before_proj (first block only) / after_proj."""
+
+    def __init__(self, base_block, block_index=0, latent_dim=512, cfg=None):
+        super().__init__()
+        model_cfg = _cfg_get(cfg, "model", "model")
+        self.copied_block = DecoderLayer(sa_block_cfg=_cfg_get(model_cfg, "sa_block_cfg"),
+                                         ca_block_cfg=_cfg_get(model_cfg, "ca_block_cfg"),
+                                         ffn_cfg=_cfg_get(model_cfg, "ffn_cfg"))
+        self.copied_block.load_state_dict(base_block.state_dict())
+        self.block_index = block_index
+        self.hidden_size = latent_dim
+        if block_index == 0:
+            self.before_proj = _zero_(nn.Linear(latent_dim, latent_dim))
+        self.after_proj = _zero_(nn.Linear(latent_dim, latent_dim))
+
+    def forward(self, *a, **k):
+        raise McmError("ControlT2MBlock runs inside ControlT2MHalf_MCM's fused forward in libmcm_b200.so")
+
+
+class ControlT2MHalf_MCM(nn.Module):
+    """controlnet_mcm.py:107-403: the base MCMTransformer plus `copy_blocks_num` control copies fed by a
+    speech / music condition `c`.  The whole controlled forward (forward_c once per run, the interleaved
+    base / control blocks per step) runs in the CUDA library."""
+
+    def __init__(self, base_model, copy_blocks_num=2, control_cond_feats=438, cfg=None):
+        super().__init__()
+        self.cfg = cfg
+        self.base_model = base_model.eval()
+        self.copy_blocks_num = copy_blocks_num
+        self.total_blocks_num = len(base_model.temporal_decoder_blocks)
+        self.controlnet = nn.ModuleList(
+            ControlT2MBlock(base_model.temporal_decoder_blocks[i], i, base_model.latent_dim, cfg)
+            for i in range(copy_blocks_num))
+        enc_cfg = _cfg_get(cfg, "condition_encode_cfg")
+        self._pre_encode = bool(_cfg_get(enc_cfg, "condition_pre_encode"))
+        if self._pre_encode:
+            # the WavEncoder (mogen/models/utils/blocks.py:53-71) is step-invariant and stays outside this
+            # library ("next" row f-3): callers hand the PRE-ENCODED audio embedding as `c`.
+            in_feats = _cfg_get(enc_cfg, "condition_latent_dim")
+        else:
+            in_feats = control_cond_feats
+        self.condition_pre_encoder = None
+        self.control_cond_feats = in_feats
+        self.control_cond_input = _zero_(nn.Linear(in_feats, base_model.latent_dim))
+        self._engine = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self._drop_engine())
+        self.eval()
+
+    # expose what the architecture wrapper touches
+    @property
+    def time_embed_dim(self):
+        return self.base_model.time_embed_dim
+
+    @property
+    def use_text_proj(self):
+        return self.base_model.use_text_proj
+
+    def get_precompute_condition(self, **kwargs):
+        return self.base_model.get_precompute_condition(**kwargs)
+
+    def post_process(self, output):
+        return self.base_model.post_process(output)
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    def load_state_dict(self, state_dict, strict=True):
+        # controlnet_mcm.py:364-376: a base-only checkpoint loads into base_model
+        if all(k.startswith(("base_model", "controlnet", "control_cond_input", "condition_pre_encoder"))
+               for k in state_dict.keys()):
+            return super().load_state_dict(state_dict, strict)
+        return self.base_model.load_state_dict(state_dict, strict)
+
+    def _drop_engine(self):
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._drop_engine()
+        return super()._apply(fn, *a, **k)
+
+    def engine(self, batch):
+        base = self.base_model
+        dev = base.sequence_embedding.device
+        if dev.type != "cuda":
+            raise McmError("motioncraft_b200 modules compute on an sm_100a CUDA device only (no CPU fallback)")
+        if self._engine is None or self._engine.device != dev or self._engine.max_batch < batch:
+            self._drop_engine()
+            sd = base._hot_state_dict()
+            for k, v in self.state_dict().items():
+                if k.startswith(("controlnet.", "control_cond_input.")) and ".ffn_channel." not in k:
+                    sd[k] = v
+            self._engine = DenoiserEngine(sd, max_batch=max(batch, base._max_batch_hint or 0),
+                                          precise_all=base._precise_all, device=dev,
+                                          num_ctrl_blocks=self.copy_blocks_num,
+                                          ctrl_cond_feats=self.control_cond_feats, **_shape_cfg(base))
+        return self._engine
+
+    def _condition(self, c):
+        if c is None:
+            return None
+        if c.shape[-1] != self.control_cond_feats:
+            raise McmError(f"control condition has {c.shape[-1]} features, control_cond_input expects "
+                           f"{self.control_cond_feats} (raw audio must be pre-encoded; see INTEGRATION.md)")
+        return c
+
+    def bind_for_sampling(self, batch, model_kwargs, device):
+        base = self.base_model
+        cond = base.get_precompute_condition(device=device, **model_kwargs)
+        xf_proj = cond["xf_proj"] if base.use_text_proj else torch.zeros(batch, base.time_embed_dim, device=device)
+        eng = self.engine(batch)
+        eng.prepare_conditions_cached(cond["xf_out"], xf_proj, self._condition(model_kwargs.get("c")))
+        return eng
+
+    def forward(self, motion, timesteps, motion_mask=None, motion_length=None, num_intervals=1, c=None, **kwargs):
+        """controlnet_mcm.py:168-233 + forward_test :306-361 (eval)."""
+        kwargs = dict(kwargs)
+        kwargs["c"] = c
+        eng = self.bind_for_sampling(motion.shape[0], kwargs, motion.device)
+        return eng.denoise(motion, timesteps)
+
+
+SUBMODULES.register_module(module=ControlT2MHalf_MCM)
+
+
+def ctrl_state_shapes(seq_len, n_ctrl, cond_feats, latent_dim=512):
+    """name -> shape of a ControlT2MHalf_MCM state_dict (condition_pre_encode=False):
+    base_model.* + controlnet.{j}.{copied_block.*, before_proj.*, after_proj.*} + control_cond_input.*
+    (controlnet_mcm.py:107-153)."""
+    base = state_shapes(seq_len=seq_len, latent_dim=latent_dim)
+    out = {"base_model." + k: v for k, v in base.items()}
+    p0 = "temporal_decoder_blocks.0."
+    for j in range(n_ctrl):
+        for k, v in base.items():
+            if k.startswith(p0):
+                out[f"controlnet.{j}.copied_block." + k[len(p0):]] = v
+        if j == 0:
+            out["controlnet.0.before_proj.weight"] = (latent_dim, latent_dim)
+            out["controlnet.0.before_proj.bias"] = (latent_dim,)
+        out[f"controlnet.{j}.after_proj.weight"] = (latent_dim, latent_dim)
+        out[f"controlnet.{j}.after_proj.bias"] = (latent_dim,)
+    out["control_cond_input.weight"] = (latent_dim, cond_feats)
+    out["control_cond_input.bias"] = (latent_dim,)
+    return out
+
+
+def engine_state_from_ctrl(sd):
+    """ControlT2MHalf_MCM state_dict -> the flat key space of the C-ABI (base_model. prefix stripped,
+    dead ffn_channel weights dropped)."""
+    out = {}
+    for k, v in sd.items():
+        if ".ffn_channel." in k:
+            continue
+        out[k[len("base_model."):] if k.startswith("base_model.") else k] = v
+    return out

@@ -1,0 +1,130 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Runs in the build container only (needs /root/reference, imported under oracle/ref_shim.py).  Inputs
+and weights are pure functions of seeds (motioncraft_b200/synth.py), so only OUTPUTS are stored.
+
+    python oracle/make_golden.py            # writes tests/golden/{t2m_T60,ctrl_T60,schedule}.npz
+"""
+import contextlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from motioncraft_b200 import synth  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+        return AttrDict(v) if isinstance(v, dict) and not isinstance(v, AttrDict) else v
+
+
+@contextlib.contextmanager
+def scripted_randn_like(noises):
+    """Replace torch.randn_like by a scripted sequence (p_sample draws exactly one per step, :685)."""
+    it = iter(noises)
+    orig = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: next(it).to(x)
+    try:
+        yield
+    finally:
+        torch.randn_like = orig
+
+
+def inputs(B, T):
+    return (synth.synth_tensor("x_T", (B, T, 322), synth.SEED_XT),
+            synth.synth_tensor("xf_out", (B, 77, 256), synth.SEED_XF_OUT),
+            synth.synth_tensor("xf_proj", (B, 2048), synth.SEED_XF_PROJ))
+
+
+def t2m(T=60, B=1):
+    ref = ref_shim.build_reference_mcm(T=T)
+    sd = synth.synth_state_dict({k: v.shape for k, v in ref.state_dict().items()})
+    ref.load_state_dict(sd)
+    x, xf_out, xf_proj = inputs(B, T)
+    kw = dict(motion_mask=torch.ones(B, T), motion_length=torch.full((B,), T), xf_proj=xf_proj, xf_out=xf_out)
+    out = {"keys": np.array(sorted(sd.keys()))}
+    with torch.no_grad():
+        for t in (999, 500, 0):
+            out[f"eps_t{t}"] = ref(x, torch.full((B,), t, dtype=torch.long), **kw).numpy()
+        ddim = ref_shim.build_reference_diffusion("15,15,8,6,6")
+        out["ddim50_x0"] = ddim.ddim_sample_loop(ref, (B, T, 322), noise=x.clone(), clip_denoised=False,
+                                                 model_kwargs=dict(kw, y={}), eta=0).numpy()
+        ddpm = ref_shim.build_reference_diffusion("10")
+        noise = synth.synth_tensor("step_noise", (10, B, T, 322), synth.SEED_STEP_NOISE)
+        with scripted_randn_like([noise[i] for i in reversed(range(10))]):
+            out["ddpm10_x0"] = ddpm.p_sample_loop(ref, (B, T, 322), noise=x.clone(), clip_denoised=False,
+                                                  model_kwargs=dict(kw, y={})).numpy()
+        out["ddpm10_timestep_map"] = np.array(ddpm.timestep_map)
+    np.savez_compressed(os.path.join(GOLD, f"t2m_T{T}.npz"), **out)
+    print("t2m", {k: (v.shape, float(np.abs(v).max())) for k, v in out.items() if v.dtype != np.dtype("<U1") and v.dtype.kind == "f"})
+
+
+def ctrl(T=60, B=1, n_ctrl=2, cond_feats=35, c_len=None):
+    """ControlT2MHalf_MCM as tools/m2d_test.py:372-381 builds it (condition_pre_encode=False)."""
+    from torch import nn
+    ref_shim.install()
+    from mogen.models.transformers.controlnet_mcm import ControlT2MHalf_MCM
+    base = ref_shim.build_reference_mcm(T=T)
+    for name in ("clip", "text_pre_proj", "textTransEncoder", "text_ln"):
+        setattr(base, name, nn.Identity())
+    model_cfg = dict(sa_block_cfg=dict(type="EfficientSelfAttention", latent_dim=T, num_heads=4, dropout=0, time_embed_dim=2048),
+                     ca_block_cfg=dict(type="EfficientCrossAttention", latent_dim=512, text_latent_dim=256, num_heads=4,
+                                       dropout=0, time_embed_dim=2048),
+                     ffn_cfg=dict(latent_dim=512, ffn_dim=1024, dropout=0, time_embed_dim=2048))
+    cfg = AttrDict(model=dict(model=model_cfg),
+                   condition_encode_cfg=dict(dataset_name="finedance", condition_pre_encode=False, condition_cfg=True))
+    net = ControlT2MHalf_MCM(base, copy_blocks_num=n_ctrl, control_cond_feats=cond_feats, cfg=cfg)
+    net.eval()
+    hot = {k: v.shape for k, v in net.state_dict().items()}
+    sd = synth.synth_state_dict(hot)
+    nn.Module.load_state_dict(net, sd)
+    c_len = c_len or T - 3
+    x, xf_out, xf_proj = inputs(B, T)
+    c = synth.synth_tensor("c_m2d", (B, c_len, cond_feats), synth.SEED_C_M2D)
+    kw = dict(motion_mask=torch.ones(B, T), motion_length=torch.full((B,), T), xf_proj=xf_proj, xf_out=xf_out)
+    out = {"keys": np.array(sorted(sd.keys()))}
+    with torch.no_grad():
+        out["eps_t999"] = net(x, torch.full((B,), 999, dtype=torch.long), c=c, **kw).numpy()
+        out["eps_t999_noc"] = net(x, torch.full((B,), 999, dtype=torch.long), c=None, **kw).numpy()
+        ddim = ref_shim.build_reference_diffusion("15,15,8,6,6")
+        out["ddim50_x0"] = ddim.ddim_sample_loop(net, (B, T, 322), noise=x.clone(), clip_denoised=False,
+                                                 model_kwargs=dict(kw, y={}, c=c), eta=0).numpy()
+    out["c_len"] = np.array(c_len)
+    np.savez_compressed(os.path.join(GOLD, f"ctrl_T{T}.npz"), **out)
+    print("ctrl", {k: (v.shape, float(np.abs(v).max())) for k, v in out.items() if v.dtype.kind == "f"})
+
+
+def schedule():
+    ref_shim.install()
+    from mogen.models.utils import gaussian_diffusion as gd
+    out = {}
+    for tag, resp in (("ddim50", "15,15,8,6,6"), ("ddpm10", "10"), ("full", None)):
+        d = ref_shim.build_reference_diffusion(resp)
+        out[f"{tag}_timestep_map"] = np.array(getattr(d, "timestep_map", list(range(1000))))
+        for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+                  "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                  "posterior_mean_coef1", "posterior_mean_coef2"):
+            out[f"{tag}_{k}"] = getattr(d, k)
+    out["space_fast27"] = np.array(sorted(gd.space_timesteps(1000, "fast27")))
+    out["space_ddim25"] = np.array(sorted(gd.space_timesteps(1000, "ddim25")))
+    np.savez_compressed(os.path.join(GOLD, "schedule.npz"), **out)
+    print("schedule ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    schedule()
+    t2m()
+    ctrl()

@@ -1,0 +1,145 @@
+"""CPU: host-side logic -- registry, module/state_dict layout, schedule tables, the C-ABI library's
+exported symbols, and the 'fail loudly without a GPU' contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import motioncraft_b200 as M
+from motioncraft_b200 import _lib, diffusion, modules
+from motioncraft_b200._lib import McmError
+from oracle import mcm_oracle as O
+from tests import common as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _t2m_cfg(T=60, inference_type="ddim", respace="15,15,8,6,6"):
+    dt = dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon", model_var_type="fixed_small")
+    test = dict(dt, respace=respace) if respace else dict(dt)
+    return dict(type="MotionDiffusion", model=dict(type="MCMTransformer", **modules.mcm_config(T)),
+                loss_recon=dict(type="MSELoss", loss_weight=1, reduction="none"), diffusion_train=dt,
+                diffusion_test=test, inference_type=inference_type)
+
+
+def test_registry_resolves_config_types():
+    for name in ("MotionDiffusion", "MCMTransformer", "EfficientSelfAttention", "EfficientCrossAttention", "MSELoss",
+                 "ControlT2MHalf_MCM"):
+        assert name in M.MODELS, name
+    assert M.build_attention(None) is None
+    with pytest.raises(KeyError):
+        M.build_submodule(dict(type="NoSuchModel"))
+    arch = M.build_architecture(_t2m_cfg())
+    assert isinstance(arch, M.MotionDiffusion) and isinstance(arch.model, M.MCMTransformer)
+    assert arch.diffusion_test.num_timesteps == 50
+    arch2 = M.build_architecture(_t2m_cfg(inference_type="ddpm", respace=None))
+    assert arch2.diffusion_test.num_timesteps == 1000
+
+
+def test_state_dict_keys_and_zero_init(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "t2m_T60.npz"))
+    m = M.MCMTransformer(**modules.mcm_config(60))
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == list(gold["keys"])           # identical to the reference's key set
+    # the reference zero-initialises out, every out_layers[2] and every linear2
+    assert float(sd["out.weight"].abs().max()) == 0.0
+    assert float(sd["temporal_decoder_blocks.3.ffn_temporal.linear2.weight"].abs().max()) == 0.0
+    assert float(sd["temporal_decoder_blocks.0.sa_block.proj_out.out_layers.2.weight"].abs().max()) == 0.0
+    assert sd["temporal_decoder_blocks.0.sa_block.query.weight"].shape == (60, 60)
+    assert sd["temporal_decoder_blocks.0.ca_block.key.weight"].shape == (512, 256)
+    assert sd["temporal_decoder_blocks.0.sa_block.proj_out.emb_layers.1.weight"].shape == (120, 2048)
+
+
+def test_control_wrapper_state_dict_layout(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "ctrl_T60.npz"))
+    base = M.MCMTransformer(**modules.mcm_config(60))
+    cfg = dict(model=dict(model=modules.mcm_config(60)),
+               condition_encode_cfg=dict(dataset_name="finedance", condition_pre_encode=False, condition_cfg=True))
+    net = M.ControlT2MHalf_MCM(base, copy_blocks_num=2, control_cond_feats=35, cfg=cfg)
+    assert sorted(net.state_dict().keys()) == list(gold["keys"])
+    assert sorted(C.ctrl_shapes(60, 2, 35).keys()) == list(gold["keys"])
+    # base-only checkpoints load into base_model (controlnet_mcm.py:364-376)
+    net.load_state_dict(base.state_dict())
+
+
+def test_sa_latent_dim_must_equal_seq_len():
+    cfg = modules.mcm_config(60)
+    cfg["sa_block_cfg"]["latent_dim"] = 64
+    with pytest.raises(McmError):
+        M.MCMTransformer(**cfg)
+
+
+def test_diffusion_tables_match_oracle_and_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "schedule.npz"))
+    d = diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                                       model_var_type="fixed_small", respace="15,15,8,6,6"))
+    assert d.timestep_map == list(g["ddim50_timestep_map"])
+    for k in ("alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+              "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped", "betas"):
+        np.testing.assert_array_equal(getattr(d, k), g[f"ddim50_{k}"], err_msg=k)
+    assert diffusion.space_timesteps(1000, "fast27") == set(O.space_timesteps(1000, "fast27"))
+    assert diffusion.space_timesteps(1000, "ddim25") == set(O.space_timesteps(1000, "ddim25"))
+    with pytest.raises(ValueError):
+        diffusion.space_timesteps(1000, "ddim999")
+
+
+def test_unsupported_parameterisations_fail_loudly():
+    with pytest.raises(McmError):
+        diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="start_x",
+                                       model_var_type="fixed_large"))
+    d = diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                                       model_var_type="fixed_small", respace="10"))
+    with pytest.raises(McmError):
+        d.ddim_sample_loop(None, (1, 60, 322), clip_denoised=False,
+                           model_kwargs={"y": {"outpainting_mask": torch.ones(1, 60, 322, dtype=torch.bool)}})
+    with pytest.raises(McmError):
+        d.training_losses()
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "mcm_b200.h")).read()
+    declared = set(re.findall(r"\b(mcm_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mcm_ctx", "mcm_config", "mcm_sampler"}
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.load()                      # raises if the .so is absent: there is no fallback
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.mcm_version()
+    assert lib.mcm_kernel_launches() >= 0
+
+
+def test_struct_layouts_match_header():
+    header = open(os.path.join(ROOT, "include", "mcm_b200.h")).read()
+    cfg_body = re.search(r"typedef struct mcm_config \{(.*?)\} mcm_config;", header, re.S).group(1)
+    fields = re.findall(r"^\s*int\s+([a-z_]+);", cfg_body, re.M)
+    assert fields == [f[0] for f in _lib.McmConfig._fields_]
+    smp_body = re.search(r"typedef struct mcm_sampler \{(.*?)\} mcm_sampler;", header, re.S).group(1)
+    fields = re.findall(r"^\s*(?:const\s+)?(?:int|float)\*?\s+([a-z_0-9]+);", smp_body, re.M)
+    assert fields == [f[0] for f in _lib.McmSampler._fields_]
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    m = M.MCMTransformer(**modules.mcm_config(60)).eval()
+    x, xf_out, xf_proj = C.inputs(1, 60)
+    with pytest.raises(McmError):
+        m(x, torch.zeros(1, dtype=torch.long), motion_mask=torch.ones(1, 60), xf_proj=xf_proj, xf_out=xf_out)
+    lib = _lib.load()
+    cfg = _lib.McmConfig(322, 60, 512, 2048, 1024, 256, 4, 8, 0, 0, 1, 77, 0)
+    ctx = ctypes.c_void_p()
+    assert lib.mcm_create(ctypes.byref(cfg), ctypes.byref(ctx)) != 0     # no device -> error status, not a crash
+    assert len(lib.mcm_last_error()) > 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "motioncraft_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "ref_shim" not in src and "/root/reference" not in src, f

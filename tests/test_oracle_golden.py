@@ -1,0 +1,113 @@
+"""CPU: the oracle restatement against vectors produced by the UNMODIFIED reference (oracle/make_golden.py)
+and against the schedule known-answers of SURVEY.md section 8(a2')."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from motioncraft_b200 import synth
+from oracle import mcm_oracle as O
+from tests import common as C
+
+
+@pytest.fixture(scope="module")
+def gold_t2m(golden_dir):
+    return np.load(os.path.join(golden_dir, "t2m_T60.npz"))
+
+
+def test_space_timesteps_known_answers():
+    want = [0, 14, 28, 43, 57, 71, 85, 99, 114, 128, 142, 156, 171, 185, 199, 200, 214, 228, 243, 257, 271, 285, 299,
+            314, 328, 342, 356, 371, 385, 399, 400, 428, 457, 485, 514, 542, 571, 599, 600, 640, 680, 719, 759, 799,
+            800, 840, 880, 919, 959, 999]
+    assert O.space_timesteps(1000, "15,15,8,6,6") == want
+    ten = O.space_timesteps(1000, "10")
+    assert ten[0] == 0 and ten[1] == 111 and ten[-2] == 888 and ten[-1] == 999 and len(ten) == 10
+    with pytest.raises(ValueError):
+        O.space_timesteps(10, "20")
+
+
+def test_spaced_tables_known_answers():
+    tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
+    ac = tables["alphas_cumprod"]
+    assert len(tmap) == 50
+    np.testing.assert_allclose(ac[[0, 1, 48, 49]], [0.9999, 0.9964144, 8.912634e-05, 4.035830e-05], rtol=2e-7)
+    np.testing.assert_allclose(tables["sqrt_recip_alphas_cumprod"][49], 157.41046, rtol=1e-7)
+    np.testing.assert_allclose(tables["sqrt_recipm1_alphas_cumprod"][49], 157.40728, rtol=1e-7)
+
+
+def test_schedule_matches_reference_tables(golden_dir):
+    g = np.load(os.path.join(golden_dir, "schedule.npz"))
+    for tag, resp in (("ddim50", "15,15,8,6,6"), ("ddpm10", "10"), ("full", None)):
+        tables, tmap = O.spaced_tables(1000, resp)
+        assert list(g[f"{tag}_timestep_map"]) == tmap
+        for k, v in tables.items():
+            np.testing.assert_array_equal(v, g[f"{tag}_{k}"], err_msg=f"{tag}:{k}")   # float64, bit-exact
+    assert list(g["space_fast27"]) == O.space_timesteps(1000, "fast27")
+    assert list(g["space_ddim25"]) == O.space_timesteps(1000, "ddim25")
+
+
+def test_state_dict_layout_matches_reference(gold_t2m):
+    assert sorted(C.base_state(60).keys()) == list(gold_t2m["keys"])
+
+
+@pytest.mark.parametrize("t", [999, 500, 0])
+def test_forward_bit_exact_vs_reference(gold_t2m, t):
+    x, xf_out, xf_proj = C.inputs(1, 60)
+    got = C.oracle_forward(C.base_state(60), x, t, xf_proj, xf_out)
+    # identical torch ops in identical order on the same host -> identical bits; allow 1e-6 relative
+    # for a different CPU / MKL code path on another machine.
+    assert C.rel_l2(got, gold_t2m[f"eps_t{t}"]) < 1e-6
+
+
+def test_ddim50_vs_reference(gold_t2m):
+    x, xf_out, xf_proj = C.inputs(1, 60)
+    got = C.oracle_ddim(C.base_state(60), x, xf_proj, xf_out)
+    assert C.rel_l2(got, gold_t2m["ddim50_x0"]) < 2e-6
+
+
+def test_ddpm10_vs_reference(gold_t2m):
+    x, xf_out, xf_proj = C.inputs(1, 60)
+    noise = synth.synth_tensor("step_noise", (10, 1, 60, 322), synth.SEED_STEP_NOISE)
+    got = C.oracle_ddpm(C.base_state(60), x, xf_proj, xf_out, noise)
+    assert list(gold_t2m["ddpm10_timestep_map"]) == O.space_timesteps(1000, "10")
+    assert C.rel_l2(got, gold_t2m["ddpm10_x0"]) < 2e-6
+
+
+def test_control_forward_vs_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ctrl_T60.npz"))
+    sd = synth.synth_state_dict(C.ctrl_shapes(60, 2, 35))
+    assert sorted(sd.keys()) == list(g["keys"])
+    x, xf_out, xf_proj = C.inputs(1, 60)
+    c = synth.synth_tensor("c_m2d", (1, int(g["c_len"]), 35), synth.SEED_C_M2D)
+    t = torch.full((1,), 999, dtype=torch.long)
+    with torch.no_grad():
+        got = O.control_forward(sd, x, t, xf_proj, xf_out, c)
+        got_noc = O.control_forward(sd, x, t, xf_proj, xf_out, None)
+    assert C.rel_l2(got, g["eps_t999"]) < 1e-6
+    assert C.rel_l2(got_noc, g["eps_t999_noc"]) < 1e-6
+
+
+def test_hoisted_cross_attention_context_is_exact():
+    """The step-invariant K/V context split (what the CUDA path caches per run) changes nothing."""
+    sd = C.base_state(60)
+    x, xf_out, xf_proj = C.inputs(2, 60)
+    h, emb = O.embed(x, torch.full((2,), 7, dtype=torch.long), xf_proj, sd)
+    pfx = "temporal_decoder_blocks.0.ca_block"
+    with torch.no_grad():
+        a = O.efficient_cross_attention(h, xf_out, emb, sd, pfx, 4)
+        ctx = O.cross_attention_context(xf_out, sd, pfx, 4)
+        b = O.efficient_cross_attention(h, None, emb, sd, pfx, 4, context=ctx)
+    assert torch.equal(a, b)
+
+
+def test_dead_ffn_channel_has_no_effect(gold_t2m):
+    """mcm.py:33-34 computes ffn_channel and discards it: perturbing its weights must change nothing
+    (this is why neither the oracle nor the CUDA path evaluates it)."""
+    sd = dict(C.base_state(60))
+    for k in list(sd):
+        if ".ffn_channel." in k:
+            sd[k] = sd[k] + 1.0
+    x, xf_out, xf_proj = C.inputs(1, 60)
+    got = C.oracle_forward(sd, x, 999, xf_proj, xf_out)
+    assert C.rel_l2(got, gold_t2m["eps_t999"]) < 1e-6
