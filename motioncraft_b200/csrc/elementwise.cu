@@ -9,7 +9,7 @@
 namespace mcm {
 namespace {
 std::atomic<unsigned long long> g_ew_launches{0};
-constexpr int MAXV = 8;   // float4 per lane -> rows of up to 1024 elements
+constexpr int MAXV_LIMIT = 8;   // float4 per lane -> rows of up to 1024 elements
 
 __device__ __forceinline__ void op_store4(const OpPtr& o, int fmt, size_t idx, float a, float b, float c, float d) {
   if (fmt == OP_F16) {
@@ -34,6 +34,7 @@ __device__ __forceinline__ void op_store4(const OpPtr& o, int fmt, size_t idx, f
 }
 
 // ------------------------------------------------------------------------------------------ ln_rows
+template <int MAXV>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const float* __restrict__ w,
                const float* __restrict__ b, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -99,42 +100,51 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
 }
 
 // ------------------------------------------------------------------------------------------ softmax_seg
-// one warp per (row, segment); seg <= 32 * MAXE
-constexpr int MAXE = 32;
+// LPS lanes cooperate on one segment (EPL elements per lane, seg <= LPS * EPL); a warp handles 32 / LPS
+// consecutive segments.  Short segments (the 49-wide heads of the channel attention) use 8 lanes each so a
+// warp covers a whole 196-float row with four 32-byte-granular streams instead of wasting 3/4 of its lanes.
+template <int LPS, int EPL>
 __global__ void __launch_bounds__(256)
-softmax_seg_kernel(const float* __restrict__ in, int rows, int ncols, int ld_in, int seg, int nseg, OpPtr out,
-                   int out_fmt) {
-  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols, int ld_in, int seg, int nseg,
+                   OpPtr out, int out_fmt) {
+  constexpr int SPW = 32 / LPS;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (gw >= (long long)rows * nseg) return;
-  const int row = (int)(gw / nseg);
-  const int sidx = (int)(gw - (long long)row * nseg);
+  const int sub = lane % LPS;
+  const long long gs = wid * SPW + lane / LPS;
+  const bool active = gs < total_segs;
+  const long long row = active ? gs / nseg : 0;
+  const int sidx = active ? (int)(gs - row * nseg) : 0;
   const float* x = in + (size_t)row * ld_in + (size_t)sidx * seg;
-  float v[MAXE];
+  float v[EPL];
   float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int c = i * 32 + lane;
-    v[i] = (c < seg) ? x[c] : -INFINITY;
+  for (int i = 0; i < EPL; ++i) {
+    const int c = i * LPS + sub;
+    v[i] = (active && c < seg) ? x[c] : -INFINITY;
     m = fmaxf(m, v[i]);
   }
-  m = warp_max(m);
+#pragma unroll
+  for (int o = LPS / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int c = i * 32 + lane;
-    v[i] = (c < seg) ? expf(v[i] - m) : 0.f;
+  for (int i = 0; i < EPL; ++i) {
+    const int c = i * LPS + sub;
+    v[i] = (active && c < seg) ? expf(v[i] - m) : 0.f;
     s += v[i];
   }
-  const float inv = 1.f / warp_sum(s);
+#pragma unroll
+  for (int o = LPS / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (!active) return;
+  const float inv = 1.f / s;
   const size_t obase = (size_t)row * out.ld + (size_t)sidx * seg;
 #pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int c = i * 32 + lane;
+  for (int i = 0; i < EPL; ++i) {
+    const int c = i * LPS + sub;
     if (c < seg) op_store1(out, out_fmt, obase + c, v[i] * inv);
   }
   if (sidx == nseg - 1) {
-    for (int c = ncols + lane; c < out.ld; c += 32) op_store1(out, out_fmt, (size_t)row * out.ld + c, 0.f);
+    for (int c = ncols + sub; c < out.ld; c += LPS) op_store1(out, out_fmt, (size_t)row * out.ld + c, 0.f);
   }
 }
 
@@ -294,14 +304,26 @@ unsigned long long elementwise_launch_count() { return g_ew_launches.load(); }
 int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, const float* b, const float* scale,
                    const float* shift, int mod_ld, int rows_per_batch, bool act_silu, OpPtr out, int out_fmt,
                    cudaStream_t stream) {
-  MCM_CHECK(d % 4 == 0 && d <= 32 * 4 * MAXV, "ln_rows: row length must be a multiple of 4 and <= 1024");
-  MCM_CHECK(ld_in % 4 == 0 && out.ld % 4 == 0 && out.ld >= d && out.ld <= 32 * 4 * MAXV, "ln_rows: bad pitch");
+  MCM_CHECK(d % 4 == 0 && d <= 32 * 4 * MAXV_LIMIT, "ln_rows: row length must be a multiple of 4 and <= 1024");
+  MCM_CHECK(ld_in % 4 == 0 && out.ld % 4 == 0 && out.ld >= d && out.ld <= 32 * 4 * MAXV_LIMIT, "ln_rows: bad pitch");
   MCM_CHECK(mod_ld % 4 == 0, "ln_rows: modulation pitch must be a multiple of 4");
   const int wpb = 8;
+  const int grid = (rows + wpb - 1) / wpb;
+  const int rpb = rows_per_batch > 0 ? rows_per_batch : 1;
+  const int nv = (out.ld / 4 + 31) / 32;      // float4 per lane needed to cover the (padded) row
   LaunchTimer lt(LK_ROW, stream);
-  ln_rows_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld,
-                                                                  rows_per_batch > 0 ? rows_per_batch : 1,
-                                                                  act_silu ? 1 : 0, out, out_fmt);
+#define MCM_LN_CASE(V)                                                                                          \
+  case V:                                                                                                       \
+    ln_rows_kernel<V><<<grid, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld, rpb,       \
+                                                     act_silu ? 1 : 0, out, out_fmt);                           \
+    break;
+  switch (nv) {
+    MCM_LN_CASE(1) MCM_LN_CASE(2) MCM_LN_CASE(3) MCM_LN_CASE(4) MCM_LN_CASE(5) MCM_LN_CASE(6) MCM_LN_CASE(7)
+    default:
+      ln_rows_kernel<8><<<grid, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld, rpb,
+                                                       act_silu ? 1 : 0, out, out_fmt);
+  }
+#undef MCM_LN_CASE
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -309,14 +331,27 @@ int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, 
 
 int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg, OpPtr out, int out_fmt,
                        cudaStream_t stream) {
-  MCM_CHECK(seg > 0 && ncols % seg == 0 && seg <= 32 * MAXE, "softmax_seg: segment must divide ncols and be <= 1024");
+  MCM_CHECK(seg > 0 && ncols % seg == 0 && seg <= 1024, "softmax_seg: segment must divide ncols and be <= 1024");
   MCM_CHECK(out.ld >= ncols, "softmax_seg: output pitch too small");
   const int nseg = ncols / seg;
-  const long long warps = (long long)rows * nseg;
+  const long long total = (long long)rows * nseg;
   const int wpb = 8;
   LaunchTimer lt(LK_ROW, stream);
-  softmax_seg_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(in, rows, ncols, ld_in, seg, nseg,
-                                                                                 out, out_fmt);
+#define MCM_SM_LAUNCH(LPS, EPL)                                                                                  \
+  {                                                                                                              \
+    const long long warps = (total + (32 / LPS) - 1) / (32 / LPS);                                               \
+    softmax_seg_kernel<LPS, EPL><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(                  \
+        in, total, ncols, ld_in, seg, nseg, out, out_fmt);                                                       \
+  }
+  if (seg <= 16) MCM_SM_LAUNCH(8, 2)
+  else if (seg <= 32) MCM_SM_LAUNCH(8, 4)
+  else if (seg <= 64) MCM_SM_LAUNCH(8, 8)
+  else if (seg < 128) MCM_SM_LAUNCH(8, 16)
+  else if (seg <= 128) MCM_SM_LAUNCH(32, 4)
+  else if (seg <= 256) MCM_SM_LAUNCH(32, 8)
+  else if (seg <= 512) MCM_SM_LAUNCH(32, 16)
+  else MCM_SM_LAUNCH(32, 32)
+#undef MCM_SM_LAUNCH
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

@@ -20,10 +20,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;    // 64 x 16-bit = 128 B = one swizzle-128B atom row
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;          // multiple of 4 (TMEM lane quadrants)
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int SMEM_BUDGET = 220 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;   // operand ring; + 33 KB static transposition buffers
 
 struct KParams {
   int M, M_pad, K, batches, inner, a_k_inner, b_batched, out_col_inner, out_rows_per_outer,
@@ -33,12 +34,6 @@ struct KParams {
   int nseg;
   EpiSeg seg[3];
 };
-
-__device__ __forceinline__ float apply_act(float v, int flags) {
-  if (flags & EPI_GELU) return gelu_erf(v);
-  if (flags & EPI_SILU) return silu(v);
-  return v;
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
@@ -50,6 +45,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float stage_buf[NUM_EPI_WARPS][32 * 33];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,7 +67,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(smem_u32(&tfull_bar[s]), 1);
-        mbar_init(smem_u32(&tempty_bar[s]), 4);   // one arrive per epilogue warp
+        mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);   // one arrive per epilogue warp
       }
       fence_mbar_init();
     }
@@ -162,8 +158,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
+    // ------------------------------------------------------------------ epilogue (warps 2 .. 2+NUM_EPI_WARPS)
+    // TMEM lane quadrant q is readable only by warps with warp % 4 == q; the NUM_EPI_WARPS / 4 warps that
+    // share a quadrant take alternate 32-column chunks of the tile.
+    const int ew = warp - 2;                          // 0 .. NUM_EPI_WARPS-1
+    const int quad = warp & 3;
+    const int chunk_phase = ew >> 2;                  // which of the interleaved chunk sets this warp takes
+    float* stg = &stage_buf[ew][0];                   // [32][33] transposition buffer of this warp
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -178,16 +179,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       while (si + 1 < p.nseg && n_tile >= p.seg[si + 1].tile0) ++si;
       const EpiSeg& sg = p.seg[si];
       const int nbase = (n_tile - sg.tile0) * p.block_n;
-      const int r = m_blk * BLOCK_M + quad * 32 + lane;         // row within the batch
-      const bool row_valid = r < p.M;
+      const int row0 = m_blk * BLOCK_M + quad * 32;             // first row (within the batch) of this warp
+      const int r = row0 + lane;                                // this thread's row in the TMEM layout
       const bool has_op = sg.op.hi != nullptr;
       const int flags = sg.flags;
+      const int op_fmt = sg.op_fmt;
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
 
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = chunk_phase * 32; c0 < p.block_n; c0 += 32 * (NUM_EPI_WARPS / 4)) {
         const int cbase = nbase + c0;                 // column within the segment of v[0]
         if (cbase >= sg.n_pad) break;                 // warp-uniform
         float v[32];
@@ -195,34 +197,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         const int ncover = min(32, p.block_n - c0);   // columns of this chunk that belong to this tile
         const int nvalid = min(ncover, sg.n - cbase); // may be <= 0 (pad-only chunk)
-        if (sg.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) v[j] += __ldg(sg.bias + cbase + j);
-        }
         const int colg0 = sg.col0 + inner * p.out_col_inner + cbase;
+
         if (!(flags & EPI_TRANSPOSED)) {
-          if (row_valid) {
-            const size_t row_g = (size_t)outer * p.out_rows_per_outer + r;
-            const size_t off32 = row_g * (size_t)sg.ld32 + colg0;
-            if (sg.addend != nullptr) {
-              const size_t arow = (flags & EPI_ADDEND_BCAST) ? (size_t)r : row_g;
-              const float* ap = sg.addend + arow * (size_t)sg.ld32 + colg0;
-              if (sg.vec32 == 4 && nvalid == 32) {
+          // ---- row-major destination: transpose the 32x32 block through smem so that a warp
+          // instruction touches ONE row (128 contiguous bytes) instead of 32 rows.
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 a4 = *reinterpret_cast<const float4*>(ap + j);
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = stg[i * 33 + lane];     // now: lane = column, i = row
+          __syncwarp();
+          const int nrows = min(32, p.M - row0);      // valid rows of this warp (<= 0: none)
+          const bool col_ok = lane < nvalid;
+          const bool col_pad = !col_ok && lane < ncover && (cbase + lane) < sg.n_pad;
+          const float bias_v = (sg.bias != nullptr && col_ok) ? __ldg(sg.bias + cbase + lane) : 0.f;
+          const size_t rowg0 = (size_t)outer * p.out_rows_per_outer + row0;
+          const int colg = colg0 + lane;
+          if (sg.addend != nullptr && col_ok) {
+            const float* ap = sg.addend + ((flags & EPI_ADDEND_BCAST) ? (size_t)row0 : rowg0) * (size_t)sg.ld32 + colg;
+            float a[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = (i < nrows) ? ap[(size_t)i * sg.ld32] : 0.f;   // all loads in flight
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += a[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bias_v;
+          if (flags & EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          } else if (flags & EPI_SILU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
+          }
+          if (flags & EPI_MASK_BLOCKDIAG) {
+            const int ch = (cbase + lane) / p.head_dim;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if ((row0 + i) / p.head_dim != ch) v[i] = 0.f;
+          }
+          if (sg.out32 != nullptr && col_ok) {
+            float* op32 = sg.out32 + rowg0 * (size_t)sg.ld32 + colg;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nrows) op32[(size_t)i * sg.ld32] = v[i];
+          }
+          if (has_op && (col_ok || col_pad)) {
+            const size_t ob = rowg0 * (size_t)sg.op.ld + colg;
+            if (op_fmt == OP_F16) {
+              uint16_t* oh = reinterpret_cast<uint16_t*>(sg.op.hi) + ob;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nrows) oh[(size_t)i * sg.op.ld] = col_ok ? f32_to_f16_bits(v[i]) : (uint16_t)0;
+            } else {
+              uint16_t* oh = reinterpret_cast<uint16_t*>(sg.op.hi) + ob;
+              uint16_t* ol = reinterpret_cast<uint16_t*>(sg.op.lo) + ob;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (i < nrows) {
+                  uint16_t h16 = 0, l16 = 0;
+                  if (col_ok) f32_to_bf16x2_bits(v[i], h16, l16);
+                  oh[(size_t)i * sg.op.ld] = h16;
+                  ol[(size_t)i * sg.op.ld] = l16;
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) v[j] += ap[j];
               }
             }
-            if (flags & (EPI_GELU | EPI_SILU)) {
+          }
+        } else {
+          // ---- transposed destination: element (r, c) -> [(outer*trans_rows + c) * ld + r]; lanes
+          // (consecutive r) are already contiguous in memory, so every access is a full 128-byte line.
+          const bool row_valid = r < p.M;
+          const bool row_pad = !row_valid && r < p.M_pad;
+          if (sg.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], flags);
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += __ldg(sg.bias + cbase + j);
+          }
+          const size_t trow0 = (size_t)outer * p.trans_rows + (size_t)colg0;
+          if (row_valid) {
+            if (sg.addend != nullptr) {
+              const float* ap = sg.addend + trow0 * (size_t)sg.ld32 + r;
+              float a[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = (j < nvalid) ? ap[(size_t)j * sg.ld32] : 0.f;   // loads first:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += a[j];   // the destination may alias the addend (residual add)
+            }
+            if (flags & EPI_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (flags & EPI_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
             }
             if (flags & EPI_MASK_BLOCKDIAG) {
               const int rh = r / p.head_dim;
@@ -231,52 +298,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if ((cbase + j) / p.head_dim != rh) v[j] = 0.f;
             }
             if (sg.out32 != nullptr) {
-              float* op32 = sg.out32 + off32;
-              if (sg.vec32 == 4 && nvalid == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(op32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) op32[j] = v[j];
-              }
-            }
-            if (has_op) {
-              const size_t offop = row_g * (size_t)sg.op.ld + colg0;
+              float* op32 = sg.out32 + trow0 * (size_t)sg.ld32 + r;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j >= nvalid) v[j] = 0.f;            // pad columns of an operand are zero
-              if ((colg0 & 7) == 0) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  if (g * 8 < ncover && cbase + g * 8 < sg.n_pad) op_store8(sg.op, sg.op_fmt, offop + g * 8, v + g * 8);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < ncover && cbase + j < sg.n_pad) op_store1(sg.op, sg.op_fmt, offop + j, v[j]);
-              }
+                if (j < nvalid) op32[(size_t)j * sg.ld32] = v[j];
             }
           }
-        } else {
-          // transposed destination: lanes (= consecutive r) are contiguous in memory
-          const bool row_pad = !row_valid && r < p.M_pad;
-          if (row_valid || (row_pad && has_op)) {
-            const int rh = (flags & EPI_MASK_BLOCKDIAG) ? r / p.head_dim : 0;
+          if (has_op && (row_valid || row_pad)) {
+            const size_t ob = trow0 * (size_t)sg.op.ld + r;
+            if (op_fmt == OP_F16) {
+              uint16_t* oh = reinterpret_cast<uint16_t*>(sg.op.hi) + ob;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nvalid) {
-                const size_t trow = (size_t)outer * p.trans_rows + (size_t)(colg0 + j);
-                float val = v[j];
-                if (row_valid) {
-                  if (sg.addend != nullptr) val += sg.addend[trow * (size_t)sg.ld32 + r];
-                  val = apply_act(val, flags);
-                  if ((flags & EPI_MASK_BLOCKDIAG) && (cbase + j) / p.head_dim != rh) val = 0.f;
-                  if (sg.out32 != nullptr) sg.out32[trow * (size_t)sg.ld32 + r] = val;
-                } else {
-                  val = 0.f;
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) oh[(size_t)j * sg.op.ld] = row_valid ? f32_to_f16_bits(v[j]) : (uint16_t)0;
+            } else {
+              uint16_t* oh = reinterpret_cast<uint16_t*>(sg.op.hi) + ob;
+              uint16_t* ol = reinterpret_cast<uint16_t*>(sg.op.lo) + ob;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < nvalid) {
+                  uint16_t h16 = 0, l16 = 0;
+                  if (row_valid) f32_to_bf16x2_bits(v[j], h16, l16);
+                  oh[(size_t)j * sg.op.ld] = h16;
+                  ol[(size_t)j * sg.op.ld] = l16;
                 }
-                if (has_op) op_store1(sg.op, sg.op_fmt, trow * (size_t)sg.op.ld + r, val);
               }
             }
           }
