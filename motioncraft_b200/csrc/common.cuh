@@ -16,6 +16,7 @@ namespace mcm {
 // mcm_last_error() hands back; nothing throws across the ABI and nothing calls exit().
 // ---------------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
+std::string mcm_last_error_string();
 #define MCM_CUDA(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \

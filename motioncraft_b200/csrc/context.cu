@@ -23,6 +23,7 @@ namespace mcm {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+std::string mcm_last_error_string() { return g_last_error; }
 
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 inline size_t smax(size_t a, size_t b) { return a > b ? a : b; }

@@ -11,6 +11,8 @@
 #include "timing.cuh"
 
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace mcm {
@@ -24,7 +26,9 @@ constexpr int NUM_EPI_WARPS = 8;          // multiple of 4 (TMEM lane quadrants)
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int SMEM_BUDGET = 192 * 1024;   // operand ring; + 33 KB static transposition buffers
+constexpr int STG_BYTES = 8192;            // per epilogue warp: 4 KB fp32 tile | 2 KB 16-bit hi | 2 KB 16-bit lo
+constexpr int SMEM_TOTAL = 224 * 1024;     // dynamic shared memory request (+ ~1.3 KB static <= 227 KB)
+constexpr int SMEM_BUDGET = SMEM_TOTAL - 1024 - NUM_EPI_WARPS * STG_BYTES;   // operand ring
 
 struct KParams {
   int M, M_pad, K, batches, inner, a_k_inner, b_batched, out_col_inner, out_rows_per_outer,
@@ -33,19 +37,79 @@ struct KParams {
   uint32_t idesc, stage_bytes, a_bytes, b_bytes;
   int nseg;
   EpiSeg seg[3];
+  int tma_mode[3];      // per segment: 0 = generic epilogue, else bit0 TMA epilogue, bit1 residual via TMA reduce-add,
+                        // bit2 addend TMA-loaded, bit3 addend broadcast over batches
 };
+
+struct EpiMaps {        // [segment][0 = fp32 out, 1 = fp32 addend, 2 = op hi, 3 = op lo]
+  CUtensorMap m[3][4];
+};
+
+enum { TM_TMA = 1, TM_RED = 2, TM_LDADD = 4, TM_BCAST = 8 };
+
+__device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(desc), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const void* desc, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(desc), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+  return r;
+}
+// two floats -> packed fp16x2 (lo half = a), saturating at +-65504
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// erf-GELU with the Abramowitz-Stegun 7.1.26 rational erf (|abs err| < 5e-7, below the fp16 rounding of the
+// result); the bf16x2 ("precise") operand path keeps erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float pe = poly * e;
+  return 0.5f * x * (x >= 0.f ? 2.f - pe : pe);
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ KParams p) {
+               const __grid_constant__ EpiMaps em, const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float stage_buf[NUM_EPI_WARPS][32 * 33];
+  __shared__ __align__(8) uint64_t abar[NUM_EPI_WARPS];   // addend-tile arrival, one per epilogue warp
+  __shared__ __align__(16) float bias_s[NUM_EPI_WARPS][32];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(smem_u32(&tfull_bar[s]), 1);
         mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);   // one arrive per epilogue warp
       }
+      for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(smem_u32(&abar[s]), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -164,7 +229,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 2;                          // 0 .. NUM_EPI_WARPS-1
     const int quad = warp & 3;
     const int chunk_phase = ew >> 2;                  // which of the interleaved chunk sets this warp takes
-    float* stg = &stage_buf[ew][0];                   // [32][33] transposition buffer of this warp
+    // per-warp staging region behind the operand ring (1024-byte aligned: TMA swizzle patterns are
+    // functions of the absolute shared-memory address)
+    const uint32_t stgA = smem_base + (uint32_t)p.stages * p.stage_bytes + (uint32_t)ew * STG_BYTES;
+    const uint32_t stgH = stgA + 4096, stgL = stgA + 6144;
+    float* stg = reinterpret_cast<float*>(smem_raw + (stgA - smem_u32(smem_raw)));   // generic path: [32][33] floats
+    const uint32_t my_abar = smem_u32(&abar[ew]);
+    uint32_t abar_phase = 0;
+    bool stores_pending = false;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -192,13 +264,147 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c0 = chunk_phase * 32; c0 < p.block_n; c0 += 32 * (NUM_EPI_WARPS / 4)) {
         const int cbase = nbase + c0;                 // column within the segment of v[0]
         if (cbase >= sg.n_pad) break;                 // warp-uniform
-        float v[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
         const int ncover = min(32, p.block_n - c0);   // columns of this chunk that belong to this tile
         const int nvalid = min(ncover, sg.n - cbase); // may be <= 0 (pad-only chunk)
         const int colg0 = sg.col0 + inner * p.out_col_inner + cbase;
+        const int tmode = p.tma_mode[si];
+        float v[32];
 
+        // The staging region may still be read by the previous chunk's bulk store.
+        if (stores_pending) {
+          if (lane == 0) tma_wait_read0();
+          __syncwarp();
+          stores_pending = false;
+        }
+        if (tmode & TM_TMA) {
+          // ================= TMA epilogue: registers -> swizzled smem tile -> bulk tensor store =================
+          if ((tmode & TM_LDADD) && lane == 0) {       // fetch the addend tile while the accumulator is read
+            mbar_expect_tx(my_abar, 4096);
+            tma_load_3d(&em.m[si][1], my_abar, stgA, colg0, row0, (tmode & TM_BCAST) ? 0 : outer);
+          }
+          float bias_r = 0.f;
+          if (sg.bias != nullptr && lane < nvalid) bias_r = __ldg(sg.bias + cbase + lane);
+          tmem_ld_32x32(taddr + (uint32_t)c0, v);
+          bias_s[ew][lane] = bias_r;
+          __syncwarp();
+          tmem_ld_wait();
+          const bool transposed = (flags & EPI_TRANSPOSED) != 0;
+          if (sg.bias != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[ew][4 * q]);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+          }
+          if (tmode & TM_LDADD) {
+            mbar_wait(my_abar, abar_phase);
+            abar_phase ^= 1u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 a4 = ld_shared_v4(stgA + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4));
+              v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+            }
+          }
+          if (flags & EPI_GELU) {
+            if (op_fmt == OP_F16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
+          } else if (flags & EPI_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+          }
+          if (flags & EPI_MASK_BLOCKDIAG) {
+            const int rh = r / p.head_dim;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((cbase + j) / p.head_dim != rh) v[j] = 0.f;
+          }
+          if (nvalid < 32 || r >= p.M) {               // pad columns / pad rows of an operand must be exactly zero
+            const bool rv = r < p.M;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= nvalid || !rv) v[j] = 0.f;
+          }
+          __syncwarp();                                // every lane is done reading the addend tile
+          if (!transposed) {
+            if (sg.out32 != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                st_shared_v4(stgA + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1],
+                             v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (has_op) {
+              const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+              if (op_fmt == OP_F16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  st_shared_v4u(stgH + (uint32_t)lane * 64u + (((uint32_t)q ^ sw) << 4), pack_f16x2_sat(v[8 * q], v[8 * q + 1]),
+                                pack_f16x2_sat(v[8 * q + 2], v[8 * q + 3]), pack_f16x2_sat(v[8 * q + 4], v[8 * q + 5]),
+                                pack_f16x2_sat(v[8 * q + 6], v[8 * q + 7]));
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t h[4], l[4];
+#pragma unroll
+                  for (int e2 = 0; e2 < 4; ++e2) {
+                    const float a0 = v[8 * q + 2 * e2], a1 = v[8 * q + 2 * e2 + 1];
+                    h[e2] = pack_bf16x2(a0, a1);
+                    l[e2] = pack_bf16x2(a0 - __uint_as_float(h[e2] << 16), a1 - __uint_as_float(h[e2] & 0xffff0000u));
+                  }
+                  st_shared_v4u(stgH + (uint32_t)lane * 64u + (((uint32_t)q ^ sw) << 4), h[0], h[1], h[2], h[3]);
+                  st_shared_v4u(stgL + (uint32_t)lane * 64u + (((uint32_t)q ^ sw) << 4), l[0], l[1], l[2], l[3]);
+                }
+              }
+            }
+          } else {
+            // transposed tile in smem: [c][r] dense rows (no swizzle), lanes (= r) contiguous
+            if (sg.out32 != nullptr) {
+              float* a = reinterpret_cast<float*>(smem_raw + (stgA - smem_u32(smem_raw)));
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j * 32 + lane] = v[j];
+            }
+            if (has_op) {
+              uint16_t* hh = reinterpret_cast<uint16_t*>(smem_raw + (stgH - smem_u32(smem_raw)));
+              uint16_t* ll = reinterpret_cast<uint16_t*>(smem_raw + (stgL - smem_u32(smem_raw)));
+              if (op_fmt == OP_F16) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hh[j * 32 + lane] = f32_to_f16_bits(v[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  uint16_t h16, l16;
+                  f32_to_bf16x2_bits(v[j], h16, l16);
+                  hh[j * 32 + lane] = h16;
+                  ll[j * 32 + lane] = l16;
+                }
+              }
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int x0 = transposed ? row0 : colg0;
+            const int x1 = transposed ? colg0 : row0;
+            if (sg.out32 != nullptr) {
+              if (tmode & TM_RED) tma_reduce_add_3d(&em.m[si][0], stgA, x0, x1, outer);
+              else tma_store_3d(&em.m[si][0], stgA, x0, x1, outer);
+            }
+            if (has_op) {
+              tma_store_3d(&em.m[si][2], stgH, x0, x1, outer);
+              if (op_fmt != OP_F16) tma_store_3d(&em.m[si][3], stgL, x0, x1, outer);
+            }
+            tma_commit();
+          }
+          stores_pending = true;
+          continue;
+        }
+
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
         if (!(flags & EPI_TRANSPOSED)) {
           // ---- row-major destination: transpose the 32x32 block through smem so that a warp
           // instruction touches ONE row (128 contiguous bytes) instead of 32 rows.
@@ -331,6 +537,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
     }
+    if (lane == 0) tma_wait_all0();   // bulk stores must have fully completed before the CTA exits
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -352,6 +560,7 @@ int g_num_sms = 0;
 std::once_flag g_init_once;
 int g_init_status = 0;
 std::atomic<unsigned long long> g_launches{0};
+bool g_force_generic = false;   // MCM_GENERIC_EPILOGUE=1: disable the TMA epilogue (A/B testing, debugging)
 
 int do_init() {
   void* fn = nullptr;
@@ -365,7 +574,8 @@ int do_init() {
   MCM_CUDA(cudaGetDeviceProperties(&prop, dev));
   MCM_CHECK(prop.major == 10, "motioncraft_b200 needs an sm_100a (B200) device; there is no fallback path");
   g_num_sms = prop.multiProcessorCount;
-  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
+  if (const char* e = getenv("MCM_GENERIC_EPILOGUE")) g_force_generic = (e[0] == '1');
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   return 0;
 }
 
@@ -391,11 +601,90 @@ int make_map(CUtensorMap* m, const void* ptr, int fmt, int k_dim, int rows, int 
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// 3-D tensor map of an epilogue destination / addend: dims {d0, d1, d2} (d0 contiguous), 32 x 32 x 1 boxes
+int make_epi_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, long long d0, long long d1,
+                 long long d2, long long stride1_elems, long long stride2_elems, CUtensorMapSwizzle sw) {
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)stride1_elems * esize, (cuuint64_t)stride2_elems * esize};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, dt, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (epilogue map) failed with CUresult " + std::to_string((int)r));
+    return 1;
+  }
+  return 0;
+}
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Decide whether segment `sg` can use the TMA epilogue and build its maps.  Falls back (mode 0) whenever an
+// alignment rule of bulk tensor copies does not hold (e.g. the [B*T, 322] eps output: 1288-byte rows).
+int setup_epi_maps(const GemmProblem& q, const EpiSeg& sg, int M_pad, int* mode, CUtensorMap* maps) {
+  *mode = 0;
+  const bool transposed = (sg.flags & EPI_TRANSPOSED) != 0;
+  const bool bcast = (sg.flags & EPI_ADDEND_BCAST) != 0;
+  const long long outer = q.batches / q.inner;
+  if (sg.out32 == nullptr && sg.op.hi == nullptr) return 0;
+  int md = TM_TMA;
+  bool ok = true;
+  if (sg.out32) ok = ok && al16(sg.out32) && (sg.ld32 % 4) == 0;
+  if (sg.op.hi) ok = ok && al16(sg.op.hi) && (sg.op.ld % 8) == 0 && (sg.op_fmt == OP_F16 || al16(sg.op.lo));
+  if (sg.addend) {
+    if (sg.addend == sg.out32 && sg.op.hi == nullptr && !bcast) md |= TM_RED;
+    else if (!transposed) { md |= TM_LDADD | (bcast ? TM_BCAST : 0); ok = ok && al16(sg.addend) && (sg.ld32 % 4) == 0; }
+    else ok = false;
+  }
+  if (!ok) return 0;
+  const long long col_end = (long long)sg.col0 + (long long)(q.inner - 1) * q.out_col_inner;
+  const CUtensorMapDataType opdt = sg.op_fmt == OP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if (!transposed) {
+    const long long rpo = q.out_rows_per_outer;
+    if (sg.out32) {
+      if (col_end + sg.n > sg.ld32) return 0;
+      MCM_TRY(make_epi_map(&maps[0], sg.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, col_end + sg.n, q.M, outer, sg.ld32,
+                           rpo * sg.ld32, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+    if (md & TM_LDADD) {
+      MCM_TRY(make_epi_map(&maps[1], sg.addend, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, col_end + sg.n, q.M, bcast ? 1 : outer,
+                           sg.ld32, (bcast ? (long long)q.M : rpo) * sg.ld32, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+    if (sg.op.hi) {
+      const long long ext = std::min<long long>(col_end + sg.n_pad, sg.op.ld);
+      MCM_TRY(make_epi_map(&maps[2], sg.op.hi, opdt, 2, ext, q.M, outer, sg.op.ld, rpo * sg.op.ld, CU_TENSOR_MAP_SWIZZLE_64B));
+      if (sg.op_fmt != OP_F16)
+        MCM_TRY(make_epi_map(&maps[3], sg.op.lo, opdt, 2, ext, q.M, outer, sg.op.ld, rpo * sg.op.ld, CU_TENSOR_MAP_SWIZZLE_64B));
+    }
+  } else {
+    // destination [(outer * trans_rows + c) * ld + r]: dims {r, c, outer}
+    if (sg.out32) {
+      if (q.M > sg.ld32) return 0;
+      MCM_TRY(make_epi_map(&maps[0], sg.out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, q.M, col_end + sg.n, outer, sg.ld32,
+                           (long long)q.trans_rows * sg.ld32, CU_TENSOR_MAP_SWIZZLE_NONE));
+    }
+    if (sg.op.hi) {
+      const long long rext = std::min<long long>(M_pad, sg.op.ld);
+      MCM_TRY(make_epi_map(&maps[2], sg.op.hi, opdt, 2, rext, col_end + sg.n, outer, sg.op.ld,
+                           (long long)q.trans_rows * sg.op.ld, CU_TENSOR_MAP_SWIZZLE_NONE));
+      if (sg.op_fmt != OP_F16)
+        MCM_TRY(make_epi_map(&maps[3], sg.op.lo, opdt, 2, rext, col_end + sg.n, outer, sg.op.ld,
+                             (long long)q.trans_rows * sg.op.ld, CU_TENSOR_MAP_SWIZZLE_NONE));
+    }
+  }
+  *mode = md;
+  return 0;
+}
 }  // namespace
 
+std::string g_init_error;
+
 int gemm_tc_init() {
-  std::call_once(g_init_once, [] { g_init_status = do_init(); });
-  if (g_init_status != 0) set_error("gemm_tc_init failed earlier (not an sm_100a device or no TMA driver entry point)");
+  std::call_once(g_init_once, [] {
+    g_init_status = do_init();
+    if (g_init_status != 0) g_init_error = mcm_last_error_string();
+  });
+  if (g_init_status != 0) set_error("gemm_tc_init failed: " + g_init_error);
   return g_init_status;
 }
 
@@ -443,7 +732,9 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   }
   const int bn_cap = split ? 128 : 256;
   const int tiles_for_max = (nmax + bn_cap - 1) / bn_cap;
-  p.block_n = std::min(bn_cap, round_up((nmax + tiles_for_max - 1) / tiles_for_max, 16));
+  // a segment split over several N tiles needs tiles of whole 32-column chunks: the TMA epilogue stores
+  // 32-wide boxes and must not spill into the neighbouring tile's columns
+  p.block_n = std::min(bn_cap, round_up((nmax + tiles_for_max - 1) / tiles_for_max, tiles_for_max > 1 ? 32 : 16));
   int tile0 = 0;
   for (int s = 0; s < q.nseg; ++s) {
     p.seg[s].tile0 = tile0;
@@ -463,6 +754,12 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   const uint32_t ab = split ? 1u : 0u;   // 0 = F16, 1 = BF16
   p.idesc = (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
+  EpiMaps em;
+  std::memset(&em, 0, sizeof(em));
+  for (int s = 0; s < q.nseg; ++s) {
+    MCM_TRY(setup_epi_maps(q, p.seg[s], p.M_pad, &p.tma_mode[s], em.m[s]));
+    if (g_force_generic) p.tma_mode[s] = 0;
+  }
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   MCM_TRY(make_map(&tmA, q.a.hi, q.fmt, q.a_k, q.a_rows, q.a_batches, q.a.ld, BLOCK_M));
   MCM_TRY(make_map(&tmB, q.b.hi, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n));
@@ -482,7 +779,7 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   }
   {
     LaunchTimer lt(LK_GEMM, stream, flops);
-    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BUDGET + 1024, stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmAlo, tmB, tmBlo, em, p);
   }
   MCM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
