@@ -58,9 +58,10 @@ struct OpPtr {       // a 16-bit operand tensor (hi, optional lo)
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint16_t f32_to_f16_bits(float v) {
-  // saturating: fp16 has a 65504 ceiling; anything larger would otherwise turn into inf -> NaN
-  v = fminf(fmaxf(v, -65504.f), 65504.f);
-  return __half_as_ushort(__float2half_rn(v));
+  // saturating (one F2FP.SATFINITE): fp16 has a 65504 ceiling; anything larger would otherwise turn into inf -> NaN
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return r;
 }
 __device__ __forceinline__ void f32_to_bf16x2_bits(float v, uint16_t& hi, uint16_t& lo) {
   __nv_bfloat16 h = __float2bfloat16_rn(v);

@@ -11,34 +11,84 @@ namespace {
 std::atomic<unsigned long long> g_ew_launches{0};
 constexpr int MAXV_LIMIT = 8;   // float4 per lane -> rows of up to 1024 elements
 
-__device__ __forceinline__ void op_store4(const OpPtr& o, int fmt, size_t idx, float a, float b, float c, float d) {
-  if (fmt == OP_F16) {
-    uint2 w;
-    w.x = (uint32_t)f32_to_f16_bits(a) | ((uint32_t)f32_to_f16_bits(b) << 16);
-    w.y = (uint32_t)f32_to_f16_bits(c) | ((uint32_t)f32_to_f16_bits(d) << 16);
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.hi) + idx) = w;
+// The row kernels were instruction-issue bound (ncu: 72-90 % issue-active at 2-2.5 TB/s), so the fp16
+// ("fast") operand path uses single-instruction saturating converts and MUFU-based exp / reciprocal
+// (relative error ~1e-6, far below the 2^-11 rounding of the fp16 value being produced); the bf16x2
+// ("precise") path keeps the IEEE expf / division so that mode stays a clean numerical reference.
+template <int FMT> __device__ __forceinline__ float exp_sel(float x) {
+  if (FMT == OP_F16) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+  }
+  return expf(x);
+}
+template <int FMT> __device__ __forceinline__ float silu_sel(float x) {
+  if (FMT == OP_F16) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return x * r;
+  }
+  return x / (1.f + expf(-x));
+}
+__device__ __forceinline__ uint32_t pk_f16(float a, float b) {   // lo half = a; saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint16_t cv_f16(float a) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pk_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// store 4 consecutive operand elements at element index idx (idx % 4 == 0)
+template <int FMT>
+__device__ __forceinline__ void st4(uint16_t* hi, uint16_t* lo, size_t idx, float a, float b, float c, float d) {
+  if (FMT == OP_F16) {
+    *reinterpret_cast<uint2*>(hi + idx) = make_uint2(pk_f16(a, b), pk_f16(c, d));
   } else {
-    uint16_t h[4], l[4];
-    f32_to_bf16x2_bits(a, h[0], l[0]);
-    f32_to_bf16x2_bits(b, h[1], l[1]);
-    f32_to_bf16x2_bits(c, h[2], l[2]);
-    f32_to_bf16x2_bits(d, h[3], l[3]);
-    uint2 wh, wl;
-    wh.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
-    wh.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
-    wl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
-    wl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.hi) + idx) = wh;
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.lo) + idx) = wl;
+    const uint32_t h0 = pk_bf16(a, b), h1 = pk_bf16(c, d);
+    const uint32_t l0 = pk_bf16(a - __uint_as_float(h0 << 16), b - __uint_as_float(h0 & 0xffff0000u));
+    const uint32_t l1 = pk_bf16(c - __uint_as_float(h1 << 16), d - __uint_as_float(h1 & 0xffff0000u));
+    *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l0, l1);
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void st1(uint16_t* hi, uint16_t* lo, size_t idx, float a) {
+  if (FMT == OP_F16) {
+    hi[idx] = cv_f16(a);
+  } else {
+    uint16_t h, l;
+    f32_to_bf16x2_bits(a, h, l);
+    hi[idx] = h;
+    lo[idx] = l;
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void st2(uint16_t* hi, uint16_t* lo, size_t idx, float a, float b) {   // idx % 2 == 0
+  if (FMT == OP_F16) {
+    *reinterpret_cast<uint32_t*>(hi + idx) = pk_f16(a, b);
+  } else {
+    const uint32_t h0 = pk_bf16(a, b);
+    *reinterpret_cast<uint32_t*>(hi + idx) = h0;
+    *reinterpret_cast<uint32_t*>(lo + idx) = pk_bf16(a - __uint_as_float(h0 << 16), b - __uint_as_float(h0 & 0xffff0000u));
   }
 }
 
 // ------------------------------------------------------------------------------------------ ln_rows
-template <int MAXV>
+template <int MAXV, int FMT>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const float* __restrict__ w,
                const float* __restrict__ b, const float* __restrict__ scale, const float* __restrict__ shift,
-               int mod_ld, int rows_per_batch, int act_silu, OpPtr out, int out_fmt) {
+               int mod_ld, int rows_per_batch, int act_silu, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo,
+               int out_ld) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -70,31 +120,31 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
   const int batch = row / rows_per_batch;
   const float* sc = scale ? scale + (size_t)batch * mod_ld : nullptr;
   const float* sh = shift ? shift + (size_t)batch * mod_ld : nullptr;
-  const int nvo = out.ld >> 2;
-  const size_t obase = (size_t)row * out.ld;
+  const int nvo = out_ld >> 2;
+  const size_t obase = (size_t)row * out_ld;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int q = i * 32 + lane;
     if (q < nv) {
-      const float4 ww = *reinterpret_cast<const float4*>(w + 4 * q);
-      const float4 bb = *reinterpret_cast<const float4*>(b + 4 * q);
-      float y[4] = {(v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y,
-                    (v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w};
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + 4 * q));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + 4 * q));
+      float y[4] = {fmaf((v[i].x - mean) * rstd, ww.x, bb.x), fmaf((v[i].y - mean) * rstd, ww.y, bb.y),
+                    fmaf((v[i].z - mean) * rstd, ww.z, bb.z), fmaf((v[i].w - mean) * rstd, ww.w, bb.w)};
       if (sc) {
-        const float4 s4 = *reinterpret_cast<const float4*>(sc + 4 * q);
-        const float4 h4 = *reinterpret_cast<const float4*>(sh + 4 * q);
-        y[0] = y[0] * (1.f + s4.x) + h4.x;
-        y[1] = y[1] * (1.f + s4.y) + h4.y;
-        y[2] = y[2] * (1.f + s4.z) + h4.z;
-        y[3] = y[3] * (1.f + s4.w) + h4.w;
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + 4 * q));
+        const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + 4 * q));
+        y[0] = fmaf(y[0], 1.f + s4.x, h4.x);
+        y[1] = fmaf(y[1], 1.f + s4.y, h4.y);
+        y[2] = fmaf(y[2], 1.f + s4.z, h4.z);
+        y[3] = fmaf(y[3], 1.f + s4.w, h4.w);
       }
       if (act_silu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = silu(y[j]);
+        for (int j = 0; j < 4; ++j) y[j] = silu_sel<FMT>(y[j]);
       }
-      op_store4(out, out_fmt, obase + 4 * q, y[0], y[1], y[2], y[3]);
+      st4<FMT>(ohi, olo, obase + 4 * q, y[0], y[1], y[2], y[3]);
     } else if (q < nvo) {
-      op_store4(out, out_fmt, obase + 4 * q, 0.f, 0.f, 0.f, 0.f);
+      st4<FMT>(ohi, olo, obase + 4 * q, 0.f, 0.f, 0.f, 0.f);
     }
   }
 }
@@ -103,10 +153,10 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
 // LPS lanes cooperate on one segment (EPL elements per lane, seg <= LPS * EPL); a warp handles 32 / LPS
 // consecutive segments.  Short segments (the 49-wide heads of the channel attention) use 8 lanes each so a
 // warp covers a whole 196-float row with four 32-byte-granular streams instead of wasting 3/4 of its lanes.
-template <int LPS, int EPL>
+template <int LPS, int EPL, int FMT>
 __global__ void __launch_bounds__(256)
 softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols, int ld_in, int seg, int nseg,
-                   OpPtr out, int out_fmt) {
+                   uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
   constexpr int SPW = 32 / LPS;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -115,13 +165,12 @@ softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols
   const bool active = gs < total_segs;
   const long long row = active ? gs / nseg : 0;
   const int sidx = active ? (int)(gs - row * nseg) : 0;
-  const float* x = in + (size_t)row * ld_in + (size_t)sidx * seg;
+  const float* x = in + (size_t)row * ld_in + (size_t)sidx * seg + sub;
   float v[EPL];
   float m = -INFINITY;
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    const int c = i * LPS + sub;
-    v[i] = (active && c < seg) ? x[c] : -INFINITY;
+    v[i] = (active && i * LPS + sub < seg) ? x[i * LPS] : -INFINITY;
     m = fmaxf(m, v[i]);
   }
 #pragma unroll
@@ -129,40 +178,38 @@ softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    const int c = i * LPS + sub;
-    v[i] = (active && c < seg) ? expf(v[i] - m) : 0.f;
+    v[i] = exp_sel<FMT>(v[i] - m);        // exp(-inf) = 0 for the lanes past the segment end
     s += v[i];
   }
 #pragma unroll
   for (int o = LPS / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (!active) return;
   const float inv = 1.f / s;
-  const size_t obase = (size_t)row * out.ld + (size_t)sidx * seg;
+  const size_t obase = (size_t)row * out_ld + (size_t)sidx * seg + sub;
 #pragma unroll
-  for (int i = 0; i < EPL; ++i) {
-    const int c = i * LPS + sub;
-    if (c < seg) op_store1(out, out_fmt, obase + c, v[i] * inv);
-  }
+  for (int i = 0; i < EPL; ++i)
+    if (i * LPS + sub < seg) st1<FMT>(ohi, olo, obase + i * LPS, v[i] * inv);
   if (sidx == nseg - 1) {
-    for (int c = ncols + sub; c < out.ld; c += LPS) op_store1(out, out_fmt, (size_t)row * out.ld + c, 0.f);
+    for (int c = ncols + sub; c < out_ld; c += LPS) st1<FMT>(ohi, olo, (size_t)row * out_ld + c, 0.f);
   }
 }
 
 // ------------------------------------------------------------------------------------------ ln_transpose
 // grid (D/32, B), block (32, 8).  tile[t][dx] (+1 pad) holds h[b, t, d0 + dx].
+template <int FMT>
 __global__ void __launch_bounds__(256)
 ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __restrict__ w,
-                    const float* __restrict__ b, OpPtr out, int out_fmt) {
+                    const float* __restrict__ b, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
   extern __shared__ float tile[];            // T * 33
   __shared__ float red[8][33];
   __shared__ float mean_s[32], rstd_s[32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int d0 = blockIdx.x * 32;
   const int bidx = blockIdx.y;
-  const float* src = h + (size_t)bidx * T * D + d0;
+  const float* src = h + (size_t)bidx * T * D + d0 + tx;
   float s = 0.f;
   for (int t = ty; t < T; t += 8) {
-    const float val = src[(size_t)t * D + tx];
+    const float val = src[(size_t)t * D];
     tile[t * 33 + tx] = val;
     s += val;
   }
@@ -190,13 +237,14 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
     rstd_s[tx] = rsqrtf(tot / (float)T + 1e-5f);
   }
   __syncthreads();
-  // write: warp ty handles columns dl = ty, ty+8, ...; lanes run along t (contiguous in the output)
+  // write: warp ty handles columns dl = ty, ty+8, ...; each lane writes two consecutive t (one 32-bit store)
   for (int dl = ty; dl < 32; dl += 8) {
     const float mu = mean_s[dl], rs = rstd_s[dl];
-    const size_t obase = ((size_t)bidx * D + d0 + dl) * out.ld;
-    for (int t = tx; t < out.ld; t += 32) {
-      const float y = (t < T) ? (tile[t * 33 + dl] - mu) * rs * w[t] + b[t] : 0.f;
-      op_store1(out, out_fmt, obase + t, y);
+    const size_t obase = ((size_t)bidx * D + d0 + dl) * out_ld;
+    for (int t = 2 * tx; t < out_ld; t += 64) {
+      const float y0 = (t < T) ? fmaf((tile[t * 33 + dl] - mu) * rs, __ldg(w + t), __ldg(b + t)) : 0.f;
+      const float y1 = (t + 1 < T) ? fmaf((tile[(t + 1) * 33 + dl] - mu) * rs, __ldg(w + t + 1), __ldg(b + t + 1)) : 0.f;
+      st2<FMT>(ohi, olo, obase + t, y0, y1);
     }
   }
 }
@@ -296,7 +344,8 @@ inline int grid_for(size_t total, int block) {
 }  // namespace
 
 int elementwise_init() {
-  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_BF16X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
   return 0;
 }
 unsigned long long elementwise_launch_count() { return g_ew_launches.load(); }
@@ -311,19 +360,23 @@ int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, 
   const int grid = (rows + wpb - 1) / wpb;
   const int rpb = rows_per_batch > 0 ? rows_per_batch : 1;
   const int nv = (out.ld / 4 + 31) / 32;      // float4 per lane needed to cover the (padded) row
+  uint16_t* hi = reinterpret_cast<uint16_t*>(out.hi);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
   LaunchTimer lt(LK_ROW, stream);
-#define MCM_LN_CASE(V)                                                                                          \
-  case V:                                                                                                       \
-    ln_rows_kernel<V><<<grid, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld, rpb,       \
-                                                     act_silu ? 1 : 0, out, out_fmt);                           \
+#define MCM_LN_GO(V, F)                                                                                          \
+  ln_rows_kernel<V, F><<<grid, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld, rpb,       \
+                                                      act_silu ? 1 : 0, hi, lo, out.ld)
+#define MCM_LN_CASE(V)                                                                                           \
+  case V:                                                                                                        \
+    if (out_fmt == OP_F16) MCM_LN_GO(V, OP_F16); else MCM_LN_GO(V, OP_BF16X2);                                   \
     break;
   switch (nv) {
     MCM_LN_CASE(1) MCM_LN_CASE(2) MCM_LN_CASE(3) MCM_LN_CASE(4) MCM_LN_CASE(5) MCM_LN_CASE(6) MCM_LN_CASE(7)
     default:
-      ln_rows_kernel<8><<<grid, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld, rpb,
-                                                       act_silu ? 1 : 0, out, out_fmt);
+      if (out_fmt == OP_F16) MCM_LN_GO(8, OP_F16); else MCM_LN_GO(8, OP_BF16X2);
   }
 #undef MCM_LN_CASE
+#undef MCM_LN_GO
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -336,13 +389,17 @@ int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg,
   const int nseg = ncols / seg;
   const long long total = (long long)rows * nseg;
   const int wpb = 8;
+  uint16_t* hi = reinterpret_cast<uint16_t*>(out.hi);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
   LaunchTimer lt(LK_ROW, stream);
-#define MCM_SM_LAUNCH(LPS, EPL)                                                                                  \
+#define MCM_SM_GO(LPS, EPL, F)                                                                                   \
   {                                                                                                              \
     const long long warps = (total + (32 / LPS) - 1) / (32 / LPS);                                               \
-    softmax_seg_kernel<LPS, EPL><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(                  \
-        in, total, ncols, ld_in, seg, nseg, out, out_fmt);                                                       \
+    softmax_seg_kernel<LPS, EPL, F><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(               \
+        in, total, ncols, ld_in, seg, nseg, hi, lo, out.ld);                                                     \
   }
+#define MCM_SM_LAUNCH(LPS, EPL)                                                                                  \
+  { if (out_fmt == OP_F16) MCM_SM_GO(LPS, EPL, OP_F16) else MCM_SM_GO(LPS, EPL, OP_BF16X2) }
   if (seg <= 16) MCM_SM_LAUNCH(8, 2)
   else if (seg <= 32) MCM_SM_LAUNCH(8, 4)
   else if (seg <= 64) MCM_SM_LAUNCH(8, 8)
@@ -352,6 +409,7 @@ int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg,
   else if (seg <= 512) MCM_SM_LAUNCH(32, 16)
   else MCM_SM_LAUNCH(32, 32)
 #undef MCM_SM_LAUNCH
+#undef MCM_SM_GO
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -359,10 +417,15 @@ int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg,
 
 int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, const float* b, OpPtr out, int out_fmt,
                         cudaStream_t stream) {
-  MCM_CHECK(D % 32 == 0 && T <= 1024 && out.ld >= T, "ln_transpose: need D % 32 == 0, T <= 1024");
+  MCM_CHECK(D % 32 == 0 && T <= 1024 && out.ld >= T && out.ld % 2 == 0, "ln_transpose: need D % 32 == 0, T <= 1024");
   dim3 grid(D / 32, B), block(32, 8);
+  uint16_t* hi = reinterpret_cast<uint16_t*>(out.hi);
+  uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
   LaunchTimer lt(LK_ROW, stream);
-  ln_transpose_kernel<<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, out, out_fmt);
+  if (out_fmt == OP_F16)
+    ln_transpose_kernel<OP_F16><<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, hi, lo, out.ld);
+  else
+    ln_transpose_kernel<OP_BF16X2><<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, hi, lo, out.ld);
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
