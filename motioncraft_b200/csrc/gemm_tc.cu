@@ -26,17 +26,20 @@ constexpr int NUM_EPI_WARPS = 8;          // multiple of 4 (TMEM lane quadrants)
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int STG_BYTES = 8192;            // per epilogue warp: 4 KB fp32 tile | 2 KB 16-bit hi | 2 KB 16-bit lo
-constexpr int SMEM_TOTAL = 224 * 1024;     // dynamic shared memory request (+ ~1.3 KB static <= 227 KB)
-constexpr int SMEM_BUDGET = SMEM_TOTAL - 1024 - NUM_EPI_WARPS * STG_BYTES;   // operand ring
+constexpr int SMEM_TOTAL = 230400;         // dynamic shared memory request (+ ~1.3 KB static <= 227 KB)
+// epilogue staging per warp: 4 KB (an fp32 tile, or 16-bit hi [+ lo]) or 8 KB when a segment writes fp32 AND an operand
 
 struct KParams {
   int M, M_pad, K, batches, inner, a_k_inner, b_batched, out_col_inner, out_rows_per_outer,
       trans_rows, head_dim;
   int block_n, m_tiles, n_tiles, num_kb, stages, split, total_tiles;
+  int stg_bytes;        // per-warp epilogue staging bytes (4096 or 8192)
+  int cs, m_supers;     // cluster size (CTAs sharing one multicast B tile) and ceil(m_tiles / cs)
   uint32_t idesc, stage_bytes, a_bytes, b_bytes;
   int nseg;
   EpiSeg seg[3];
+  int prefetch;         // producer issues L2 prefetches for the next work item's A tile
+  int debug;            // MCM_DEBUG_EPI: 1 = skip staging + stores, 2 = also skip the TMEM read (timing experiments only)
   int tma_mode[3];      // per segment: 0 = generic epilogue, else bit0 TMA epilogue, bit1 residual via TMA reduce-add,
                         // bit2 addend TMA-loaded, bit3 addend broadcast over batches
 };
@@ -46,6 +49,32 @@ struct EpiMaps {        // [segment][0 = fp32 out, 1 = fp32 addend, 2 = op hi, 3
 };
 
 enum { TM_TMA = 1, TM_RED = 2, TM_LDADD = 4, TM_BCAST = 8 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// B slice load, delivered to the same smem offset (and signalled on the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_3d_mc(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const void* desc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(desc), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 
 __device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -98,6 +127,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (x >= 0.f ? 2.f - pe : pe);
 }
 
+template <bool WITH_GENERIC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -127,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(smem_u32(&full_bar[s]), 1);
-        mbar_init(smem_u32(&empty_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), (uint32_t)p.cs);   // one tcgen05.commit arrival from every CTA of the cluster
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(smem_u32(&tfull_bar[s]), 1);
@@ -141,8 +171,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const int crank = p.cs > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / p.cs;
+  const int n_clusters = gridDim.x / p.cs;
+  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -150,11 +185,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = p.stage_bytes;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
         const int n_tile = tile % p.n_tiles;
         const int t2 = tile / p.n_tiles;
-        const int m_blk = t2 % p.m_tiles;
-        const int batch = t2 / p.m_tiles;
+        const int m_blk = (t2 % p.m_supers) * p.cs + crank;
+        const int batch = t2 / p.m_supers;
         const int outer = batch / p.inner;
         const int inner = batch - outer * p.inner;
         int si = 0;
@@ -163,19 +198,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int a_k0 = inner * p.a_k_inner;
         const int a_z = outer;
         const int b_z = p.b_batched ? batch : 0;
+        if (p.prefetch) {
+          // pull the NEXT work item's A rows (activations, usually DRAM-resident) into L2 while this one is loaded
+          const int nt = tile + n_clusters;
+          if (nt < p.total_tiles) {
+            const int nt2 = nt / p.n_tiles;
+            const int nm = (nt2 % p.m_supers) * p.cs + crank;
+            const int nbatch = nt2 / p.m_supers;
+            const int nouter = nbatch / p.inner;
+            const int nk0 = (nbatch - nouter * p.inner) * p.a_k_inner;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+              tma_prefetch_3d(&tmA, nk0 + kb * BLOCK_K, nm * BLOCK_M, nouter);
+              if (p.split) tma_prefetch_3d(&tmAlo, nk0 + kb * BLOCK_K, nm * BLOCK_M, nouter);
+            }
+          }
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           mbar_expect_tx(bar, tx);
+          // A: this CTA's own 128 rows.  B: this CTA fetches rows [crank, crank+1) * block_n / cs of the tile and
+          // multicasts them to every CTA of the cluster (each CTA's barrier counts the whole tile's bytes).
+          const int slice_rows = p.block_n / p.cs;
+          const int b_r = b_row + crank * slice_rows;
+          const uint32_t b_off = (uint32_t)(crank * slice_rows) * (BLOCK_K * 2);
           if (!p.split) {
             tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            tma_load_3d(&tmB, bar, sa + p.a_bytes, kb * BLOCK_K, b_row, b_z);
+            if (p.cs > 1) tma_load_3d_mc(&tmB, bar, sa + p.a_bytes + b_off, kb * BLOCK_K, b_r, b_z, cmask);
+            else tma_load_3d(&tmB, bar, sa + p.a_bytes, kb * BLOCK_K, b_row, b_z);
           } else {
             tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
             tma_load_3d(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            tma_load_3d(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_row, b_z);
-            tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_row, b_z);
+            if (p.cs > 1) {
+              tma_load_3d_mc(&tmB, bar, sa + 2 * p.a_bytes + b_off, kb * BLOCK_K, b_r, b_z, cmask);
+              tma_load_3d_mc(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes + b_off, kb * BLOCK_K, b_r, b_z, cmask);
+            } else {
+              tma_load_3d(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_row, b_z);
+              tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_row, b_z);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -187,7 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
@@ -216,7 +277,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_f16(taddr, ah, bh, p.idesc, 1u);
             }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));   // smem stage reusable once these MMAs retire
+          // the stage is rewritten by multicasts from every CTA of the cluster: release it on all of them
+          if (p.cs > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), cmask);
+          else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
@@ -231,20 +294,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int chunk_phase = ew >> 2;                  // which of the interleaved chunk sets this warp takes
     // per-warp staging region behind the operand ring (1024-byte aligned: TMA swizzle patterns are
     // functions of the absolute shared-memory address)
-    const uint32_t stgA = smem_base + (uint32_t)p.stages * p.stage_bytes + (uint32_t)ew * STG_BYTES;
-    const uint32_t stgH = stgA + 4096, stgL = stgA + 6144;
-    float* stg = reinterpret_cast<float*>(smem_raw + (stgA - smem_u32(smem_raw)));   // generic path: [32][33] floats
+    const uint32_t stg_base = smem_base + (uint32_t)p.stages * p.stage_bytes + (uint32_t)(ew * p.stg_bytes);
+    float* stg = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw)));   // generic path: [32][33] floats
     const uint32_t my_abar = smem_u32(&abar[ew]);
     uint32_t abar_phase = 0;
-    bool stores_pending = false;
+    int pending_groups = 0;      // bulk-store groups of this warp that may still be reading the staging region
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int n_tile = tile % p.n_tiles;
       const int t2 = tile / p.n_tiles;
-      const int m_blk = t2 % p.m_tiles;
-      const int batch = t2 / p.m_tiles;
+      const int m_blk = (t2 % p.m_supers) * p.cs + crank;
+      const int batch = t2 / p.m_supers;
       const int outer = batch / p.inner;
       const int inner = batch - outer * p.inner;
       int si = 0;
@@ -257,35 +319,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int flags = sg.flags;
       const int op_fmt = sg.op_fmt;
 
+      // bias of this warp's (up to 4) chunks, fetched before waiting for the accumulator
+      constexpr int CSTRIDE = 32 * (NUM_EPI_WARPS / 4);
+      float bias_pre[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cb = nbase + chunk_phase * 32 + k * CSTRIDE + lane;
+        bias_pre[k] = (sg.bias != nullptr && chunk_phase * 32 + k * CSTRIDE + lane < p.block_n && cb < sg.n) ? __ldg(sg.bias + cb) : 0.f;
+      }
+      const int tmode_t = p.tma_mode[si];
+      // staging layout: a chunk that needs <= 4 KB (fp32 only, or 16-bit only) alternates between two 4 KB slots
+      const bool dbl = !(sg.out32 != nullptr && has_op);
+
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
 
-      for (int c0 = chunk_phase * 32; c0 < p.block_n; c0 += 32 * (NUM_EPI_WARPS / 4)) {
+      int kchunk = -1;
+      for (int c0 = chunk_phase * 32; c0 < p.block_n; c0 += CSTRIDE) {
+        ++kchunk;
         const int cbase = nbase + c0;                 // column within the segment of v[0]
         if (cbase >= sg.n_pad) break;                 // warp-uniform
         const int ncover = min(32, p.block_n - c0);   // columns of this chunk that belong to this tile
         const int nvalid = min(ncover, sg.n - cbase); // may be <= 0 (pad-only chunk)
         const int colg0 = sg.col0 + inner * p.out_col_inner + cbase;
-        const int tmode = p.tma_mode[si];
+        const int tmode = tmode_t;
         float v[32];
 
-        // The staging region may still be read by the previous chunk's bulk store.
-        if (stores_pending) {
+        // The staging slot may still be read by an earlier bulk store of this warp.
+        if (pending_groups > 0) {
           if (lane == 0) tma_wait_read0();
           __syncwarp();
-          stores_pending = false;
+          pending_groups = 0;
         }
+        const uint32_t stgA = stg_base;
+        const uint32_t stgH = dbl ? stg_base : stg_base + 4096u;          // `dbl`: the segment has ONE kind of output
+        const uint32_t stgL = dbl ? stg_base + 2048u : stg_base + 6144u;
         if (tmode & TM_TMA) {
           // ================= TMA epilogue: registers -> swizzled smem tile -> bulk tensor store =================
+          if (p.debug >= 2) continue;
           if ((tmode & TM_LDADD) && lane == 0) {       // fetch the addend tile while the accumulator is read
             mbar_expect_tx(my_abar, 4096);
             tma_load_3d(&em.m[si][1], my_abar, stgA, colg0, row0, (tmode & TM_BCAST) ? 0 : outer);
           }
-          float bias_r = 0.f;
-          if (sg.bias != nullptr && lane < nvalid) bias_r = __ldg(sg.bias + cbase + lane);
           tmem_ld_32x32(taddr + (uint32_t)c0, v);
-          bias_s[ew][lane] = bias_r;
+          bias_s[ew][lane] = kchunk == 0 ? bias_pre[0] : (kchunk == 1 ? bias_pre[1] : (kchunk == 2 ? bias_pre[2] : bias_pre[3]));
           __syncwarp();
           tmem_ld_wait();
           const bool transposed = (flags & EPI_TRANSPOSED) != 0;
@@ -330,6 +408,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (j >= nvalid || !rv) v[j] = 0.f;
           }
           __syncwarp();                                // every lane is done reading the addend tile
+          if (p.debug == 1) {
+            if (v[0] == 1.2345e-30f && v[17] == 3.3e-33f) bias_s[ew][lane] = v[5];   // keep the loads alive
+            continue;
+          }
           if (!transposed) {
             if (sg.out32 != nullptr) {
 #pragma unroll
@@ -399,9 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tma_commit();
           }
-          stores_pending = true;
+          ++pending_groups;
           continue;
         }
+        if (!WITH_GENERIC) continue;   // (never reached: the host launches the WITH_GENERIC instantiation if needed)
 
         tmem_ld_32x32(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -543,6 +626,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();     // no CTA may exit while peers still multicast into / arrive on its smem
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -560,6 +644,13 @@ int g_num_sms = 0;
 std::once_flag g_init_once;
 int g_init_status = 0;
 std::atomic<unsigned long long> g_launches{0};
+int g_debug_epi = 0;
+int g_prefetch = 0;                 // MCM_PREFETCH=1: producer issues L2 prefetches one work item ahead (measured: no gain)
+int g_stage_cap = MAX_STAGES;      // MCM_STAGES: cap on the operand ring depth (experiments)
+int g_max_cs = 1;                 // MCM_MAX_CLUSTER: largest cluster size the launcher may choose (1, 2 or 4).
+                                  // Multicast of the B tile is implemented and tested, but measured neutral on B200 for
+                                  // clusters <= 4 (the mainloop is bound by L2->SM ingest per SM, which multicast does not cut)
+int g_max_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters per cluster size (cudaOccupancyMaxActiveClusters)
 bool g_force_generic = false;   // MCM_GENERIC_EPILOGUE=1: disable the TMA epilogue (A/B testing, debugging)
 
 int do_init() {
@@ -575,7 +666,26 @@ int do_init() {
   MCM_CHECK(prop.major == 10, "motioncraft_b200 needs an sm_100a (B200) device; there is no fallback path");
   g_num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("MCM_GENERIC_EPILOGUE")) g_force_generic = (e[0] == '1');
-  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  if (const char* e = getenv("MCM_DEBUG_EPI")) g_debug_epi = atoi(e);
+  if (const char* e = getenv("MCM_PREFETCH")) g_prefetch = atoi(e);
+  if (const char* e = getenv("MCM_STAGES")) g_stage_cap = std::max(1, std::min(MAX_STAGES, atoi(e)));
+  if (const char* e = getenv("MCM_MAX_CLUSTER")) g_max_cs = std::max(1, std::min(4, atoi(e)));
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  for (int cs = 1; cs <= 4; cs *= 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g_num_sms / cs * cs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    g_max_clusters[cs] = n;
+  }
+  MCM_CHECK(g_max_clusters[1] > 0, "gemm_tc_kernel does not fit on this device");
   return 0;
 }
 
@@ -712,6 +822,8 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   p.head_dim = q.head_dim > 0 ? q.head_dim : 1;
   p.split = split;
   p.nseg = q.nseg;
+  p.debug = g_debug_epi;
+  p.prefetch = g_prefetch;
 
   int nmax = 0;
   for (int s = 0; s < q.nseg; ++s) {
@@ -730,11 +842,23 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
                    ? 4 : 1;
     nmax = std::max(nmax, sg.n_pad);
   }
+  p.m_tiles = (q.M + BLOCK_M - 1) / BLOCK_M;
+  // cluster size: CTAs of a cluster take consecutive M tiles of ONE (batch, N tile) and share its B tile by
+  // TMA multicast, cutting the L2 -> SM operand traffic that bounds these small-K GEMMs
+  int cs = 1;
+  for (int c = g_max_cs; c >= 2; c /= 2) {
+    const bool aligned = (q.batches == 1) ? (p.m_tiles >= c) : (p.m_tiles % c == 0);
+    if (aligned && g_max_clusters[c] > 0) { cs = c; break; }
+  }
+  p.cs = cs;
+  p.m_supers = (p.m_tiles + cs - 1) / cs;
   const int bn_cap = split ? 128 : 256;
   const int tiles_for_max = (nmax + bn_cap - 1) / bn_cap;
   // a segment split over several N tiles needs tiles of whole 32-column chunks: the TMA epilogue stores
   // 32-wide boxes and must not spill into the neighbouring tile's columns
-  p.block_n = std::min(bn_cap, round_up((nmax + tiles_for_max - 1) / tiles_for_max, tiles_for_max > 1 ? 32 : 16));
+  // ... and a tile is fetched as cs slices of whole 8-row swizzle atoms
+  const int gran = std::max(tiles_for_max > 1 ? 32 : 16, 8 * cs);
+  p.block_n = std::min(bn_cap, round_up((nmax + tiles_for_max - 1) / tiles_for_max, gran));
   int tile0 = 0;
   for (int s = 0; s < q.nseg; ++s) {
     p.seg[s].tile0 = tile0;
@@ -742,35 +866,40 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     tile0 += p.seg[s].n_tiles;
   }
   p.n_tiles = tile0;
-  p.m_tiles = (q.M + BLOCK_M - 1) / BLOCK_M;
-  p.num_kb = (q.K + BLOCK_K - 1) / BLOCK_K;
-  p.total_tiles = p.n_tiles * p.m_tiles * q.batches;
-  p.a_bytes = BLOCK_M * BLOCK_K * 2;
-  p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
-  p.stage_bytes = (split ? 2u : 1u) * (p.a_bytes + p.b_bytes);
-  p.stages = std::min(MAX_STAGES, (int)(SMEM_BUDGET / p.stage_bytes));
-  MCM_CHECK(p.stages >= 2, "tile does not fit a 2-stage pipeline");
-  // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a/b format, K-major both, N>>3, M>>4
-  const uint32_t ab = split ? 1u : 0u;   // 0 = F16, 1 = BF16
-  p.idesc = (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-
   EpiMaps em;
   std::memset(&em, 0, sizeof(em));
   for (int s = 0; s < q.nseg; ++s) {
     MCM_TRY(setup_epi_maps(q, p.seg[s], p.M_pad, &p.tma_mode[s], em.m[s]));
     if (g_force_generic) p.tma_mode[s] = 0;
   }
+  p.num_kb = (q.K + BLOCK_K - 1) / BLOCK_K;
+  p.total_tiles = p.n_tiles * p.m_supers * q.batches;   // cluster work items
+  p.a_bytes = BLOCK_M * BLOCK_K * 2;
+  p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  p.stage_bytes = (split ? 2u : 1u) * (p.a_bytes + p.b_bytes);
+  bool big_stg = false;
+  for (int s = 0; s < q.nseg; ++s)
+    big_stg = big_stg || !(p.tma_mode[s] & TM_TMA) || (p.seg[s].out32 != nullptr && p.seg[s].op.hi != nullptr);
+  p.stg_bytes = big_stg ? 8192 : 4096;
+  const int ring_budget = SMEM_TOTAL - 1024 - NUM_EPI_WARPS * p.stg_bytes;
+  p.stages = std::min(g_stage_cap, (int)(ring_budget / p.stage_bytes));
+  MCM_CHECK(p.stages >= 1, "tile does not fit in shared memory");
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a/b format, K-major both, N>>3, M>>4
+  const uint32_t ab = split ? 1u : 0u;   // 0 = F16, 1 = BF16
+  p.idesc = (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   MCM_TRY(make_map(&tmA, q.a.hi, q.fmt, q.a_k, q.a_rows, q.a_batches, q.a.ld, BLOCK_M));
-  MCM_TRY(make_map(&tmB, q.b.hi, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n));
+  MCM_TRY(make_map(&tmB, q.b.hi, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n / cs));
   if (split) {
     MCM_TRY(make_map(&tmAlo, q.a.lo, q.fmt, q.a_k, q.a_rows, q.a_batches, q.a.ld, BLOCK_M));
-    MCM_TRY(make_map(&tmBlo, q.b.lo, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n));
+    MCM_TRY(make_map(&tmBlo, q.b.lo, q.fmt, q.b_k, q.b_rows, q.b_batches, q.b.ld, p.block_n / cs));
   } else {
     tmAlo = tmA;
     tmBlo = tmB;
   }
-  const int grid = std::min(p.total_tiles, g_num_sms);
+  const int n_clusters = std::min(p.total_tiles, g_max_clusters[cs]);
+  const int grid = n_clusters * cs;
   double flops = q.algo_flops;
   if (flops <= 0.0) {
     long long ncols = 0;
@@ -779,7 +908,20 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   }
   {
     LaunchTimer lt(LK_GEMM, stream, flops);
-    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmAlo, tmB, tmBlo, em, p);
+    bool need_generic = false;
+    for (int s = 0; s < q.nseg; ++s) need_generic = need_generic || !(p.tma_mode[s] & TM_TMA);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t le = need_generic ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA, tmAlo, tmB, tmBlo, em, p)
+                                  : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, tmA, tmAlo, tmB, tmBlo, em, p);
+    MCM_CUDA(le);
   }
   MCM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);

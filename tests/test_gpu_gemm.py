@@ -45,3 +45,37 @@ def test_bad_arguments_return_error_not_crash():
         tc_linear(torch.zeros(0, 8).cuda(), torch.zeros(8, 8).cuda(), None, 0)
     with pytest.raises(McmError):
         tc_linear(torch.zeros(8, 8).cuda(), torch.zeros(8, 8).cuda(), None, 7)
+
+
+@pytest.mark.parametrize("env", [{"MCM_MAX_CLUSTER": "4"}, {"MCM_MAX_CLUSTER": "2", "MCM_PREFETCH": "1"},
+                                 {"MCM_GENERIC_EPILOGUE": "1"}])
+def test_kernel_variants_in_subprocess(env):
+    """Cluster-multicast (B tile shared by 2 / 4 CTAs), producer L2 prefetch and the non-TMA fallback epilogue
+    are selected by environment at library init, so each runs in a fresh process: GEMM shapes + a full denoise."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from motioncraft_b200.engine import test_linear, DenoiserEngine
+from tests import common as C
+g = torch.Generator().manual_seed(3)
+for (M, N, K) in [(515, 600, 75), (1000, 512, 322), (4096, 1024, 512), (130, 2440, 2048)]:
+    A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
+    got = test_linear(A.cuda(), W.cuda(), b.cuda(), 0)
+    ref = A.cuda().half().double() @ W.cuda().half().double().T + b.cuda().double()
+    assert C.rel_l2(got, ref) < 2e-6, (M, N, K)
+T, B = 60, 3
+sd = C.base_state(T)
+x, xf_out, xf_proj = C.inputs(B, T)
+want = C.oracle_forward(sd, x, 321, xf_proj, xf_out, torch.float64)
+eng = DenoiserEngine(C.hot(sd), seq_len=T, max_batch=B)
+eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda())
+assert C.rel_l2(eng.denoise(x.cuda(), 321), want) < 1e-3
+print("variant ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
