@@ -9,6 +9,8 @@
 //   16-bit GEMM operands are K-major rows with a pitch that is a multiple of 8 elements, pad columns 0.
 // The channel-attention ("SA") works on h^T without ever materialising a transposed fp32 tensor: the
 // transposing LayerNorm writes the operand (B*D rows x T), and GEMM epilogues write back transposed.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -50,6 +52,7 @@ using namespace mcm;
 struct mcm_ctx {
   mcm_config cfg;
   int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
+  int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
   bool finalized = false;
   bool cond_ready = false;
   int cond_batch = 0;
@@ -95,6 +98,9 @@ int alloc_op(mcm_ctx* c, OpPtr* o, size_t elems, int ld, bool with_lo) {
   return 0;
 }
 inline OpPtr view(const OpPtr& o, int ld) { return OpPtr{o.hi, o.lo, ld}; }
+inline OpPtr offs(const OpPtr& o, size_t elems) {
+  return OpPtr{reinterpret_cast<uint16_t*>(o.hi) + elems, o.lo ? reinterpret_cast<uint16_t*>(o.lo) + elems : nullptr, o.ld};
+}
 
 int get_param(mcm_ctx* c, const std::string& name, long long numel, const float** out) {
   auto it = c->params.find(name);
@@ -210,7 +216,7 @@ int build_block(mcm_ctx* c, const std::string& pfx, Block* b, int mod_off, cudaS
 // final GEMM also emits the 16-bit copy of the new h into c->hop in that format.
 // ---------------------------------------------------------------------------------------------
 int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int mod_ld, OpPtr final_op,
-              int final_op_fmt, cudaStream_t st) {
+              int final_op_fmt, cudaStream_t st, int b0 = 0) {
   const int T = c->T, Tp = c->Tp, D = c->D, F = c->F, H = c->H, hdT = c->hdT, hdD = c->hdD;
   const int ff = c->fmt_fast();
   const OpPtr opA_t = view(c->opA, Tp), opC_t = view(c->opC, Tp);
@@ -297,7 +303,7 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));
     g.a = opC_d; g.a_rows = T; g.a_k = D; g.a_batches = B;
-    g.b = k.ca_ctxT; g.b_rows = hdD; g.b_k = hdD; g.b_batches = B * H; g.b_batched = 1;
+    g.b = offs(k.ca_ctxT, (size_t)b0 * H * hdD * hdD); g.b_rows = hdD; g.b_k = hdD; g.b_batches = B * H; g.b_batched = 1;
     g.fmt = ff; g.M = T; g.K = hdD; g.batches = B * H; g.inner = H; g.a_k_inner = hdD;
     g.out_col_inner = hdD; g.out_rows_per_outer = T;
     g.nseg = 1;
@@ -359,6 +365,61 @@ int check_batch(mcm_ctx* c, int B) {
   return 0;
 }
 
+// joint_embed -> decoder layers (+ control branch) -> out, for samples [b0, b0 + B) of the current step
+int run_layers(mcm_ctx* c, int b0, int B, float* eps_out, cudaStream_t st) {
+  const int T = c->T, D = c->D, IN = c->IN;
+  const int fp = c->fmt_prec();
+  const size_t r0 = (size_t)b0 * T;           // first row of this chunk in per-sample tensors
+  {  // h = joint_embed(x) + sequence_embedding[:T]               (diffusion_transformer.py:215-218)
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = offs(c->xop, r0 * c->INp); g.a_rows = T; g.a_k = c->INp; g.a_batches = B;
+    g.b = c->w_joint; g.b_rows = D; g.b_k = c->INp; g.b_batches = 1;
+    g.fmt = fp; g.M = T; g.K = IN; g.batches = B; g.inner = 1;
+    g.out_rows_per_outer = T;
+    g.nseg = 1;
+    g.seg[0] = seg_default(D, 0);
+    g.seg[0].bias = c->b_joint; g.seg[0].addend = c->seq_emb; g.seg[0].flags = EPI_ADDEND_BCAST;
+    g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  const OpPtr none{nullptr, nullptr, 0};
+  const OpPtr hop_out = view(c->hop, D);
+  const int nL = c->nL, nC = (c->have_c ? c->nC : 0);
+  const float* mod = c->mod32 + (size_t)b0 * c->mod_total;
+  const int mld = c->mod_total;
+  // MCMTransformer.forward_test (mcm.py:93-102) / ControlT2MHalf_MCM.forward_test (controlnet_mcm.py:306-361)
+  MCM_TRY(run_block(c, c->blocks[0], B, c->h32, mod, mld, (nL == 1) ? hop_out : none, fp, st, b0));
+  for (int i = 1; i < nL; ++i) {
+    if (i <= nC) {
+      const int j = i - 1;
+      const Block& cb = c->blocks[nL + j];
+      const Ctrl& ct = c->ctrls[j];
+      if (j == 0) {  // c = copied_block(x = h + before_proj(c))      (controlnet_mcm.py:65-75)
+        GemmProblem g = linear_problem(offs(view(c->cc_op, D), r0 * D), B * T, ct.before_w, D, D, c->fmt_fast());
+        g.seg[0] = seg_default(D, 0);
+        g.seg[0].bias = ct.before_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->c32; g.seg[0].ld32 = D;
+        MCM_TRY(gemm_tc_launch(g, st));
+      }
+      MCM_TRY(run_block(c, cb, B, c->c32, mod, mld, view(c->c_op, D), c->fmt_fast(), st, b0));
+      {  // h = h + after_proj(c)                                       (:75,85 ; :341-349)
+        GemmProblem g = linear_problem(view(c->c_op, D), B * T, ct.after_w, D, D, c->fmt_fast());
+        g.seg[0] = seg_default(D, 0);
+        g.seg[0].bias = ct.after_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
+        MCM_TRY(gemm_tc_launch(g, st));
+      }
+    }
+    MCM_TRY(run_block(c, c->blocks[i], B, c->h32, mod, mld, (i == nL - 1) ? hop_out : none, fp, st, b0));
+  }
+  {  // eps = out(h)                                                (mcm.py:102)
+    GemmProblem g = linear_problem(hop_out, B * T, c->w_out, IN, D, fp);
+    g.seg[0] = seg_default(IN, 0);
+    g.seg[0].bias = c->b_out; g.seg[0].out32 = eps_out + r0 * IN; g.seg[0].ld32 = IN;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  return 0;
+}
+
 // the whole denoiser on x32/xop already in place: writes eps32
 int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float* eps_out, cudaStream_t st) {
   const int T = c->T, D = c->D, E = c->E, IN = c->IN;
@@ -379,53 +440,11 @@ int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float
     MCM_TRY(gemm_tc_launch(g, st));
   }
   MCM_TRY(run_mod(c, B, c->emb32, 0, (int)c->blocks.size(), st));
-  {  // h = joint_embed(x) + sequence_embedding[:T]               (:215-218)
-    GemmProblem g;
-    std::memset(&g, 0, sizeof(g));
-    g.a = c->xop; g.a_rows = T; g.a_k = c->INp; g.a_batches = B;
-    g.b = c->w_joint; g.b_rows = D; g.b_k = c->INp; g.b_batches = 1;
-    g.fmt = fp; g.M = T; g.K = IN; g.batches = B; g.inner = 1;
-    g.out_rows_per_outer = T;
-    g.nseg = 1;
-    g.seg[0] = seg_default(D, 0);
-    g.seg[0].bias = c->b_joint; g.seg[0].addend = c->seq_emb; g.seg[0].flags = EPI_ADDEND_BCAST;
-    g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
-    MCM_TRY(gemm_tc_launch(g, st));
-  }
-  const OpPtr none{nullptr, nullptr, 0};
-  const OpPtr hop_out = view(c->hop, D);
-  const int nL = c->nL, nC = (c->have_c ? c->nC : 0);
-  const float* mod = c->mod32;
-  const int mld = c->mod_total;
-  // MCMTransformer.forward_test (mcm.py:93-102) / ControlT2MHalf_MCM.forward_test (controlnet_mcm.py:306-361)
-  MCM_TRY(run_block(c, c->blocks[0], B, c->h32, mod, mld, (nL == 1) ? hop_out : none, fp, st));
-  for (int i = 1; i < nL; ++i) {
-    if (i <= nC) {
-      const int j = i - 1;
-      const Block& cb = c->blocks[nL + j];
-      const Ctrl& ct = c->ctrls[j];
-      if (j == 0) {  // c = copied_block(x = h + before_proj(c))      (controlnet_mcm.py:65-75)
-        GemmProblem g = linear_problem(view(c->cc_op, D), B * T, ct.before_w, D, D, c->fmt_fast());
-        g.seg[0] = seg_default(D, 0);
-        g.seg[0].bias = ct.before_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->c32; g.seg[0].ld32 = D;
-        MCM_TRY(gemm_tc_launch(g, st));
-      }
-      MCM_TRY(run_block(c, cb, B, c->c32, mod, mld, view(c->c_op, D), c->fmt_fast(), st));
-      {  // h = h + after_proj(c)                                       (:75,85 ; :341-349)
-        GemmProblem g = linear_problem(view(c->c_op, D), B * T, ct.after_w, D, D, c->fmt_fast());
-        g.seg[0] = seg_default(D, 0);
-        g.seg[0].bias = ct.after_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
-        MCM_TRY(gemm_tc_launch(g, st));
-      }
-    }
-    MCM_TRY(run_block(c, c->blocks[i], B, c->h32, mod, mld, (i == nL - 1) ? hop_out : none, fp, st));
-  }
-  {  // eps = out(h)                                                (mcm.py:102)
-    GemmProblem g = linear_problem(hop_out, B * T, c->w_out, IN, D, fp);
-    g.seg[0] = seg_default(IN, 0);
-    g.seg[0].bias = c->b_out; g.seg[0].out32 = eps_out; g.seg[0].ld32 = IN;
-    MCM_TRY(gemm_tc_launch(g, st));
-  }
+  // Layer stack, in chunks of `chunk` samples: every op is per-sample, so a chunk runs the whole stack on
+  // chunk-local activations (h, operands and fp32 scratch reuse the SAME addresses for every chunk) which then stay
+  // resident in the 126 MB L2 instead of bouncing through HBM between kernels.
+  const int chunk = c->chunk > 0 ? std::min(c->chunk, B) : B;
+  for (int b0 = 0; b0 < B; b0 += chunk) MCM_TRY(run_layers(c, b0, std::min(chunk, B - b0), eps_out, st));
   return 0;
 }
 
@@ -475,6 +494,7 @@ const char* mcm_version(void) { return "motioncraft_b200 0.1.0 (sm_100a, tcgen05
 unsigned long long mcm_gemm_launches(void) { return gemm_tc_launch_count(); }
 unsigned long long mcm_kernel_launches(void) { return gemm_tc_launch_count() + elementwise_launch_count(); }
 
+int mcm_debug_read(unsigned long long* out, int reset) { return gemm_tc_debug_read(out, reset); }
 void mcm_timing_enable(int on) { timing_enable(on != 0); }
 int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops) {
   MCM_CHECK(ms && launches && flops, "null argument");
@@ -500,6 +520,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   c->NTmax = cfg->max_text_tokens > 0 ? cfg->max_text_tokens : 77; c->NTp = rup(c->NTmax, 8);
   c->nL = cfg->num_layers; c->nC = cfg->num_ctrl_blocks; c->Cin = cfg->ctrl_cond_feats; c->Cinp = rup(c->Cin > 0 ? c->Cin : 8, 8);
   c->hdT = c->T / c->H; c->hdD = c->D / c->H; c->Bmax = cfg->max_batch;
+  if (const char* e = getenv("MCM_CHUNK")) c->chunk = atoi(e);
   c->mod_total = (c->nL + c->nC) * (2 * c->T + 4 * c->D);
 
   const size_t B = c->Bmax, R1 = B * c->T, R2 = B * c->D;

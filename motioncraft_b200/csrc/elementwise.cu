@@ -237,14 +237,16 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
     rstd_s[tx] = rsqrtf(tot / (float)T + 1e-5f);
   }
   __syncthreads();
-  // write: warp ty handles columns dl = ty, ty+8, ...; each lane writes two consecutive t (one 32-bit store)
+  // write: warp ty handles columns dl = ty, ty+8, ...; lanes run along t (conflict-free smem reads, stride 33);
+  // neighbouring lanes exchange values so every even lane emits one packed 32-bit store of two consecutive t
   for (int dl = ty; dl < 32; dl += 8) {
     const float mu = mean_s[dl], rs = rstd_s[dl];
     const size_t obase = ((size_t)bidx * D + d0 + dl) * out_ld;
-    for (int t = 2 * tx; t < out_ld; t += 64) {
-      const float y0 = (t < T) ? fmaf((tile[t * 33 + dl] - mu) * rs, __ldg(w + t), __ldg(b + t)) : 0.f;
-      const float y1 = (t + 1 < T) ? fmaf((tile[(t + 1) * 33 + dl] - mu) * rs, __ldg(w + t + 1), __ldg(b + t + 1)) : 0.f;
-      st2<FMT>(ohi, olo, obase + t, y0, y1);
+    for (int t0 = 0; t0 < out_ld; t0 += 32) {
+      const int t = t0 + tx;
+      const float y = (t < T) ? fmaf((tile[t * 33 + dl] - mu) * rs, __ldg(w + t), __ldg(b + t)) : 0.f;
+      const float yn = __shfl_down_sync(0xffffffffu, y, 1);
+      if ((tx & 1) == 0 && t < out_ld) st2<FMT>(ohi, olo, obase + t, y, yn);
     }
   }
 }

@@ -11,6 +11,7 @@
 #include "timing.cuh"
 
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -34,10 +35,12 @@ struct KParams {
       trans_rows, head_dim;
   int block_n, m_tiles, n_tiles, num_kb, stages, split, total_tiles;
   int stg_bytes;        // per-warp epilogue staging bytes (4096 or 8192)
+  int pair;             // 1: cta_group::2 -- a CTA pair computes a 256 x block_n tile, each CTA holds half of B
   int cs, m_supers;     // cluster size (CTAs sharing one multicast B tile) and ceil(m_tiles / cs)
   uint32_t idesc, stage_bytes, a_bytes, b_bytes;
   int nseg;
   EpiSeg seg[3];
+  unsigned long long* dbg;   // MCM_DEBUG_EPI=3: per-phase clock totals of the epilogue warps
   int prefetch;         // producer issues L2 prefetches for the next work item's A tile
   int debug;            // MCM_DEBUG_EPI: 1 = skip staging + stores, 2 = also skip the TMEM read (timing experiments only)
   int tma_mode[3];      // per segment: 0 = generic epilogue, else bit0 TMA epilogue, bit1 residual via TMA reduce-add,
@@ -70,6 +73,42 @@ __device__ __forceinline__ void tma_load_3d_mc(const void* desc, uint32_t bar, u
 __device__ __forceinline__ void tma_prefetch_3d(const void* desc, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                ::"l"(desc), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// ---- cta_group::2 (CTA pair) forms.  In a cluster, 32-bit shared addresses carry the CTA rank in bit 24, so
+// clearing it makes a barrier operand refer to the pair's leader (rank 0) -- the CUTLASS Sm100MmaPeerBitMask idiom.
+__device__ __forceinline__ void tma_load_3d_2sm(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(desc), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -127,7 +166,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (x >= 0.f ? 2.f - pe : pe);
 }
 
-template <bool WITH_GENERIC>
+template <bool WITH_GENERIC, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -157,17 +196,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(smem_u32(&full_bar[s]), 1);
-        mbar_init(smem_u32(&empty_bar[s]), (uint32_t)p.cs);   // one tcgen05.commit arrival from every CTA of the cluster
+        // multicast mode: one tcgen05.commit arrival from every CTA of the cluster; pair mode: one (the leader's)
+        mbar_init(smem_u32(&empty_bar[s]), PAIR ? 1u : (uint32_t)p.cs);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(smem_u32(&tfull_bar[s]), 1);
-        mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);   // one arrive per epilogue warp
+        mbar_init(smem_u32(&tempty_bar[s]), PAIR ? 2u * NUM_EPI_WARPS : (uint32_t)NUM_EPI_WARPS);   // per epilogue warp (of both CTAs)
       }
       for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(smem_u32(&abar[s]), 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+    if constexpr (PAIR) tmem_alloc_2sm(smem_u32(&tmem_slot), TMEM_COLS);
+    else tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -217,6 +258,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
+          if constexpr (PAIR) {
+            // CTA pair: each CTA loads its own A rows and its half of the B rows into its OWN smem; all bytes are
+            // accounted on the LEADER's barrier, which its MMA thread waits on.
+            if (crank == 0) mbar_expect_tx(bar, 2u * tx);
+            const int b_rp = b_row + crank * (p.block_n / 2);
+            tma_load_3d_2sm(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
+            if (!p.split) {
+              tma_load_3d_2sm(&tmB, bar, sa + p.a_bytes, kb * BLOCK_K, b_rp, b_z);
+            } else {
+              tma_load_3d_2sm(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
+              tma_load_3d_2sm(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_rp, b_z);
+              tma_load_3d_2sm(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_rp, b_z);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(bar, tx);
           // A: this CTA's own 128 rows.  B: this CTA fetches rows [crank, crank+1) * block_n / cs of the tile and
           // multicasts them to every CTA of the cluster (each CTA's barrier counts the whole tile's bytes).
@@ -243,8 +300,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+    if (lane == 0 && !(PAIR && crank != 0)) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -260,6 +317,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const int kleft = p.K - kb * BLOCK_K;
           const int nk = kleft >= BLOCK_K ? BLOCK_K / UMMA_K : (kleft + UMMA_K - 1) / UMMA_K;
+          if constexpr (PAIR) {
+            if (!p.split) {
+              const uint32_t sb = sa + p.a_bytes;
+              for (int k = 0; k < nk; ++k)
+                umma_f16_2sm(taddr, make_smem_desc_sw128(sa + k * UMMA_K * 2), make_smem_desc_sw128(sb + k * UMMA_K * 2),
+                             p.idesc, (uint32_t)((kb | k) != 0));
+            } else {
+              const uint32_t sal = sa + p.a_bytes, sb = sa + 2 * p.a_bytes, sbl = sb + p.b_bytes;
+              for (int k = 0; k < nk; ++k) {
+                const uint32_t o = k * UMMA_K * 2;
+                const uint64_t ah = make_smem_desc_sw128(sa + o), al = make_smem_desc_sw128(sal + o);
+                const uint64_t bh = make_smem_desc_sw128(sb + o), bl = make_smem_desc_sw128(sbl + o);
+                umma_f16_2sm(taddr, al, bh, p.idesc, (uint32_t)((kb | k) != 0));
+                umma_f16_2sm(taddr, ah, bl, p.idesc, 1u);
+                umma_f16_2sm(taddr, ah, bh, p.idesc, 1u);
+              }
+            }
+            umma_commit_2sm(smem_u32(&empty_bar[stage]), (uint16_t)3);   // frees the stage in BOTH CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           if (!p.split) {
             const uint32_t sb = sa + p.a_bytes;
             for (int k = 0; k < nk; ++k) {
@@ -282,7 +360,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
+        if constexpr (PAIR) umma_commit_2sm(smem_u32(&tfull_bar[acc]), (uint16_t)3);   // both CTAs' epilogues
+        else umma_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
       }
     }
   } else {
@@ -299,6 +378,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t my_abar = smem_u32(&abar[ew]);
     uint32_t abar_phase = 0;
     int pending_groups = 0;      // bulk-store groups of this warp that may still be reading the staging region
+    long long tph[6] = {0, 0, 0, 0, 0, 0};   // debug: cycles in [wait acc | wait staging | tmem ld | math | stage+issue | chunks]
+    const bool prof = p.debug == 3;
+#define MCM_TICK(i) do { if (prof) { const long long _n = clock64(); tph[i] += _n - tlast; tlast = _n; } } while (0)
+    long long tlast = prof ? clock64() : 0;
     int it = 0;
     for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
       const int acc = it & 1;
@@ -333,6 +416,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
+      MCM_TICK(0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
 
       int kchunk = -1;
@@ -352,12 +436,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           pending_groups = 0;
         }
+        MCM_TICK(1);
         const uint32_t stgA = stg_base;
         const uint32_t stgH = dbl ? stg_base : stg_base + 4096u;          // `dbl`: the segment has ONE kind of output
         const uint32_t stgL = dbl ? stg_base + 2048u : stg_base + 6144u;
         if (tmode & TM_TMA) {
           // ================= TMA epilogue: registers -> swizzled smem tile -> bulk tensor store =================
-          if (p.debug >= 2) continue;
+          if (p.debug == 2) continue;
           if ((tmode & TM_LDADD) && lane == 0) {       // fetch the addend tile while the accumulator is read
             mbar_expect_tx(my_abar, 4096);
             tma_load_3d(&em.m[si][1], my_abar, stgA, colg0, row0, (tmode & TM_BCAST) ? 0 : outer);
@@ -366,6 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bias_s[ew][lane] = kchunk == 0 ? bias_pre[0] : (kchunk == 1 ? bias_pre[1] : (kchunk == 2 ? bias_pre[2] : bias_pre[3]));
           __syncwarp();
           tmem_ld_wait();
+          MCM_TICK(2);
           const bool transposed = (flags & EPI_TRANSPOSED) != 0;
           if (sg.bias != nullptr) {
 #pragma unroll
@@ -408,6 +494,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (j >= nvalid || !rv) v[j] = 0.f;
           }
           __syncwarp();                                // every lane is done reading the addend tile
+          MCM_TICK(3);
           if (p.debug == 1) {
             if (v[0] == 1.2345e-30f && v[17] == 3.3e-33f) bias_s[ew][lane] = v[5];   // keep the loads alive
             continue;
@@ -482,6 +569,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_commit();
           }
           ++pending_groups;
+          MCM_TICK(4);
+          if (prof) tph[5] += 1;
           continue;
         }
         if (!WITH_GENERIC) continue;   // (never reached: the host launches the WITH_GENERIC instantiation if needed)
@@ -618,10 +707,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_remote(smem_u32(&tempty_bar[acc]), 0u);   // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(smem_u32(&tempty_bar[acc]));
+      }
     }
     if (lane == 0) tma_wait_all0();   // bulk stores must have fully completed before the CTA exits
     __syncwarp();
+    if (prof && lane == 0 && p.dbg != nullptr) {
+      for (int i = 0; i < 6; ++i) atomicAdd(p.dbg + i, (unsigned long long)tph[i]);
+    }
+#undef MCM_TICK
   }
 
   tc_fence_before();
@@ -629,7 +725,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.cs > 1) cluster_sync_all();     // no CTA may exit while peers still multicast into / arrive on its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -645,11 +742,15 @@ std::once_flag g_init_once;
 int g_init_status = 0;
 std::atomic<unsigned long long> g_launches{0};
 int g_debug_epi = 0;
+unsigned long long* g_dbg = nullptr;
+int g_pair = 0;                     // MCM_PAIR=1 enables cta_group::2 pair tiles (256 x block_n per CTA pair; validated,
+                                    // -5..10 % mainloop time but a slower epilogue overlap: net neutral this round)
 int g_prefetch = 0;                 // MCM_PREFETCH=1: producer issues L2 prefetches one work item ahead (measured: no gain)
 int g_stage_cap = MAX_STAGES;      // MCM_STAGES: cap on the operand ring depth (experiments)
 int g_max_cs = 1;                 // MCM_MAX_CLUSTER: largest cluster size the launcher may choose (1, 2 or 4).
                                   // Multicast of the B tile is implemented and tested, but measured neutral on B200 for
                                   // clusters <= 4 (the mainloop is bound by L2->SM ingest per SM, which multicast does not cut)
+int g_max_pairs = 0;              // co-resident CTA pairs of the cta_group::2 instantiation
 int g_max_clusters[5] = {0, 0, 0, 0, 0};   // co-resident clusters per cluster size (cudaOccupancyMaxActiveClusters)
 bool g_force_generic = false;   // MCM_GENERIC_EPILOGUE=1: disable the TMA epilogue (A/B testing, debugging)
 
@@ -668,10 +769,13 @@ int do_init() {
   if (const char* e = getenv("MCM_GENERIC_EPILOGUE")) g_force_generic = (e[0] == '1');
   if (const char* e = getenv("MCM_DEBUG_EPI")) g_debug_epi = atoi(e);
   if (const char* e = getenv("MCM_PREFETCH")) g_prefetch = atoi(e);
+  if (const char* e = getenv("MCM_PAIR")) g_pair = atoi(e);
   if (const char* e = getenv("MCM_STAGES")) g_stage_cap = std::max(1, std::min(MAX_STAGES, atoi(e)));
   if (const char* e = getenv("MCM_MAX_CLUSTER")) g_max_cs = std::max(1, std::min(4, atoi(e)));
-  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  MCM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   for (int cs = 1; cs <= 4; cs *= 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g_num_sms / cs * cs);
@@ -682,10 +786,19 @@ int do_init() {
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<false, false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
     g_max_clusters[cs] = n;
+    if (cs == 2) {
+      int np = 0;
+      if (cudaOccupancyMaxActiveClusters(&np, gemm_tc_kernel<false, true>, &cfg) != cudaSuccess) { cudaGetLastError(); np = 0; }
+      g_max_pairs = np;
+    }
   }
   MCM_CHECK(g_max_clusters[1] > 0, "gemm_tc_kernel does not fit on this device");
+  if (g_debug_epi == 3) {
+    MCM_CUDA(cudaMalloc(&g_dbg, 8 * sizeof(unsigned long long)));
+    MCM_CUDA(cudaMemset(g_dbg, 0, 8 * sizeof(unsigned long long)));
+  }
   return 0;
 }
 
@@ -800,6 +913,15 @@ int gemm_tc_init() {
 
 unsigned long long gemm_tc_launch_count() { return g_launches.load(); }
 
+int gemm_tc_debug_read(unsigned long long* out, int reset) {
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (g_dbg == nullptr) return 0;
+  MCM_CUDA(cudaDeviceSynchronize());
+  MCM_CUDA(cudaMemcpy(out, g_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) MCM_CUDA(cudaMemset(g_dbg, 0, 8 * sizeof(unsigned long long)));
+  return 0;
+}
+
 int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   MCM_TRY(gemm_tc_init());
   MCM_CHECK(q.nseg >= 1 && q.nseg <= 3, "1..3 output segments");
@@ -824,6 +946,7 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   p.nseg = q.nseg;
   p.debug = g_debug_epi;
   p.prefetch = g_prefetch;
+  p.dbg = g_dbg;
 
   int nmax = 0;
   for (int s = 0; s < q.nseg; ++s) {
@@ -850,6 +973,13 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     const bool aligned = (q.batches == 1) ? (p.m_tiles >= c) : (p.m_tiles % c == 0);
     if (aligned && g_max_clusters[c] > 0) { cs = c; break; }
   }
+  // CTA pairs (cta_group::2): the two CTAs of a cluster compute one 256 x block_n tile, each holding its own 128 A rows
+  // and HALF of the B rows -- a third fewer operand bytes per MMA through the L2 -> SM path that bounds the mainloop.
+  p.pair = 0;
+  if (g_pair && g_max_pairs > 0 && ((q.batches == 1) ? (p.m_tiles >= 2) : (p.m_tiles % 2 == 0))) {
+    p.pair = 1;
+    cs = 2;
+  }
   p.cs = cs;
   p.m_supers = (p.m_tiles + cs - 1) / cs;
   const int bn_cap = split ? 128 : 256;
@@ -875,7 +1005,7 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   p.num_kb = (q.K + BLOCK_K - 1) / BLOCK_K;
   p.total_tiles = p.n_tiles * p.m_supers * q.batches;   // cluster work items
   p.a_bytes = BLOCK_M * BLOCK_K * 2;
-  p.b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  p.b_bytes = (uint32_t)(p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;   // per CTA
   p.stage_bytes = (split ? 2u : 1u) * (p.a_bytes + p.b_bytes);
   bool big_stg = false;
   for (int s = 0; s < q.nseg; ++s)
@@ -886,7 +1016,8 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   MCM_CHECK(p.stages >= 1, "tile does not fit in shared memory");
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a/b format, K-major both, N>>3, M>>4
   const uint32_t ab = split ? 1u : 0u;   // 0 = F16, 1 = BF16
-  p.idesc = (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  p.idesc = (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+            ((uint32_t)((p.pair ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
 
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   MCM_TRY(make_map(&tmA, q.a.hi, q.fmt, q.a_k, q.a_rows, q.a_batches, q.a.ld, BLOCK_M));
@@ -898,7 +1029,7 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     tmAlo = tmA;
     tmBlo = tmB;
   }
-  const int n_clusters = std::min(p.total_tiles, g_max_clusters[cs]);
+  const int n_clusters = std::min(p.total_tiles, p.pair ? g_max_pairs : g_max_clusters[cs]);
   const int grid = n_clusters * cs;
   double flops = q.algo_flops;
   if (flops <= 0.0) {
@@ -919,12 +1050,23 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t le = need_generic ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA, tmAlo, tmB, tmBlo, em, p)
-                                  : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, tmA, tmAlo, tmB, tmBlo, em, p);
+    cudaError_t le;
+    if (p.pair) le = need_generic ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true>, tmA, tmAlo, tmB, tmBlo, em, p)
+                                  : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, tmA, tmAlo, tmB, tmBlo, em, p);
+    else le = need_generic ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, false>, tmA, tmAlo, tmB, tmBlo, em, p)
+                           : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, false>, tmA, tmAlo, tmB, tmBlo, em, p);
     MCM_CUDA(le);
   }
   MCM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
+  if (g_debug_epi == 3 && getenv("MCM_DEBUG_PRINT")) {
+    unsigned long long d[8];
+    gemm_tc_debug_read(d, 1);
+    const double ch = d[5] ? (double)d[5] : 1.0;
+    fprintf(stderr, "gemm M=%d K=%d batches=%d bn=%d tiles=%d nseg=%d n0=%d flags0=%d tma=%d/%d/%d pair=%d | per chunk: acc %.0f stg %.0f ld %.0f math %.0f issue %.0f | chunks %llu\n",
+            q.M, q.K, q.batches, p.block_n, p.total_tiles, q.nseg, q.seg[0].n, q.seg[0].flags, p.tma_mode[0], p.tma_mode[1],
+            p.tma_mode[2], p.pair, d[0] / ch, d[1] / ch, d[2] / ch, d[3] / ch, d[4] / ch, d[5]);
+  }
   return 0;
 }
 

@@ -65,5 +65,7 @@ int gemm_tc_init();
 
 // number of tcgen05 GEMM launches since process start (bench.py's gpu_launches evidence)
 unsigned long long gemm_tc_launch_count();
+// MCM_DEBUG_EPI=3: summed epilogue-warp cycles per phase (development aid)
+int gemm_tc_debug_read(unsigned long long* out, int reset);
 
 }  // namespace mcm
