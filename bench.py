@@ -321,7 +321,11 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one sampling run)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["tflops"]) if achieved else None,
+                         # dram__bytes_read+write summed over the 85 GEMM launches of one denoise step (ncu, profiles/
+                         # r01_launches_step_t2m_final.csv: 13.4 GB) x 50 steps; only measured for the t2m workload
+                         "traffic": 13.406e9 * N_STEPS if (args.workload == "t2m" and B == 256) else None,
+                         "traffic_unit": "bytes per sampling run (all gemm_tc_kernel launches)",
                          "peak_source": peaks["source"], "algorithmic_gflop_per_frame": flops_run / (B * T) / 1e9,
                          "gemm_ms_per_run": gemm_ms, "gemm_launches_per_run": tm["gemm"]["launches"],
                          "row_kernel_ms_per_run": tm["row"]["ms"], "row_kernel_launches_per_run": tm["row"]["launches"],

@@ -221,3 +221,43 @@ def test_errors_are_reported_not_fatal():
     eng.close()
     with pytest.raises(McmError):
         DenoiserEngine({}, seq_len=60, max_batch=1)        # missing parameters
+
+
+@pytest.mark.parametrize("T,n_ctrl,c_feats,c_len", [(300, 2, 2048, 297), (1024, 4, 35, 1024)])
+def test_control_at_benchmark_shapes(T, n_ctrl, c_feats, c_len):
+    """BASELINE configs 2 (s2g: T=300, 2 control blocks, pre-encoded audio embedding [B, 297, 2048]) and 3 (m2d: T=1024,
+    4 control blocks, music features [B, 1024, 35]) at B=1 against the fp32 oracle."""
+    sd = synth.synth_state_dict(modules.ctrl_state_shapes(T, n_ctrl, c_feats))
+    x, xf_out, xf_proj = C.inputs(1, T)
+    c = synth.synth_tensor("c", (1, c_len, c_feats), synth.SEED_C_EMB)
+    t = torch.full((1,), 640, dtype=torch.long)
+    with torch.no_grad():
+        want = O.control_forward(sd, x, t, xf_proj, xf_out, c)
+    eng = DenoiserEngine(modules.engine_state_from_ctrl(sd), seq_len=T, max_batch=1, num_ctrl_blocks=n_ctrl,
+                         ctrl_cond_feats=c_feats)
+    eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda(), c.cuda())
+    assert C.rel_l2(eng.denoise(x.cuda(), 640), want) < TOL_FAST
+    eng.close()
+
+
+def test_full_batch_properties_t2m():
+    """BASELINE config 1 at FULL size (B=256, T=196): size-independent checks -- finite output, bit-determinism,
+    and rows of the big batch equal the same samples run alone (batch independence), plus oracle parity of 2 rows."""
+    T, B = 196, 256
+    sd = C.base_state(T)
+    x = synth.synth_rows("x_T", (T, 322), synth.SEED_XT, 0, B)
+    xf_out = synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, 0, B)
+    xf_proj = synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, 0, B)
+    tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
+    st = SamplerTables(tables, tmap, "ddim")
+    eng = _engine(T, B, False)
+    eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda())
+    x0 = eng.sample(st, x.cuda())
+    assert torch.isfinite(x0).all()
+    assert torch.equal(eng.sample(st, x.cuda()), x0)
+    sel = [3, 200]
+    eng.prepare_conditions(xf_out[sel].cuda(), xf_proj[sel].cuda())
+    assert torch.equal(eng.sample(st, x[sel].cuda()), x0[sel])
+    want = C.oracle_ddim(sd, x[sel], xf_proj[sel], xf_out[sel])
+    assert C.rel_l2(x0[sel], want) < TOL_FAST
+    eng.close()
