@@ -117,7 +117,7 @@ int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const f
 void mcm_timing_enable(int on);
 int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops);
 
-/* Development aid (MCM_DEBUG_EPI=3): summed clock cycles of the GEMM epilogue warps per phase; out[8]. */
+/* Development aid (MCM_DEBUG_EPI=3): summed clock cycles of the GEMM epilogue warps per phase; out[16]. */
 int mcm_debug_read(unsigned long long* out, int reset);
 
 const char* mcm_last_error(void);

@@ -222,9 +222,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The WHOLE warp runs the loop (so addresses / coordinates stay warp-uniform and live in uniform registers);
+    // only the issuing instructions are predicated on one elected lane.  A divergent `if (lane == 0)` around the
+    // loop makes the compiler wrap every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall.
+    {
       int stage = 0;
       uint32_t phase = 0;
+      long long pr_wait = 0, pr_kb = 0, pr_t0 = (p.debug == 3) ? clock64() : 0;
       const uint32_t tx = p.stage_bytes;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
         const int n_tile = tile % p.n_tiles;
@@ -239,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int a_k0 = inner * p.a_k_inner;
         const int a_z = outer;
         const int b_z = p.b_batched ? batch : 0;
-        if (p.prefetch) {
+        if (p.prefetch && lane == 0) {
           // pull the NEXT work item's A rows (activations, usually DRAM-resident) into L2 while this one is loaded
           const int nt = tile + n_clusters;
           if (nt < p.total_tiles) {
@@ -255,12 +259,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          long long tp0 = 0;
+          if (p.debug == 3) tp0 = clock64();
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          if (p.debug == 3) { const long long n = clock64(); pr_wait += n - tp0; pr_kb += 1; }
           const uint32_t bar = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           if constexpr (PAIR) {
             // CTA pair: each CTA loads its own A rows and its half of the B rows into its OWN smem; all bytes are
             // accounted on the LEADER's barrier, which its MMA thread waits on.
+            if (elect_one()) {
             if (crank == 0) mbar_expect_tx(bar, 2u * tx);
             const int b_rp = b_row + crank * (p.block_n / 2);
             tma_load_3d_2sm(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
@@ -271,9 +279,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d_2sm(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_rp, b_z);
               tma_load_3d_2sm(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_rp, b_z);
             }
+            }   // elect_one
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
+          if (elect_one()) {
           mbar_expect_tx(bar, tx);
           // A: this CTA's own 128 rows.  B: this CTA fetches rows [crank, crank+1) * block_n / cs of the tile and
           // multicasts them to every CTA of the cluster (each CTA's barrier counts the whole tile's bytes).
@@ -295,29 +306,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_row, b_z);
             }
           }
+          }   // elect_one
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (p.debug == 3 && p.dbg != nullptr && lane == 0) {
+        atomicAdd(p.dbg + 8, (unsigned long long)pr_wait);
+        atomicAdd(p.dbg + 9, (unsigned long long)(clock64() - pr_t0));
+        atomicAdd(p.dbg + 10, (unsigned long long)pr_kb);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
-    if (lane == 0 && !(PAIR && crank != 0)) {
+    if (!(PAIR && crank != 0)) {      // whole warp, converged; tcgen05.mma / commit issued by one elected lane
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long mm_wacc = 0, mm_wfull = 0, mm_t0 = (p.debug == 3) ? clock64() : 0;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        long long tm0 = (p.debug == 3) ? clock64() : 0;
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+        if (p.debug == 3) mm_wacc += clock64() - tm0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(acc * ACC_STRIDE);
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          long long tf0 = (p.debug == 3) ? clock64() : 0;
           mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (p.debug == 3) mm_wfull += clock64() - tf0;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const int kleft = p.K - kb * BLOCK_K;
           const int nk = kleft >= BLOCK_K ? BLOCK_K / UMMA_K : (kleft + UMMA_K - 1) / UMMA_K;
           if constexpr (PAIR) {
+            if (elect_one()) {
             if (!p.split) {
               const uint32_t sb = sa + p.a_bytes;
               for (int k = 0; k < nk; ++k)
@@ -335,9 +359,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             umma_commit_2sm(smem_u32(&empty_bar[stage]), (uint16_t)3);   // frees the stage in BOTH CTAs
+            }   // elect_one
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
+          if (elect_one()) {
           if (!p.split) {
             const uint32_t sb = sa + p.a_bytes;
             for (int k = 0; k < nk; ++k) {
@@ -358,10 +385,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // the stage is rewritten by multicasts from every CTA of the cluster: release it on all of them
           if (p.cs > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), cmask);
           else umma_commit(smem_u32(&empty_bar[stage]));
+          }   // elect_one
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (PAIR) umma_commit_2sm(smem_u32(&tfull_bar[acc]), (uint16_t)3);   // both CTAs' epilogues
-        else umma_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
+        if (elect_one()) {
+          if constexpr (PAIR) umma_commit_2sm(smem_u32(&tfull_bar[acc]), (uint16_t)3);   // both CTAs' epilogues
+          else umma_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete
+        }
+        __syncwarp();
+      }
+      if (p.debug == 3 && p.dbg != nullptr && lane == 0) {
+        atomicAdd(p.dbg + 11, (unsigned long long)mm_wacc);
+        atomicAdd(p.dbg + 12, (unsigned long long)mm_wfull);
+        atomicAdd(p.dbg + 13, (unsigned long long)(clock64() - mm_t0));
       }
     }
   } else {
@@ -443,7 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (tmode & TM_TMA) {
           // ================= TMA epilogue: registers -> swizzled smem tile -> bulk tensor store =================
           if (p.debug == 2) continue;
-          if ((tmode & TM_LDADD) && lane == 0) {       // fetch the addend tile while the accumulator is read
+          if ((tmode & TM_LDADD) && elect_one()) {     // fetch the addend tile while the accumulator is read
             mbar_expect_tx(my_abar, 4096);
             tma_load_3d(&em.m[si][1], my_abar, stgA, colg0, row0, (tmode & TM_BCAST) ? 0 : outer);
           }
@@ -555,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             const int x0 = transposed ? row0 : colg0;
             const int x1 = transposed ? colg0 : row0;
             if (sg.out32 != nullptr) {
@@ -796,8 +833,8 @@ int do_init() {
   }
   MCM_CHECK(g_max_clusters[1] > 0, "gemm_tc_kernel does not fit on this device");
   if (g_debug_epi == 3) {
-    MCM_CUDA(cudaMalloc(&g_dbg, 8 * sizeof(unsigned long long)));
-    MCM_CUDA(cudaMemset(g_dbg, 0, 8 * sizeof(unsigned long long)));
+    MCM_CUDA(cudaMalloc(&g_dbg, 16 * sizeof(unsigned long long)));
+    MCM_CUDA(cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long)));
   }
   return 0;
 }
@@ -914,11 +951,11 @@ int gemm_tc_init() {
 unsigned long long gemm_tc_launch_count() { return g_launches.load(); }
 
 int gemm_tc_debug_read(unsigned long long* out, int reset) {
-  for (int i = 0; i < 8; ++i) out[i] = 0;
+  for (int i = 0; i < 16; ++i) out[i] = 0;
   if (g_dbg == nullptr) return 0;
   MCM_CUDA(cudaDeviceSynchronize());
-  MCM_CUDA(cudaMemcpy(out, g_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (reset) MCM_CUDA(cudaMemset(g_dbg, 0, 8 * sizeof(unsigned long long)));
+  MCM_CUDA(cudaMemcpy(out, g_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) MCM_CUDA(cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long)));
   return 0;
 }
 
@@ -1060,12 +1097,16 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   MCM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   if (g_debug_epi == 3 && getenv("MCM_DEBUG_PRINT")) {
-    unsigned long long d[8];
+    unsigned long long d[16];
     gemm_tc_debug_read(d, 1);
     const double ch = d[5] ? (double)d[5] : 1.0;
-    fprintf(stderr, "gemm M=%d K=%d batches=%d bn=%d tiles=%d nseg=%d n0=%d flags0=%d tma=%d/%d/%d pair=%d | per chunk: acc %.0f stg %.0f ld %.0f math %.0f issue %.0f | chunks %llu\n",
+    fprintf(stderr, "gemm M=%d K=%d batches=%d bn=%d tiles=%d nseg=%d n0=%d flags0=%d tma=%d/%d/%d pair=%d | per chunk: acc %.0f stg %.0f ld %.0f math %.0f issue %.0f | chunks %llu"
+            " || producer: wait-empty %.0f%% of %.0f cyc/kblock | mma: wait-acc %.0f%% wait-full %.0f%% of its time, %.0f cyc/kblock\n",
             q.M, q.K, q.batches, p.block_n, p.total_tiles, q.nseg, q.seg[0].n, q.seg[0].flags, p.tma_mode[0], p.tma_mode[1],
-            p.tma_mode[2], p.pair, d[0] / ch, d[1] / ch, d[2] / ch, d[3] / ch, d[4] / ch, d[5]);
+            p.tma_mode[2], p.pair, d[0] / ch, d[1] / ch, d[2] / ch, d[3] / ch, d[4] / ch, d[5],
+            100.0 * d[8] / (d[9] ? (double)d[9] : 1.0), (double)d[9] / (d[10] ? (double)d[10] : 1.0),
+            100.0 * d[11] / (d[13] ? (double)d[13] : 1.0), 100.0 * d[12] / (d[13] ? (double)d[13] : 1.0),
+            (double)d[13] / (d[10] ? (double)d[10] : 1.0));
   }
   return 0;
 }

@@ -12,7 +12,7 @@ g = torch.Generator().manual_seed(0)
 x = torch.randn(B, T, 322, generator=g).cuda()
 eng.prepare_conditions(torch.randn(B, 77, 256, generator=g).cuda(), torch.randn(B, 2048, generator=g).cuda())
 lib = _lib.load()
-out = (ctypes.c_ulonglong * 8)()
+out = (ctypes.c_ulonglong * 16)()
 for _ in range(2):
     eng.denoise(x, 500)
 lib.mcm_debug_read(out, 1)
