@@ -154,18 +154,18 @@ def run_reference_arm(args, wl, rank, world):
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    B_cpu = args.cpu_batch or 8
+    B_cpu = args.cpu_batch or 64
     oracle_cpu_setup(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu)
     for _ in range(args.warmup):
         oracle_cpu_rate(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 1)
     vals, wall, cores = [], 0.0, None
     for _ in range(args.steps):
-        v, dt, cores = oracle_cpu_rate(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 2)
+        v, dt, cores = oracle_cpu_rate(wl["T"], wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 10)
         vals.append(v)
         wall += dt
     value = sum(vals) / len(vals)
     sample = (f"reference CPU arithmetic (oracle port, bit-identical to mogen's PyTorch path on CPU): B={B_cpu} samples x "
-              f"2 of 50 DDIM steps per bench step, fp32, {cores} threads, frames/s = B*T/(50*t_denoise_step)")
+              f"10 of 50 DDIM steps per bench step, fp32, {cores} threads, frames/s = B*T/(50*t_denoise_step)")
     line = {"impl": "reference", "metric": "sampled motion frames/sec (50-step DDIM)", "value": value, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -290,10 +290,14 @@ def main():
     ms_e2e = (time.perf_counter() - t0) * 1e3
 
     # ---- roofline leg: separate instrumented run (events around every launch), not part of the numbers above
+    # (single stream, eager launches: with the two-stream schedule of the timed region kernels of different streams
+    # share the SMs, so per-kernel event times would no longer be times of a kernel running alone)
+    eng.set_option("dual", 0)
     _lib.timing_enable(True)
     one_run_device()
     tm = _lib.timing_collect()
     _lib.timing_enable(False)
+    eng.set_option("dual", 1)
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
@@ -319,7 +323,7 @@ def main():
                     "d2h_bytes_per_step": int(out_pin.numel() * 4), "api": "mcm_sample_host (pinned host x_T -> x_0)"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one sampling run)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one sampling run; timed single-stream, eager)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None,
                          # dram__bytes_read+write summed over the 85 GEMM launches of one denoise step (ncu, profiles/
@@ -332,11 +336,11 @@ def main():
                          "whole_step_achieved": whole, "whole_step_frac": whole / peaks["tflops"]},
         }
         if not args.no_cpu_baseline:
-            B_cpu = args.cpu_batch or 8
+            B_cpu = args.cpu_batch or 64
             torch.set_num_threads(os.cpu_count() or 1)
-            v, dt, cores = oracle_cpu_rate(T, wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 3)
+            v, dt, cores = oracle_cpu_rate(T, wl["n_ctrl"], wl["c_feats"], wl["c_len"], B_cpu, 25)
             line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle (bit-identical restatement of mogen's CPU path): B={B_cpu} x 3 of 50 "
+                                    "sample": f"oracle (bit-identical restatement of mogen's CPU path): B={B_cpu} x 25 of 50 "
                                               f"DDIM steps, fp32, {dt:.1f} s of CPU work, extrapolated B*T/(50*t_step)"}
         print(json.dumps(line), flush=True)
     eng.close()

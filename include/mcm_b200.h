@@ -63,6 +63,12 @@ typedef struct mcm_sampler {
 int mcm_create(const mcm_config* cfg, mcm_ctx** out);
 void mcm_destroy(mcm_ctx* ctx);
 
+/* Scheduling options (no effect on results, which are bit-identical in every mode):
+ *   "dual"  1 = run the two halves of a batch on two streams (default), 0 = one stream
+ *   "graph" 1 = replay a captured CUDA graph per sampler step (default), 0 = eager launches
+ *   "chunk" n = pass the batch through the layer stack n samples at a time (default 0 = whole batch) */
+int mcm_set_option(mcm_ctx* ctx, const char* name, int value);
+
 /* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key
  * (SURVEY.md section 8b), e.g. "temporal_decoder_blocks.3.ca_block.query.weight"; ControlNet keys are
  * "controlnet.{j}.copied_block.*", "controlnet.{j}.before_proj.*", "controlnet.{j}.after_proj.*",

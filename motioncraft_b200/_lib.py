@@ -38,6 +38,7 @@ _VP, _I, _LL = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
 SIGNATURES = {
     "mcm_create": (_I, [ctypes.POINTER(McmConfig), ctypes.POINTER(_VP)]),
     "mcm_destroy": (None, [_VP]),
+    "mcm_set_option": (_I, [_VP, ctypes.c_char_p, _I]),
     "mcm_set_param": (_I, [_VP, ctypes.c_char_p, _VP, _LL]),
     "mcm_finalize_params": (_I, [_VP, _VP]),
     "mcm_prepare_conditions": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _VP]),

@@ -45,6 +45,13 @@ struct Ctrl {
   OpPtr before_w, after_w;
   float *before_b, *after_b;
 };
+
+// Activations / operands that live only inside one pass through the layer stack.  Two sets exist so that the two
+// halves of a batch can run concurrently on two streams (set 1 is sized for half the batch).
+struct Scratch {
+  float *h32, *f32A, *f32B, *c32;
+  OpPtr opA, opB, opC, opD, hop, ctxT_sa, c_op;
+};
 }  // namespace mcm
 
 using namespace mcm;
@@ -67,14 +74,33 @@ struct mcm_ctx {
   float *b_joint, *b_te0, *b_te2, *b_mod, *b_out, *b_cci, *seq_emb;
 
   // workspace
-  float *h32, *f32A, *f32B, *mod32, *emb32, *xfproj32, *eps32, *x32, *cc32, *c32;
-  OpPtr opA, opB, opC, opD, hop, ctxT_sa, xop, te_op, t1_op, emb_op, cc_op, c_op;
+  Scratch ws[2];
+  float *mod32, *emb32, *xfproj32, *eps32, *x32, *cc32;
+  OpPtr xop, te_op, t1_op, emb_op, cc_op;
+  cudaStream_t s1 = nullptr;             // second stream: the other half of the batch
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s0 = nullptr;             // capture / replay stream used when the caller's stream is the legacy default
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  int dual = 1;                          // MCM_DUAL=0: single stream
+  // CUDA graph of one denoise step (sampler loop): captured once per (batch, control on/off), replayed every step;
+  // the step's timestep is read from `t_buf`, so the graph is identical for all steps.
+  int use_graph = 1;                     // MCM_GRAPH=0: eager launches
+  long long* t_buf = nullptr;
+  struct StepGraph { int B; bool have_c; cudaGraphExec_t exec; unsigned long long n_gemm, n_row; };
+  std::vector<StepGraph> graphs;
 
   int fmt_fast() const { return cfg.precise_all ? OP_BF16X2 : OP_F16; }
   int fmt_prec() const { return OP_BF16X2; }
 
   ~mcm_ctx() {
     for (void* p : allocs) cudaFree(p);
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    if (s1) cudaStreamDestroy(s1);
+    if (s0) cudaStreamDestroy(s0);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
   }
 };
 
@@ -213,16 +239,16 @@ int build_block(mcm_ctx* c, const std::string& pfx, Block* b, int mod_off, cudaS
 // ---------------------------------------------------------------------------------------------
 // one DecoderLayer (mcm.py:25-41) on the fp32 residual stream `h` [B*T, D], in place.
 // `mod` points at this block's modulation vectors (pitch mod_ld).  If hop_out_fmt >= 0 the block's
-// final GEMM also emits the 16-bit copy of the new h into c->hop in that format.
+// final GEMM also emits the 16-bit copy of the new h into c->ws[0].hop in that format.
 // ---------------------------------------------------------------------------------------------
-int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int mod_ld, OpPtr final_op,
+int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const float* mod, int mod_ld, OpPtr final_op,
               int final_op_fmt, cudaStream_t st, int b0 = 0) {
   const int T = c->T, Tp = c->Tp, D = c->D, F = c->F, H = c->H, hdT = c->hdT, hdD = c->hdD;
   const int ff = c->fmt_fast();
-  const OpPtr opA_t = view(c->opA, Tp), opC_t = view(c->opC, Tp);
-  const OpPtr opA_d = view(c->opA, D), opB_d = view(c->opB, D), opC_d = view(c->opC, D), opD_d = view(c->opD, D);
-  const OpPtr opB_f = view(c->opB, F);
-  const OpPtr hop = view(c->hop, D);
+  const OpPtr opA_t = view(w.opA, Tp), opC_t = view(w.opC, Tp);
+  const OpPtr opA_d = view(w.opA, D), opB_d = view(w.opB, D), opC_d = view(w.opC, D), opD_d = view(w.opD, D);
+  const OpPtr opB_f = view(w.opB, F);
+  const OpPtr hop = view(w.hop, D);
 
   // ---- channel attention (EfficientSelfAttention on x^T, efficient_attention.py:25-46) ----
   // xn^T = LayerNorm_T(h^T)                                   -> opA [B*D, Tp]
@@ -236,16 +262,16 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     g.out_rows_per_outer = D; g.trans_rows = T;
     g.nseg = 3;
     g.seg[0] = seg_default(T, 0);
-    g.seg[0].bias = k.sa_bqkv; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = T;
+    g.seg[0].bias = k.sa_bqkv; g.seg[0].out32 = w.f32A; g.seg[0].ld32 = T;
     g.seg[1] = seg_default(T, T);
-    g.seg[1].bias = k.sa_bqkv + T; g.seg[1].out32 = c->f32B; g.seg[1].ld32 = D; g.seg[1].flags = EPI_TRANSPOSED;
+    g.seg[1].bias = k.sa_bqkv + T; g.seg[1].out32 = w.f32B; g.seg[1].ld32 = D; g.seg[1].flags = EPI_TRANSPOSED;
     g.seg[2] = seg_default(T, 2 * T);
     g.seg[2].bias = k.sa_bqkv + 2 * T; g.seg[2].op = opB_d; g.seg[2].op_fmt = ff; g.seg[2].flags = EPI_TRANSPOSED;
     MCM_TRY(gemm_tc_launch(g, st));
   }
   // q: softmax over each head's T/H features; k: softmax over the D channel-tokens (a row in [B,T',D])
-  MCM_TRY(softmax_seg_launch(c->f32A, B * D, T, T, hdT, opC_t, ff, st));
-  MCM_TRY(softmax_seg_launch(c->f32B, B * T, D, D, D, opD_d, ff, st));
+  MCM_TRY(softmax_seg_launch(w.f32A, B * D, T, T, hdT, opC_t, ff, st));
+  MCM_TRY(softmax_seg_launch(w.f32B, B * T, D, D, D, opD_d, ff, st));
   {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, stored transposed: ctxT[b][l][dk]
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));
@@ -255,7 +281,7 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     g.out_rows_per_outer = T; g.trans_rows = T; g.head_dim = hdT;
     g.nseg = 1;
     g.seg[0] = seg_default(T, 0);
-    g.seg[0].op = view(c->ctxT_sa, Tp); g.seg[0].op_fmt = ff;
+    g.seg[0].op = view(w.ctxT_sa, Tp); g.seg[0].op_fmt = ff;
     g.seg[0].flags = EPI_TRANSPOSED | EPI_MASK_BLOCKDIAG;
     g.algo_flops = 2.0 * T * hdT * D * B;      // only the per-head diagonal blocks are algorithmic work
     MCM_TRY(gemm_tc_launch(g, st));
@@ -264,17 +290,17 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));
     g.a = opC_t; g.a_rows = D; g.a_k = Tp; g.a_batches = B;
-    g.b = view(c->ctxT_sa, Tp); g.b_rows = T; g.b_k = Tp; g.b_batches = B; g.b_batched = 1;
+    g.b = view(w.ctxT_sa, Tp); g.b_rows = T; g.b_k = Tp; g.b_batches = B; g.b_batched = 1;
     g.fmt = ff; g.M = D; g.K = T; g.batches = B; g.inner = 1;
     g.out_rows_per_outer = D;
     g.nseg = 1;
     g.seg[0] = seg_default(T, 0);
-    g.seg[0].out32 = c->f32A; g.seg[0].ld32 = T;
+    g.seg[0].out32 = w.f32A; g.seg[0].ld32 = T;
     g.algo_flops = 2.0 * D * T * hdT * B;
     MCM_TRY(gemm_tc_launch(g, st));
   }
   // StylizationBlock over T: SiLU(LN(y) (1 + scale) + shift)    -> opA [B*D, Tp]
-  MCM_TRY(ln_rows_launch(c->f32A, B * D, T, T, k.sa_pn_w, k.sa_pn_b, mod + k.mod_off, mod + k.mod_off + T, mod_ld, D,
+  MCM_TRY(ln_rows_launch(w.f32A, B * D, T, T, k.sa_pn_w, k.sa_pn_b, mod + k.mod_off, mod + k.mod_off + T, mod_ld, D,
                          true, opA_t, ff, st));
   {  // h[b, t', d] += (. W_o^T + b_o)[(b,d), t']
     GemmProblem g;
@@ -295,10 +321,10 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
   {
     GemmProblem g = linear_problem(opA_d, B * T, k.ca_wq, D, D, ff);
     g.seg[0] = seg_default(D, 0);
-    g.seg[0].bias = k.ca_bq; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = D;
+    g.seg[0].bias = k.ca_bq; g.seg[0].out32 = w.f32A; g.seg[0].ld32 = D;
     MCM_TRY(gemm_tc_launch(g, st));
   }
-  MCM_TRY(softmax_seg_launch(c->f32A, B * T, D, D, hdD, opC_d, ff, st));
+  MCM_TRY(softmax_seg_launch(w.f32A, B * T, D, D, hdD, opC_d, ff, st));
   {  // y[b, :, head] = softmax(q)[b, :, head] ctx[b, head]     (context precomputed per run)
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));
@@ -308,10 +334,10 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
     g.out_col_inner = hdD; g.out_rows_per_outer = T;
     g.nseg = 1;
     g.seg[0] = seg_default(hdD, 0);
-    g.seg[0].out32 = c->f32A; g.seg[0].ld32 = D;
+    g.seg[0].out32 = w.f32A; g.seg[0].ld32 = D;
     MCM_TRY(gemm_tc_launch(g, st));
   }
-  MCM_TRY(ln_rows_launch(c->f32A, B * T, D, D, k.ca_pn_w, k.ca_pn_b, mod + k.mod_off + 2 * T,
+  MCM_TRY(ln_rows_launch(w.f32A, B * T, D, D, k.ca_pn_w, k.ca_pn_b, mod + k.mod_off + 2 * T,
                          mod + k.mod_off + 2 * T + D, mod_ld, T, true, opA_d, ff, st));
   {  // h += . W_o^T + b_o ; also emit the 16-bit copy of h that linear1 reads
     GemmProblem g = linear_problem(opA_d, B * T, k.ca_wo, D, D, ff);
@@ -331,10 +357,10 @@ int run_block(mcm_ctx* c, const Block& k, int B, float* h, const float* mod, int
   {
     GemmProblem g = linear_problem(opB_f, B * T, k.f_w2, D, F, ff);
     g.seg[0] = seg_default(D, 0);
-    g.seg[0].bias = k.f_b2; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = D;
+    g.seg[0].bias = k.f_b2; g.seg[0].out32 = w.f32A; g.seg[0].ld32 = D;
     MCM_TRY(gemm_tc_launch(g, st));
   }
-  MCM_TRY(ln_rows_launch(c->f32A, B * T, D, D, k.f_pn_w, k.f_pn_b, mod + k.mod_off + 2 * T + 2 * D,
+  MCM_TRY(ln_rows_launch(w.f32A, B * T, D, D, k.f_pn_w, k.f_pn_b, mod + k.mod_off + 2 * T + 2 * D,
                          mod + k.mod_off + 2 * T + 3 * D, mod_ld, T, true, opA_d, ff, st));
   {
     GemmProblem g = linear_problem(opA_d, B * T, k.f_wo, D, D, ff);
@@ -366,7 +392,7 @@ int check_batch(mcm_ctx* c, int B) {
 }
 
 // joint_embed -> decoder layers (+ control branch) -> out, for samples [b0, b0 + B) of the current step
-int run_layers(mcm_ctx* c, int b0, int B, float* eps_out, cudaStream_t st) {
+int run_layers(mcm_ctx* c, Scratch& w, int b0, int B, float* eps_out, cudaStream_t st) {
   const int T = c->T, D = c->D, IN = c->IN;
   const int fp = c->fmt_prec();
   const size_t r0 = (size_t)b0 * T;           // first row of this chunk in per-sample tensors
@@ -380,16 +406,16 @@ int run_layers(mcm_ctx* c, int b0, int B, float* eps_out, cudaStream_t st) {
     g.nseg = 1;
     g.seg[0] = seg_default(D, 0);
     g.seg[0].bias = c->b_joint; g.seg[0].addend = c->seq_emb; g.seg[0].flags = EPI_ADDEND_BCAST;
-    g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
+    g.seg[0].out32 = w.h32; g.seg[0].ld32 = D;
     MCM_TRY(gemm_tc_launch(g, st));
   }
   const OpPtr none{nullptr, nullptr, 0};
-  const OpPtr hop_out = view(c->hop, D);
+  const OpPtr hop_out = view(w.hop, D);
   const int nL = c->nL, nC = (c->have_c ? c->nC : 0);
   const float* mod = c->mod32 + (size_t)b0 * c->mod_total;
   const int mld = c->mod_total;
   // MCMTransformer.forward_test (mcm.py:93-102) / ControlT2MHalf_MCM.forward_test (controlnet_mcm.py:306-361)
-  MCM_TRY(run_block(c, c->blocks[0], B, c->h32, mod, mld, (nL == 1) ? hop_out : none, fp, st, b0));
+  MCM_TRY(run_block(c, w, c->blocks[0], B, w.h32, mod, mld, (nL == 1) ? hop_out : none, fp, st, b0));
   for (int i = 1; i < nL; ++i) {
     if (i <= nC) {
       const int j = i - 1;
@@ -398,18 +424,18 @@ int run_layers(mcm_ctx* c, int b0, int B, float* eps_out, cudaStream_t st) {
       if (j == 0) {  // c = copied_block(x = h + before_proj(c))      (controlnet_mcm.py:65-75)
         GemmProblem g = linear_problem(offs(view(c->cc_op, D), r0 * D), B * T, ct.before_w, D, D, c->fmt_fast());
         g.seg[0] = seg_default(D, 0);
-        g.seg[0].bias = ct.before_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->c32; g.seg[0].ld32 = D;
+        g.seg[0].bias = ct.before_b; g.seg[0].addend = w.h32; g.seg[0].out32 = w.c32; g.seg[0].ld32 = D;
         MCM_TRY(gemm_tc_launch(g, st));
       }
-      MCM_TRY(run_block(c, cb, B, c->c32, mod, mld, view(c->c_op, D), c->fmt_fast(), st, b0));
+      MCM_TRY(run_block(c, w, cb, B, w.c32, mod, mld, view(w.c_op, D), c->fmt_fast(), st, b0));
       {  // h = h + after_proj(c)                                       (:75,85 ; :341-349)
-        GemmProblem g = linear_problem(view(c->c_op, D), B * T, ct.after_w, D, D, c->fmt_fast());
+        GemmProblem g = linear_problem(view(w.c_op, D), B * T, ct.after_w, D, D, c->fmt_fast());
         g.seg[0] = seg_default(D, 0);
-        g.seg[0].bias = ct.after_b; g.seg[0].addend = c->h32; g.seg[0].out32 = c->h32; g.seg[0].ld32 = D;
+        g.seg[0].bias = ct.after_b; g.seg[0].addend = w.h32; g.seg[0].out32 = w.h32; g.seg[0].ld32 = D;
         MCM_TRY(gemm_tc_launch(g, st));
       }
     }
-    MCM_TRY(run_block(c, c->blocks[i], B, c->h32, mod, mld, (i == nL - 1) ? hop_out : none, fp, st, b0));
+    MCM_TRY(run_block(c, w, c->blocks[i], B, w.h32, mod, mld, (i == nL - 1) ? hop_out : none, fp, st, b0));
   }
   {  // eps = out(h)                                                (mcm.py:102)
     GemmProblem g = linear_problem(hop_out, B * T, c->w_out, IN, D, fp);
@@ -443,8 +469,65 @@ int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float
   // Layer stack, in chunks of `chunk` samples: every op is per-sample, so a chunk runs the whole stack on
   // chunk-local activations (h, operands and fp32 scratch reuse the SAME addresses for every chunk) which then stay
   // resident in the 126 MB L2 instead of bouncing through HBM between kernels.
+  if (c->dual && c->chunk <= 0 && B >= 2) {
+    // Two halves of the batch on two streams.  The tensor-core GEMMs (one persistent CTA per SM, ~25 % of the issue
+    // slots) and the issue-bound row kernels stress complementary resources, and the halves are independent, so half
+    // A's GEMM co-resides with half B's row kernels on the same SMs.  Fork after the shared prologue, join before the
+    // caller's next kernel; everything stays ordered with respect to the caller's stream.
+    const int B0 = (B + 1) / 2;
+    MCM_CUDA(cudaEventRecord(c->ev_fork, st));
+    MCM_CUDA(cudaStreamWaitEvent(c->s1, c->ev_fork, 0));
+    MCM_TRY(run_layers(c, c->ws[0], 0, B0, eps_out, st));
+    MCM_TRY(run_layers(c, c->ws[1], B0, B - B0, eps_out, c->s1));
+    MCM_CUDA(cudaEventRecord(c->ev_join, c->s1));
+    MCM_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+    return 0;
+  }
   const int chunk = c->chunk > 0 ? std::min(c->chunk, B) : B;
-  for (int b0 = 0; b0 < B; b0 += chunk) MCM_TRY(run_layers(c, b0, std::min(chunk, B - b0), eps_out, st));
+  for (int b0 = 0; b0 < B; b0 += chunk) MCM_TRY(run_layers(c, c->ws[0], b0, std::min(chunk, B - b0), eps_out, st));
+  return 0;
+}
+
+// One denoise step of the sampler loop (x already packed in c->xop, eps -> c->eps32) through a cached CUDA graph.
+int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
+  if (!c->use_graph || timing_enabled()) return run_denoiser(c, B, nullptr, t, c->eps32, st);
+  // the legacy default stream cannot be captured: hop onto a private stream, ordered by events on both sides
+  const bool hop_stream = (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread);
+  cudaStream_t gs = hop_stream ? c->s0 : st;
+  if (hop_stream) {
+    MCM_CUDA(cudaEventRecord(c->ev_in, st));
+    MCM_CUDA(cudaStreamWaitEvent(gs, c->ev_in, 0));
+  }
+  MCM_TRY(fill_timesteps_launch(c->t_buf, (long long)t, B, gs));
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : c->graphs)
+    if (g.B == B && g.have_c == c->have_c) {
+      exec = g.exec;
+      gemm_tc_count_replayed(g.n_gemm);          // keep the library's launch counters truthful under graph replay
+      elementwise_count_replayed(g.n_row);
+    }
+  if (exec == nullptr) {
+    // capture (the launches are recorded, not executed), instantiate, remember
+    cudaGraph_t graph = nullptr;
+    const unsigned long long g0 = gemm_tc_launch_count(), r0 = elementwise_launch_count();
+    MCM_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_denoiser(c, B, c->t_buf, 0, c->eps32, gs);
+    const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    MCM_CUDA(ce);
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    MCM_CUDA(ie);
+    c->graphs.push_back({B, c->have_c, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0});
+  }
+  MCM_CUDA(cudaGraphLaunch(exec, gs));
+  if (hop_stream) {
+    MCM_CUDA(cudaEventRecord(c->ev_out, gs));
+    MCM_CUDA(cudaStreamWaitEvent(st, c->ev_out, 0));
+  }
   return 0;
 }
 
@@ -453,7 +536,7 @@ int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const float* step_noise
   const size_t n = rows * c->IN;
   // x_io holds x_T on entry and x_0 on exit; xop must already hold the operand copy of x_T
   for (int i = s->n_steps - 1; i >= 0; --i) {
-    MCM_TRY(run_denoiser(c, B, nullptr, s->timestep_map[i], c->eps32, st));
+    MCM_TRY(run_denoiser_step(c, B, s->timestep_map[i], st));
     const float* noise = step_noise ? step_noise + (size_t)i * n : nullptr;
     if (s->mode == 0) {
       DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
@@ -530,35 +613,87 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   size_t szB = smax(smax(R1 * c->D, R1 * c->F), R2 * c->NTp);
   if (c->nC > 0) szB = smax(szB, R1 * c->Cinp);
   size_t szC = smax(smax(R2 * c->Tp, R1 * c->D), R2 * c->NTp);
-  if (alloc_f32(c, &c->h32, R1 * c->D)) return fail(0);
-  if (alloc_f32(c, &c->f32A, smax(smax(R2 * c->T, R1 * c->D), R2 * c->NTp))) return fail(0);
-  if (alloc_f32(c, &c->f32B, R1 * c->D)) return fail(0);
+  if (alloc_f32(c, &c->ws[0].h32, R1 * c->D)) return fail(0);
+  if (alloc_f32(c, &c->ws[0].f32A, smax(smax(R2 * c->T, R1 * c->D), R2 * c->NTp))) return fail(0);
+  if (alloc_f32(c, &c->ws[0].f32B, R1 * c->D)) return fail(0);
   if (alloc_f32(c, &c->mod32, B * c->mod_total)) return fail(0);
   if (alloc_f32(c, &c->emb32, B * c->E)) return fail(0);
   if (alloc_f32(c, &c->xfproj32, B * c->E)) return fail(0);
   if (alloc_f32(c, &c->eps32, R1 * c->IN)) return fail(0);
   if (alloc_f32(c, &c->x32, R1 * c->IN)) return fail(0);
-  if (alloc_op(c, &c->opA, szA, 8, lo)) return fail(0);
-  if (alloc_op(c, &c->opB, szB, 8, true)) return fail(0);      // lo: also stages the bf16x2 control condition
-  if (alloc_op(c, &c->opC, szC, 8, lo)) return fail(0);
-  if (alloc_op(c, &c->opD, R1 * c->D, 8, lo)) return fail(0);
-  if (alloc_op(c, &c->hop, R1 * c->D, c->D, true)) return fail(0);
-  if (alloc_op(c, &c->ctxT_sa, B * c->T * c->Tp, c->Tp, lo)) return fail(0);
+  if (alloc_op(c, &c->ws[0].opA, szA, 8, lo)) return fail(0);
+  if (alloc_op(c, &c->ws[0].opB, szB, 8, true)) return fail(0);      // lo: also stages the bf16x2 control condition
+  if (alloc_op(c, &c->ws[0].opC, szC, 8, lo)) return fail(0);
+  if (alloc_op(c, &c->ws[0].opD, R1 * c->D, 8, lo)) return fail(0);
+  if (alloc_op(c, &c->ws[0].hop, R1 * c->D, c->D, true)) return fail(0);
+  if (alloc_op(c, &c->ws[0].ctxT_sa, B * c->T * c->Tp, c->Tp, lo)) return fail(0);
   if (alloc_op(c, &c->xop, R1 * c->INp, c->INp, true)) return fail(0);
   if (alloc_op(c, &c->te_op, B * c->D, c->D, true)) return fail(0);
   if (alloc_op(c, &c->t1_op, B * c->E, c->E, true)) return fail(0);
   if (alloc_op(c, &c->emb_op, B * c->E, c->E, true)) return fail(0);
   if (c->nC > 0) {
     if (alloc_f32(c, &c->cc32, R1 * c->D)) return fail(0);
-    if (alloc_f32(c, &c->c32, R1 * c->D)) return fail(0);
+    if (alloc_f32(c, &c->ws[0].c32, R1 * c->D)) return fail(0);
     if (alloc_op(c, &c->cc_op, R1 * c->D, c->D, lo)) return fail(0);
-    if (alloc_op(c, &c->c_op, R1 * c->D, c->D, lo)) return fail(0);
+    if (alloc_op(c, &c->ws[0].c_op, R1 * c->D, c->D, lo)) return fail(0);
+  }
+  if (const char* e = getenv("MCM_DUAL")) c->dual = atoi(e);
+  if (const char* e = getenv("MCM_GRAPH")) c->use_graph = atoi(e);
+  if (dev_alloc(c, reinterpret_cast<void**>(&c->t_buf), (size_t)c->Bmax * sizeof(long long))) return fail(0);
+  if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("could not create the graph stream / events");
+    return fail(0);
+  }
+  if (c->Bmax < 2) c->dual = 0;
+  if (c->dual) {
+    // second scratch set for the second half of the batch (only what a pass through the layer stack touches)
+    const size_t Bh = c->Bmax / 2, H1 = Bh * c->T, H2 = Bh * c->D;
+    Scratch& w = c->ws[1];
+    std::memset(&w, 0, sizeof(w));
+    if (alloc_f32(c, &w.h32, H1 * c->D)) return fail(0);
+    if (alloc_f32(c, &w.f32A, smax(H2 * c->T, H1 * c->D))) return fail(0);
+    if (alloc_f32(c, &w.f32B, H1 * c->D)) return fail(0);
+    if (alloc_op(c, &w.opA, smax(H2 * c->Tp, H1 * c->D), 8, lo)) return fail(0);
+    if (alloc_op(c, &w.opB, smax(H1 * c->D, H1 * c->F), 8, lo)) return fail(0);
+    if (alloc_op(c, &w.opC, smax(H2 * c->Tp, H1 * c->D), 8, lo)) return fail(0);
+    if (alloc_op(c, &w.opD, H1 * c->D, 8, lo)) return fail(0);
+    if (alloc_op(c, &w.hop, H1 * c->D, c->D, true)) return fail(0);
+    if (alloc_op(c, &w.ctxT_sa, Bh * c->T * c->Tp, c->Tp, lo)) return fail(0);
+    if (c->nC > 0) {
+      if (alloc_f32(c, &w.c32, H1 * c->D)) return fail(0);
+      if (alloc_op(c, &w.c_op, H1 * c->D, c->D, lo)) return fail(0);
+    }
+    if (cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("could not create the second stream / events");
+      return fail(0);
+    }
   }
   *out = c;
   return 0;
 }
 
 void mcm_destroy(mcm_ctx* ctx) { delete ctx; }
+
+int mcm_set_option(mcm_ctx* c, const char* name, int value) {
+  MCM_CHECK(c != nullptr && name != nullptr, "bad argument");
+  const std::string n(name);
+  if (n == "dual") {
+    MCM_CHECK(value == 0 || c->s1 != nullptr, "dual-stream mode was disabled at creation (no second scratch set)");
+    c->dual = value;
+  } else if (n == "graph") {
+    c->use_graph = value;
+  } else if (n == "chunk") {
+    c->chunk = value;
+  } else {
+    set_error("unknown option: " + n);
+    return 1;
+  }
+  return 0;
+}
 
 int mcm_set_param(mcm_ctx* ctx, const char* name, const float* dev_ptr, long long numel) {
   MCM_CHECK(ctx && name && dev_ptr && numel > 0, "bad argument");
@@ -634,7 +769,7 @@ int mcm_prepare_conditions(mcm_ctx* c, int B, const float* xf_out, int n_tokens,
   MCM_CUDA(cudaMemcpyAsync(c->xfproj32, xf_proj, (size_t)B * c->E * 4, cudaMemcpyDeviceToDevice, st));
   for (size_t i = 0; i < c->blocks.size(); ++i) {
     const Block& k = c->blocks[i];
-    const OpPtr xfn = view(c->opA, L), vT = view(c->opB, Np), pT = view(c->opC, Np);
+    const OpPtr xfn = view(c->ws[0].opA, L), vT = view(c->ws[0].opB, Np), pT = view(c->ws[0].opC, Np);
     // LN_L(xf) -> [B*N, L]
     MCM_TRY(ln_rows_launch(xf_out, B * N, L, L, k.ca_tn_w, k.ca_tn_b, nullptr, nullptr, 4, N, false, xfn, ff, st));
     {  // key | value = LN(xf) W^T + b, both written transposed: [B, D, Np] (tokens contiguous)
@@ -646,13 +781,13 @@ int mcm_prepare_conditions(mcm_ctx* c, int B, const float* xf_out, int n_tokens,
       g.out_rows_per_outer = N; g.trans_rows = D;
       g.nseg = 2;
       g.seg[0] = seg_default(D, 0);
-      g.seg[0].bias = k.ca_bkv; g.seg[0].out32 = c->f32A; g.seg[0].ld32 = Np; g.seg[0].flags = EPI_TRANSPOSED;
+      g.seg[0].bias = k.ca_bkv; g.seg[0].out32 = c->ws[0].f32A; g.seg[0].ld32 = Np; g.seg[0].flags = EPI_TRANSPOSED;
       g.seg[1] = seg_default(D, D);
       g.seg[1].bias = k.ca_bkv + D; g.seg[1].op = vT; g.seg[1].op_fmt = ff; g.seg[1].flags = EPI_TRANSPOSED;
       MCM_TRY(gemm_tc_launch(g, st));
     }
     // softmax over the N text tokens (dim=1 of [B, N, H, hd], efficient_attention.py:78)
-    MCM_TRY(softmax_seg_launch(c->f32A, B * D, N, Np, N, pT, ff, st));
+    MCM_TRY(softmax_seg_launch(c->ws[0].f32A, B * D, N, Np, N, pT, ff, st));
     {  // ctx[b, h] = softmax(key)_h^T value_h  (hd x hd), stored transposed for the per-step q * ctx GEMM
       GemmProblem g;
       std::memset(&g, 0, sizeof(g));
@@ -672,7 +807,7 @@ int mcm_prepare_conditions(mcm_ctx* c, int B, const float* xf_out, int n_tokens,
     MCM_CHECK(c_len >= 1 && c_len <= T, "control condition longer than seq_len");
     // forward_c (controlnet_mcm.py:155-166): control_cond_input(c), zero-pad to T, + sequence_embedding[:len_c]
     const int fp = c->fmt_prec();
-    const OpPtr cin = view(c->opB, c->Cinp);
+    const OpPtr cin = view(c->ws[0].opB, c->Cinp);
     MCM_TRY(pack_op_launch(cond, B * c_len, c->Cin, c->Cin, false, cin, fp, st));
     MCM_CUDA(cudaMemsetAsync(c->cc32, 0, (size_t)B * T * D * 4, st));
     MCM_CUDA(cudaMemsetAsync(c->cc_op.hi, 0, (size_t)B * T * D * 2, st));
@@ -714,7 +849,7 @@ int mcm_block_forward(mcm_ctx* c, int kind, int index, int B, float* x_inout, co
   const int bi = kind == 0 ? index : c->nL + index;
   MCM_TRY(run_mod(c, B, emb, bi, 1, st));
   const OpPtr none{nullptr, nullptr, 0};
-  return run_block(c, c->blocks[bi], B, x_inout, c->mod32, c->mod_total, none, 0, st);
+  return run_block(c, c->ws[0], c->blocks[bi], B, x_inout, c->mod32, c->mod_total, none, 0, st);
 }
 
 int mcm_sample(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T, const float* step_noise, float* x0_out,

@@ -339,11 +339,24 @@ ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_mo
   }
 }
 
+__global__ void fill_timesteps_kernel(long long* __restrict__ t_buf, long long t, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) t_buf[i] = t;
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   return (int)std::min<size_t>(g, 148 * 16);
 }
 }  // namespace
+
+int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream) {
+  LaunchTimer lt(LK_ROW, stream);
+  fill_timesteps_kernel<<<(B + 255) / 256, 256, 0, stream>>>(t_buf, t, B);
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
 
 int elementwise_init() {
   MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
@@ -351,6 +364,7 @@ int elementwise_init() {
   return 0;
 }
 unsigned long long elementwise_launch_count() { return g_ew_launches.load(); }
+void elementwise_count_replayed(unsigned long long n) { g_ew_launches.fetch_add(n); }
 
 int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, const float* b, const float* scale,
                    const float* shift, int mod_ld, int rows_per_batch, bool act_silu, OpPtr out, int out_fmt,

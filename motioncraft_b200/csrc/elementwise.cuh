@@ -41,7 +41,11 @@ int ddim_update_launch(const float* x, const float* eps, const float* noise, flo
 int ddpm_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
                        DdpmCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream);
 
+// t_buf[0..B) = t  (the timestep of the current sampler step, read by the graph-captured timestep embedding)
+int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream);
+
 int elementwise_init();
 unsigned long long elementwise_launch_count();
+void elementwise_count_replayed(unsigned long long n);
 
 }  // namespace mcm

@@ -65,6 +65,7 @@ int gemm_tc_init();
 
 // number of tcgen05 GEMM launches since process start (bench.py's gpu_launches evidence)
 unsigned long long gemm_tc_launch_count();
+void gemm_tc_count_replayed(unsigned long long n);   // kernels executed by a CUDA-graph replay
 // MCM_DEBUG_EPI=3: summed epilogue-warp cycles per phase (development aid)
 int gemm_tc_debug_read(unsigned long long* out, int reset);
 

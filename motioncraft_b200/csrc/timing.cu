@@ -39,6 +39,7 @@ LaunchTimer::~LaunchTimer() {
 }
 
 void timing_enable(bool on) { g_on.store(on); }
+bool timing_enabled() { return g_on.load(std::memory_order_relaxed); }
 
 int timing_collect(double* ms, unsigned long long* launches, double* flops) {
   cudaDeviceSynchronize();

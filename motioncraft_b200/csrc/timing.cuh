@@ -18,6 +18,7 @@ class LaunchTimer {
 };
 
 void timing_enable(bool on);
+bool timing_enabled();
 // returns 0; fills ms / launches / flops per LaunchKind and clears the record
 int timing_collect(double* ms, unsigned long long* launches, double* flops);
 }  // namespace mcm

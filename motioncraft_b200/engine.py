@@ -85,6 +85,10 @@ class DenoiserEngine:
         except Exception:
             pass
 
+    def set_option(self, name, value):
+        """Scheduling knobs ("dual", "graph", "chunk"); results are bit-identical in every mode."""
+        _lib.check(self.lib.mcm_set_option(self._ctx, name.encode(), int(value)))
+
     # ------------------------------------------------------------------ conditions
     def prepare_conditions(self, xf_out, xf_proj, c=None):
         xf_out = _f32c(xf_out, self.device)

@@ -261,3 +261,41 @@ def test_full_batch_properties_t2m():
     want = C.oracle_ddim(sd, x[sel], xf_proj[sel], xf_out[sel])
     assert C.rel_l2(x0[sel], want) < TOL_FAST
     eng.close()
+
+
+@pytest.mark.parametrize("env", [{"MCM_GRAPH": "0", "MCM_DUAL": "0"}, {"MCM_GRAPH": "0", "MCM_DUAL": "1"},
+                                 {"MCM_GRAPH": "1", "MCM_DUAL": "0"}, {"MCM_CHUNK": "2"}, {"MCM_PAIR": "1"}])
+def test_execution_modes_give_identical_results(env, tmp_path):
+    """Eager vs CUDA-graph replay, one vs two streams (batch halves), sample chunking and cta_group::2 pair tiles are
+    scheduling choices: the sampled x_0 must be BIT-identical to the default mode (graph + dual stream).  Modes are read
+    from the environment at context creation, so each runs in a fresh process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from motioncraft_b200.engine import DenoiserEngine, SamplerTables
+from oracle import mcm_oracle as O
+from tests import common as C
+T, B = 60, 5
+x, xf_out, xf_proj = C.inputs(B, T)
+eng = DenoiserEngine(C.hot(C.base_state(T)), seq_len=T, max_batch=B)
+eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda())
+tables, tmap = O.spaced_tables(1000, "10")
+x0 = eng.sample(SamplerTables(tables, tmap, "ddim"), x.cuda())
+x0b = eng.sample(SamplerTables(tables, tmap, "ddim"), x.cuda())      # second run replays the cached graph
+assert torch.equal(x0, x0b)
+torch.save(x0.cpu(), sys.argv[1])
+""" % root
+    outs = []
+    for e_extra in ({}, env):
+        e = dict(os.environ)
+        for k in ("MCM_GRAPH", "MCM_DUAL", "MCM_CHUNK", "MCM_PAIR"):
+            e.pop(k, None)
+        e.update(e_extra)
+        f = str(tmp_path / ("x0_%d.pt" % len(outs)))
+        r = subprocess.run([sys.executable, "-c", code, f], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        outs.append(torch.load(f))
+    assert torch.equal(outs[0], outs[1])
