@@ -205,6 +205,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Programmatic dependent launch: every kernel of this library is launched with the programmatic-stream-serialization
+// attribute.  pdl_trigger() (first statement) lets the NEXT kernel of the stream be scheduled while this one still
+// runs; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible, and must precede the
+// first global-memory access.  What overlaps is the launch latency and the memory-free prologue of each kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 __device__ __forceinline__ float warp_sum(float v) {
@@ -218,5 +224,24 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// host-side launch with the PDL attribute (MCM_PDL=0 disables it)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 }  // namespace mcm

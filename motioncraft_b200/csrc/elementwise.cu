@@ -89,6 +89,8 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
                const float* __restrict__ b, const float* __restrict__ scale, const float* __restrict__ shift,
                int mod_ld, int rows_per_batch, int act_silu, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo,
                int out_ld) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -157,6 +159,8 @@ template <int LPS, int EPL, int FMT>
 __global__ void __launch_bounds__(256)
 softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols, int ld_in, int seg, int nseg,
                    uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int SPW = 32 / LPS;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -200,6 +204,8 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __restrict__ w,
                     const float* __restrict__ b, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float tile[];            // T * 33
   __shared__ float red[8][33];
   __shared__ float mean_s[32], rstd_s[32];
@@ -254,6 +260,8 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
 // ------------------------------------------------------------------------------------------ pack_op
 __global__ void __launch_bounds__(256)
 pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, int act_silu, OpPtr out, int out_fmt) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = rows * (size_t)out.ld;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / out.ld;
@@ -270,6 +278,8 @@ pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, i
 // ------------------------------------------------------------------------------------------ timestep embedding
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t_dev, int t_uniform, int B, int dim,
                                           OpPtr out, int out_fmt) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * out.ld) return;
@@ -291,6 +301,8 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t_dev, i
 __global__ void __launch_bounds__(256)
 ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_model, const float* __restrict__ noise,
                    float* __restrict__ x_out, size_t rows, int cols, DdimCoefs k, OpPtr xop, int op_fmt) {
+  pdl_trigger();
+  pdl_wait();
   // gaussian_diffusion.py:572-577 (x0 from eps), :587-591 (eps re-derived), :839-852 (Equation 12);
   // same fp32 operation order as the reference, no fused multiply-adds
   const float one_m_abp = __fsub_rn(1.f, k.alpha_bar_prev);
@@ -320,6 +332,8 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_mo
 __global__ void __launch_bounds__(256)
 ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_model, const float* __restrict__ noise,
                    float* __restrict__ x_out, size_t rows, int cols, DdpmCoefs k, OpPtr xop, int op_fmt) {
+  pdl_trigger();
+  pdl_wait();
   // gaussian_diffusion.py:572-577, :445-449 (posterior mean), :694 (mean + exp(0.5 logvar) * noise)
   const float sd = expf(__fmul_rn(0.5f, k.log_var));
   const int ldo = xop.hi ? xop.ld : cols;
@@ -340,6 +354,8 @@ ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_mo
 }
 
 __global__ void fill_timesteps_kernel(long long* __restrict__ t_buf, long long t, int B) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) t_buf[i] = t;
 }
@@ -352,7 +368,7 @@ inline int grid_for(size_t total, int block) {
 
 int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream) {
   LaunchTimer lt(LK_ROW, stream);
-  fill_timesteps_kernel<<<(B + 255) / 256, 256, 0, stream>>>(t_buf, t, B);
+  MCM_CUDA(launch_pdl(fill_timesteps_kernel, dim3((B + 255) / 256), dim3(256), (size_t)(0), stream, t_buf, t, B));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -380,16 +396,16 @@ int ln_rows_launch(const float* in, int rows, int d, int ld_in, const float* w, 
   uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
   LaunchTimer lt(LK_ROW, stream);
 #define MCM_LN_GO(V, F)                                                                                          \
-  ln_rows_kernel<V, F><<<grid, wpb * 32, 0, stream>>>(in, rows, d, ld_in, w, b, scale, shift, mod_ld, rpb,       \
-                                                      act_silu ? 1 : 0, hi, lo, out.ld)
+  MCM_CUDA(launch_pdl(ln_rows_kernel<V, F>, dim3(grid), dim3(wpb * 32), (size_t)0, stream, in, rows, d, ld_in, w, b,   \
+                      scale, shift, mod_ld, rpb, act_silu ? 1 : 0, hi, lo, out.ld))
 #define MCM_LN_CASE(V)                                                                                           \
   case V:                                                                                                        \
-    if (out_fmt == OP_F16) MCM_LN_GO(V, OP_F16); else MCM_LN_GO(V, OP_BF16X2);                                   \
+    if (out_fmt == OP_F16) { MCM_LN_GO(V, OP_F16); } else { MCM_LN_GO(V, OP_BF16X2); }                           \
     break;
   switch (nv) {
     MCM_LN_CASE(1) MCM_LN_CASE(2) MCM_LN_CASE(3) MCM_LN_CASE(4) MCM_LN_CASE(5) MCM_LN_CASE(6) MCM_LN_CASE(7)
     default:
-      if (out_fmt == OP_F16) MCM_LN_GO(8, OP_F16); else MCM_LN_GO(8, OP_BF16X2);
+      if (out_fmt == OP_F16) { MCM_LN_GO(8, OP_F16); } else { MCM_LN_GO(8, OP_BF16X2); }
   }
 #undef MCM_LN_CASE
 #undef MCM_LN_GO
@@ -411,8 +427,8 @@ int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg,
 #define MCM_SM_GO(LPS, EPL, F)                                                                                   \
   {                                                                                                              \
     const long long warps = (total + (32 / LPS) - 1) / (32 / LPS);                                               \
-    softmax_seg_kernel<LPS, EPL, F><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(               \
-        in, total, ncols, ld_in, seg, nseg, hi, lo, out.ld);                                                     \
+    MCM_CUDA(launch_pdl(softmax_seg_kernel<LPS, EPL, F>, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), (size_t)(0), stream, \
+        in, total, ncols, ld_in, seg, nseg, hi, lo, out.ld));                                                     \
   }
 #define MCM_SM_LAUNCH(LPS, EPL)                                                                                  \
   { if (out_fmt == OP_F16) MCM_SM_GO(LPS, EPL, OP_F16) else MCM_SM_GO(LPS, EPL, OP_BF16X2) }
@@ -439,9 +455,9 @@ int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, con
   uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
   LaunchTimer lt(LK_ROW, stream);
   if (out_fmt == OP_F16)
-    ln_transpose_kernel<OP_F16><<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, hi, lo, out.ld);
+    MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_F16>, dim3(grid), dim3(block), (size_t)((size_t)T * 33 * sizeof(float)), stream, h, T, D, w, b, hi, lo, out.ld));
   else
-    ln_transpose_kernel<OP_BF16X2><<<grid, block, (size_t)T * 33 * sizeof(float), stream>>>(h, T, D, w, b, hi, lo, out.ld);
+    MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_BF16X2>, dim3(grid), dim3(block), (size_t)((size_t)T * 33 * sizeof(float)), stream, h, T, D, w, b, hi, lo, out.ld));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -452,7 +468,7 @@ int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu
   MCM_CHECK(out.ld >= cols, "pack_op: output pitch too small");
   const size_t total = (size_t)rows * out.ld;
   LaunchTimer lt(LK_ROW, stream);
-  pack_op_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, (size_t)rows, cols, ld_in, act_silu ? 1 : 0, out, out_fmt);
+  MCM_CUDA(launch_pdl(pack_op_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, in, (size_t)rows, cols, ld_in, act_silu ? 1 : 0, out, out_fmt));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -462,7 +478,7 @@ int timestep_embedding_launch(const long long* t_dev, int t_uniform, int B, int 
                               cudaStream_t stream) {
   const int total = B * out.ld;
   LaunchTimer lt(LK_ROW, stream);
-  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t_dev, t_uniform, B, dim, out, out_fmt);
+  MCM_CUDA(launch_pdl(timestep_embedding_kernel, dim3((total + 255) / 256), dim3(256), (size_t)(0), stream, t_dev, t_uniform, B, dim, out, out_fmt));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -473,7 +489,7 @@ int ddim_update_launch(const float* x, const float* eps, const float* noise, flo
   MCM_CHECK(!c.add_noise || noise != nullptr, "ddim_update: eta != 0 needs step noise");
   const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
   LaunchTimer lt(LK_ROW, stream);
-  ddim_update_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, eps, noise, x_out, rows, cols, c, xop, op_fmt);
+  MCM_CUDA(launch_pdl(ddim_update_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, x, eps, noise, x_out, rows, cols, c, xop, op_fmt));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;
@@ -484,7 +500,7 @@ int ddpm_update_launch(const float* x, const float* eps, const float* noise, flo
   MCM_CHECK(!c.add_noise || noise != nullptr, "ddpm_update: needs step noise");
   const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
   LaunchTimer lt(LK_ROW, stream);
-  ddpm_update_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, eps, noise, x_out, rows, cols, c, xop, op_fmt);
+  MCM_CUDA(launch_pdl(ddpm_update_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, x, eps, noise, x_out, rows, cols, c, xop, op_fmt));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

@@ -180,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t abar[NUM_EPI_WARPS];   // addend-tile arrival, one per epilogue warp
   __shared__ __align__(16) float bias_s[NUM_EPI_WARPS][32];
 
+  pdl_trigger();                                      // the next kernel of the stream may start its prologue
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -214,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
+  pdl_wait();                                         // prologue done; from here on global memory is touched
   const uint32_t tmem_base = tmem_slot;
   const int crank = p.cs > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / p.cs;
@@ -948,6 +950,11 @@ int gemm_tc_init() {
   return g_init_status;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MCM_PDL"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 unsigned long long gemm_tc_launch_count() { return g_launches.load(); }
 void gemm_tc_count_replayed(unsigned long long n) { g_launches.fetch_add(n); }
 
@@ -1084,10 +1091,12 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_TOTAL;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t le;
     if (p.pair) le = need_generic ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, true>, tmA, tmAlo, tmB, tmBlo, em, p)
                                   : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, true>, tmA, tmAlo, tmB, tmBlo, em, p);
