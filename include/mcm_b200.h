@@ -66,7 +66,9 @@ void mcm_destroy(mcm_ctx* ctx);
 /* Scheduling options (no effect on results, which are bit-identical in every mode):
  *   "dual"  1 = run the two halves of a batch on two streams (default), 0 = one stream
  *   "graph" 1 = replay a captured CUDA graph per sampler step (default), 0 = eager launches
- *   "chunk" n = pass the batch through the layer stack n samples at a time (default 0 = whole batch) */
+ *   "chunk" n = pass the batch through the layer stack n samples at a time (default 0 = whole batch)
+ *   "fused" 1 = cross-attention + FFN of a layer in one persistent kernel (default; same arithmetic, fp32 reduction
+ *               order of the LayerNorm statistics differs), 0 = one kernel per GEMM / row op */
 int mcm_set_option(mcm_ctx* ctx, const char* name, int value);
 
 /* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key
@@ -123,6 +125,10 @@ int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const f
 void mcm_timing_enable(int on);
 int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops);
 
+/* Development aid for the fused cross-attention + FFN kernel: after mcm_set_option(ctx, "fused_stop", k) every tile runs
+ * only its first k phases; what = 0 copies the fp16 dump of the shared-memory operand tile [B*T, 512], what = 1 the
+ * hidden-activation scratch, into device memory dst_dev. */
+int mcm_debug_copy(mcm_ctx* ctx, int what, void* dst_dev, long long bytes);
 /* Development aid (MCM_DEBUG_EPI=3): summed clock cycles of the GEMM epilogue warps per phase; out[16]. */
 int mcm_debug_read(unsigned long long* out, int reset);
 

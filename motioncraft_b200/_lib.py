@@ -51,6 +51,7 @@ SIGNATURES = {
     "mcm_timing_collect": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong),
                                 ctypes.POINTER(ctypes.c_double)]),
     "mcm_debug_read": (_I, [ctypes.POINTER(ctypes.c_ulonglong), _I]),
+    "mcm_debug_copy": (_I, [_VP, _I, _VP, _LL]),
     "mcm_last_error": (ctypes.c_char_p, []),
     "mcm_gemm_launches": (ctypes.c_ulonglong, []),
     "mcm_kernel_launches": (ctypes.c_ulonglong, []),

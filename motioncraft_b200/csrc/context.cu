@@ -18,6 +18,7 @@
 
 #include "../../include/mcm_b200.h"
 #include "elementwise.cuh"
+#include "fused_block.cuh"
 #include "gemm_tc.cuh"
 #include "timing.cuh"
 
@@ -51,6 +52,7 @@ struct Ctrl {
 struct Scratch {
   float *h32, *f32A, *f32B, *c32;
   OpPtr opA, opB, opC, opD, hop, ctxT_sa, c_op;
+  void* hid;   // hidden-activation scratch of the fused cross-attention + FFN kernel
 };
 }  // namespace mcm
 
@@ -59,6 +61,9 @@ using namespace mcm;
 struct mcm_ctx {
   mcm_config cfg;
   int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
+  int fused = 1;          // MCM_FUSED=0: run cross-attention + FFN as separate GEMM / row kernels (the round-1 path)
+  int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
+  void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
   bool finalized = false;
   bool cond_ready = false;
@@ -86,7 +91,7 @@ struct mcm_ctx {
   // the step's timestep is read from `t_buf`, so the graph is identical for all steps.
   int use_graph = 1;                     // MCM_GRAPH=0: eager launches
   long long* t_buf = nullptr;
-  struct StepGraph { int B; bool have_c; cudaGraphExec_t exec; unsigned long long n_gemm, n_row; };
+  struct StepGraph { int B; bool have_c; int fused; cudaGraphExec_t exec; unsigned long long n_gemm, n_row, n_fused; };
   std::vector<StepGraph> graphs;
 
   int fmt_fast() const { return cfg.precise_all ? OP_BF16X2 : OP_F16; }
@@ -316,6 +321,26 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     MCM_TRY(gemm_tc_launch(g, st));
   }
 
+  if (c->fused && ff == OP_F16 && w.hid != nullptr && fused_block_supported(T, D, F, H)) {
+    // ---- cross attention + FFN in ONE persistent kernel (fused_block.cu) ----
+    FusedBlockArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.h = h; a.rows = B * T; a.T = T; a.batch = B;
+    a.ca_ln_w = k.ca_ln_w; a.ca_ln_b = k.ca_ln_b; a.ca_wq = k.ca_wq; a.ca_bq = k.ca_bq;
+    a.ca_ctxT = offs(k.ca_ctxT, (size_t)b0 * H * hdD * hdD);
+    a.ca_pn_w = k.ca_pn_w; a.ca_pn_b = k.ca_pn_b;
+    a.ca_scale = mod + k.mod_off + 2 * T; a.ca_shift = mod + k.mod_off + 2 * T + D;
+    a.ca_wo = k.ca_wo; a.ca_bo = k.ca_bo;
+    a.f_w1 = k.f_w1; a.f_b1 = k.f_b1; a.f_w2 = k.f_w2; a.f_b2 = k.f_b2;
+    a.f_pn_w = k.f_pn_w; a.f_pn_b = k.f_pn_b;
+    a.f_scale = mod + k.mod_off + 2 * T + 2 * D; a.f_shift = mod + k.mod_off + 2 * T + 3 * D;
+    a.f_wo = k.f_wo; a.f_bo = k.f_bo;
+    a.mod_ld = mod_ld; a.hid = w.hid; a.stop = c->fused_stop; a.dbg = c->fused_dbg;
+    MCM_TRY(fused_block_launch(a, st));
+    if (final_op.hi) MCM_TRY(pack_op_launch(h, B * T, D, D, false, final_op, final_op_fmt, st));
+    return 0;
+  }
+
   // ---- text cross attention (EfficientCrossAttention, efficient_attention.py:64-92) ----
   MCM_TRY(ln_rows_launch(h, B * T, D, D, k.ca_ln_w, k.ca_ln_b, nullptr, nullptr, 4, T, false, opA_d, ff, st));
   {
@@ -501,15 +526,16 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
   MCM_TRY(fill_timesteps_launch(c->t_buf, (long long)t, B, gs));
   cudaGraphExec_t exec = nullptr;
   for (auto& g : c->graphs)
-    if (g.B == B && g.have_c == c->have_c) {
+    if (g.B == B && g.have_c == c->have_c && g.fused == c->fused) {
       exec = g.exec;
       gemm_tc_count_replayed(g.n_gemm);          // keep the library's launch counters truthful under graph replay
       elementwise_count_replayed(g.n_row);
+      fused_block_count_replayed(g.n_fused);
     }
   if (exec == nullptr) {
     // capture (the launches are recorded, not executed), instantiate, remember
     cudaGraph_t graph = nullptr;
-    const unsigned long long g0 = gemm_tc_launch_count(), r0 = elementwise_launch_count();
+    const unsigned long long g0 = gemm_tc_launch_count(), r0 = elementwise_launch_count(), f0 = fused_block_launch_count();
     MCM_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
     const int rc = run_denoiser(c, B, c->t_buf, 0, c->eps32, gs);
     const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
@@ -521,7 +547,8 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     MCM_CUDA(ie);
-    c->graphs.push_back({B, c->have_c, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0});
+    c->graphs.push_back({B, c->have_c, c->fused, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
+                         fused_block_launch_count() - f0});
   }
   MCM_CUDA(cudaGraphLaunch(exec, gs));
   if (hop_stream) {
@@ -574,10 +601,18 @@ extern "C" {
 
 const char* mcm_last_error(void) { return g_last_error.c_str(); }
 const char* mcm_version(void) { return "motioncraft_b200 0.1.0 (sm_100a, tcgen05)"; }
-unsigned long long mcm_gemm_launches(void) { return gemm_tc_launch_count(); }
-unsigned long long mcm_kernel_launches(void) { return gemm_tc_launch_count() + elementwise_launch_count(); }
+unsigned long long mcm_gemm_launches(void) { return gemm_tc_launch_count() + fused_block_launch_count(); }
+unsigned long long mcm_kernel_launches(void) { return gemm_tc_launch_count() + fused_block_launch_count() + elementwise_launch_count(); }
 
 int mcm_debug_read(unsigned long long* out, int reset) { return gemm_tc_debug_read(out, reset); }
+int mcm_debug_copy(mcm_ctx* c, int what, void* dst_dev, long long bytes) {
+  MCM_CHECK(c != nullptr && dst_dev != nullptr && bytes > 0, "bad argument");
+  const void* src = what == 0 ? c->fused_dbg : c->ws[0].hid;
+  MCM_CHECK(src != nullptr, "no such debug buffer");
+  MCM_CUDA(cudaDeviceSynchronize());
+  MCM_CUDA(cudaMemcpy(dst_dev, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+  return 0;
+}
 void mcm_timing_enable(int on) { timing_enable(on != 0); }
 int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops) {
   MCM_CHECK(ms && launches && flops, "null argument");
@@ -637,6 +672,11 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
     if (alloc_op(c, &c->cc_op, R1 * c->D, c->D, lo)) return fail(0);
     if (alloc_op(c, &c->ws[0].c_op, R1 * c->D, c->D, lo)) return fail(0);
   }
+  if (const char* e = getenv("MCM_FUSED")) c->fused = atoi(e);
+  c->ws[0].hid = nullptr;
+  if (!lo && fused_block_supported(c->T, c->D, c->F, c->H)) {
+    if (dev_alloc(c, &c->ws[0].hid, fused_block_hid_bytes())) return fail(0);
+  }
   if (const char* e = getenv("MCM_DUAL")) c->dual = atoi(e);
   if (const char* e = getenv("MCM_GRAPH")) c->use_graph = atoi(e);
   if (dev_alloc(c, reinterpret_cast<void**>(&c->t_buf), (size_t)c->Bmax * sizeof(long long))) return fail(0);
@@ -661,6 +701,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
     if (alloc_op(c, &w.opD, H1 * c->D, 8, lo)) return fail(0);
     if (alloc_op(c, &w.hop, H1 * c->D, c->D, true)) return fail(0);
     if (alloc_op(c, &w.ctxT_sa, Bh * c->T * c->Tp, c->Tp, lo)) return fail(0);
+    if (c->ws[0].hid != nullptr && dev_alloc(c, &w.hid, fused_block_hid_bytes())) return fail(0);
     if (c->nC > 0) {
       if (alloc_f32(c, &w.c32, H1 * c->D)) return fail(0);
       if (alloc_op(c, &w.c_op, H1 * c->D, c->D, lo)) return fail(0);
@@ -688,6 +729,13 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     c->use_graph = value;
   } else if (n == "chunk") {
     c->chunk = value;
+  } else if (n == "fused") {
+    c->fused = value;
+  } else if (n == "fused_stop") {
+    MCM_CHECK(value >= 0 && value <= 7, "fused_stop must be 0..7");
+    c->fused_stop = value;
+    if (value != 0 && c->fused_dbg == nullptr)
+      MCM_TRY(dev_alloc(c, &c->fused_dbg, (size_t)c->Bmax * c->T * c->D * 2));
   } else {
     set_error("unknown option: " + n);
     return 1;

@@ -1,0 +1,746 @@
+// motioncraft_b200 -- fused cross-attention + FFN token kernel (see fused_block.cuh).
+//
+// One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256-row tile; each CTA owns 128 rows:
+//   warp 0      TMA producer : streams weight / context / hidden slabs (128 rows x 64 fp16, 128B swizzle) through a
+//                              4-slot ring; each CTA loads its half of every B tile, all bytes land on the LEADER's barrier
+//   warp 1      MMA issuer   : leader CTA only, tcgen05.mma.cta_group::2 (M = 256, N = 256 or 128), accumulators in TMEM
+//   warps 2..9  compute      : row phases.  "P" phases read h rows (warp per row, coalesced) and write the A operand
+//                              tile OPA (128 x 512 fp16, 8 swizzled slabs) in shared memory; "E" phases read the TMEM
+//                              accumulator (thread = row) and apply bias / softmax / LayerNorm + AdaLN + SiLU / GELU,
+//                              writing either OPA (the next GEMM's A operand), the hidden scratch (TMA store) or the
+//                              residual stream h (TMA reduce-add).
+// Per tile (reference lines in brackets):
+//   P0  OPA = LN(h)                          [efficient_attention.py:73 norm]
+//   G1  q = OPA Wq^T                   E1  OPA = softmax_head(q + bq)               [:73, :75 query softmax]
+//   per sample s of the tile:
+//   G2  y = OPA blockdiag(ctx[s])      E2  rows of s: OPA = SiLU(LN(y) (1+scale_s) + shift_s)   [:88-90, stylization_block.py:38-39]
+//   G3  d = OPA Wo^T                   E3  h += d + bo ; OPA = fp16(h)              [:39-40 ; residual efficient_attention.py:91]
+//   G4  u = OPA W1^T (4 quarters)      E4  HID = GELU(u + b1)                       [diffusion_transformer.py:26]
+//   G5  y = HID W2^T                   E5  OPA = SiLU(LN(y + b2) (1+scale) + shift) [:26-27]
+//   G6  d = OPA Wo2^T                  E6  h += d + bo2
+// The MMA <-> compute hand-off uses one "accumulator half drained / operand written" barrier per TMEM half (tempty,
+// on the leader, 16 warp arrivals) and one "accumulator half complete" barrier (tfull, multicast commit).
+#include "fused_block.cuh"
+
+#include <atomic>
+#include <cstring>
+
+#include "gemm_tc.cuh"
+#include "ptx_extra.cuh"
+#include "timing.cuh"
+
+namespace mcm {
+namespace {
+
+constexpr int D = 512, F = 1024, H = 4, HD = 128;
+constexpr int ROWS = 128;                  // rows per CTA
+constexpr int SLAB = 16384;                // 128 rows x 64 fp16
+constexpr int NSLOT = 4;
+constexpr int NCW = 8;                     // compute warps
+constexpr int THREADS = 64 + 32 * NCW;
+constexpr int OPA_BYTES = (D / 64) * SLAB;
+constexpr int RING_BYTES = NSLOT * SLAB;
+constexpr int STG_BYTES = NCW * 4096;
+constexpr int SMEM_BYTES = OPA_BYTES + RING_BYTES + STG_BYTES + 1024;
+constexpr int MAX_SAMPLES = 6;             // samples a 256-row tile may span (4 KB of staged AdaLN parameters each)
+constexpr int XCH_OFF = MAX_SAMPLES * 4096;   // LayerNorm partial statistics, inside the staging region
+constexpr int TMEM_COLS = 512;
+constexpr float L2E = 1.4426950408889634f;
+
+struct FbMaps {
+  CUtensorMap wq, ctx, wo, w1, hida, w2, wo2, hred, hidst;
+};
+
+struct FbParams {
+  const float* h;
+  int rows, T, batch, n_tiles, mod_ld, stop;
+  const float *ca_ln_w, *ca_ln_b, *ca_bq, *ca_pn_w, *ca_pn_b, *ca_scale, *ca_shift, *ca_bo;
+  const float *f_b1, *f_b2, *f_pn_w, *f_pn_b, *f_scale, *f_shift, *f_bo;
+  uint16_t* dbg;
+};
+
+__device__ __forceinline__ void st_shared_v2u(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float silu_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + ex2_fast(-x * L2E)));
+  return x * r;
+}
+// shared-memory address of the 16-byte chunk holding columns [col, col + 8) of row `row` of the operand tile
+__device__ __forceinline__ uint32_t opa_addr(uint32_t opa, int row, int col) {
+  return opa + (uint32_t)(col >> 6) * SLAB + (uint32_t)row * 128u + (((((uint32_t)col >> 3) & 7u) ^ ((uint32_t)row & 7u)) << 4);
+}
+// v[j] += b[j] where lane j holds b[j]: through the warp's 128-byte shared slot (1 STS + 8 broadcast LDS.128)
+__device__ __forceinline__ void add_bias32(float* slot, int lane, float mine, float* v) {
+  slot[lane] = mine;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b4 = *reinterpret_cast<const float4*>(slot + 4 * q);
+    v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+  }
+  __syncwarp();
+}
+
+// ---- P phase: 128 rows of h -> (LayerNorm) -> fp16 -> OPA.  Warp per row, the reduction order of ln_rows_kernel.
+template <bool LN>
+__device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int rows, long long g0, uint32_t opa, int ew,
+                                            int lane, const float* __restrict__ lnw, const float* __restrict__ lnb) {
+  float4 gw[4], gb[4];
+  if (LN) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gw[j] = __ldg(reinterpret_cast<const float4*>(lnw) + j * 32 + lane);
+      gb[j] = __ldg(reinterpret_cast<const float4*>(lnb) + j * 32 + lane);
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < ROWS / NCW; i += 2) {
+    float4 x[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long g = g0 + ew + NCW * (i + u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        x[u][j] = g < rows ? __ldcg(reinterpret_cast<const float4*>(h + g * D) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = ew + NCW * (i + u);
+      float mean = 0.f, rstd = 1.f;
+      if (LN) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += (x[u][j].x + x[u][j].y) + (x[u][j].z + x[u][j].w);
+        mean = warp_sum(s) / (float)D;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = x[u][j].x - mean, b = x[u][j].y - mean, c = x[u][j].z - mean, e = x[u][j].w - mean;
+          ss += (a * a + b * b) + (c * c + e * e);
+        }
+        rstd = rsqrtf(warp_sum(ss) / (float)D + 1e-5f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y0 = x[u][j].x, y1 = x[u][j].y, y2 = x[u][j].z, y3 = x[u][j].w;
+        if (LN) {
+          y0 = fmaf((y0 - mean) * rstd, gw[j].x, gb[j].x);
+          y1 = fmaf((y1 - mean) * rstd, gw[j].y, gb[j].y);
+          y2 = fmaf((y2 - mean) * rstd, gw[j].z, gb[j].z);
+          y3 = fmaf((y3 - mean) * rstd, gw[j].w, gb[j].w);
+        }
+        const int col = j * 128 + lane * 4;
+        st_shared_v2u(opa_addr(opa, r, col) + (uint32_t)(lane & 1) * 8u, pack_f16x2_sat(y0, y1), pack_f16x2_sat(y2, y3));
+      }
+    }
+  }
+}
+
+// ---- E1: per-head softmax of (acc + bq) over the 128 columns of each of this warp's two heads -> OPA
+__device__ __forceinline__ void epi_softmax(uint32_t trow, int hf, int row, uint32_t opa, float* bslot, int lane,
+                                            const float (&bp)[8]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int col0 = hf * 256 + i * 128;
+    float v[128];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld_32x32(trow + (uint32_t)(col0 + c * 32), v + 32 * c);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) add_bias32(bslot, lane, bp[i * 4 + c], v + 32 * c);
+    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+    for (int j = 4; j < 128; j += 4) {
+      m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+    }
+    const float ml = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * L2E;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 128; j += 4) {
+      v[j] = ex2_fast(fmaf(v[j], L2E, -ml));         s0 += v[j];
+      v[j + 1] = ex2_fast(fmaf(v[j + 1], L2E, -ml)); s1 += v[j + 1];
+      v[j + 2] = ex2_fast(fmaf(v[j + 2], L2E, -ml)); s2 += v[j + 2];
+      v[j + 3] = ex2_fast(fmaf(v[j + 3], L2E, -ml)); s3 += v[j + 3];
+    }
+    const float inv = 1.f / ((s0 + s1) + (s2 + s3));
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      st_shared_v4u(opa_addr(opa, row, col0 + 8 * q), pack_f16x2_sat(v[8 * q] * inv, v[8 * q + 1] * inv),
+                    pack_f16x2_sat(v[8 * q + 2] * inv, v[8 * q + 3] * inv), pack_f16x2_sat(v[8 * q + 4] * inv, v[8 * q + 5] * inv),
+                    pack_f16x2_sat(v[8 * q + 6] * inv, v[8 * q + 7] * inv));
+  }
+}
+
+// ---- E2 / E5: OPA = SiLU(LN_512(acc [+ bias]) * gamma' + beta') for the rows with act = true.
+// gamma' = w (1 + scale), beta' = b (1 + scale) + shift were staged per sample in shared memory (prm: [gamma' 512 | beta' 512]).
+// The two warps of a lane quadrant each own 256 columns and exchange (mean, M2) partial statistics.
+template <bool BIAS>
+__device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool act, const float* prm, float* xch, int ew,
+                                          int quad, uint32_t opa, float* bslot, int lane, const float (&bp)[8]) {
+  float K = 0.f, sd = 0.f, sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v[32];
+    tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
+    tmem_ld_wait();
+    if (BIAS) add_bias32(bslot, lane, bp[c], v);
+    if (c == 0) K = v[0];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = v[j] - K;
+      sd += d;
+      sq = fmaf(d, d, sq);
+    }
+  }
+  const float mean_w = fmaf(sd, 1.f / 256.f, K);
+  const float m2_w = fmaf(-sd * (1.f / 256.f), sd, sq);
+  xch[(ew * 32 + lane) * 2] = mean_w;
+  xch[(ew * 32 + lane) * 2 + 1] = m2_w;
+  bar_sync(1 + quad, 64);
+  const float mean_o = xch[((ew ^ 4) * 32 + lane) * 2];
+  const float m2_o = xch[((ew ^ 4) * 32 + lane) * 2 + 1];
+  const float delta = mean_o - mean_w;
+  const float mean = 0.5f * (mean_w + mean_o);
+  const float m2 = (m2_w + m2_o) + delta * delta * 128.f;
+  const float rstd = rsqrtf(m2 * (1.f / (float)D) + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v[32];
+    tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
+    tmem_ld_wait();
+    if (BIAS) add_bias32(bslot, lane, bp[c], v);
+    const int col = hf * 256 + c * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 ga = *reinterpret_cast<const float4*>(prm + col + 8 * q);
+      const float4 gb = *reinterpret_cast<const float4*>(prm + col + 8 * q + 4);
+      const float4 ba = *reinterpret_cast<const float4*>(prm + D + col + 8 * q);
+      const float4 bb = *reinterpret_cast<const float4*>(prm + D + col + 8 * q + 4);
+      const float y0 = silu_fast(fmaf((v[8 * q] - mean) * rstd, ga.x, ba.x));
+      const float y1 = silu_fast(fmaf((v[8 * q + 1] - mean) * rstd, ga.y, ba.y));
+      const float y2 = silu_fast(fmaf((v[8 * q + 2] - mean) * rstd, ga.z, ba.z));
+      const float y3 = silu_fast(fmaf((v[8 * q + 3] - mean) * rstd, ga.w, ba.w));
+      const float y4 = silu_fast(fmaf((v[8 * q + 4] - mean) * rstd, gb.x, bb.x));
+      const float y5 = silu_fast(fmaf((v[8 * q + 5] - mean) * rstd, gb.y, bb.y));
+      const float y6 = silu_fast(fmaf((v[8 * q + 6] - mean) * rstd, gb.z, bb.z));
+      const float y7 = silu_fast(fmaf((v[8 * q + 7] - mean) * rstd, gb.w, bb.w));
+      if (act)
+        st_shared_v4u(opa_addr(opa, row, col + 8 * q), pack_f16x2_sat(y0, y1), pack_f16x2_sat(y2, y3), pack_f16x2_sat(y4, y5),
+                      pack_f16x2_sat(y6, y7));
+    }
+  }
+}
+
+// ---- E3 / E6: h[rows, 256 columns of this warp] += acc + bias, 32 x 32 fp32 tiles through the warp's staging slot
+__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int hf, uint32_t stgw, const CUtensorMap* map, int grow0,
+                                             float* bslot, int lane, const float (&bp)[8], bool& pending) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v[32];
+    tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
+    tmem_ld_wait();
+    add_bias32(bslot, lane, bp[c], v);
+    if (pending) {
+      if (lane == 0) tma_wait_read0();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      st_shared_v4(stgw + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_3d(map, stgw, hf * 256 + c * 32, grow0, 0);
+      tma_commit();
+    }
+    pending = true;
+  }
+}
+
+__device__ __forceinline__ void stage_params(float* dst, int nsamp, int s_first, int batch, const float* __restrict__ w,
+                                             const float* __restrict__ b, const float* __restrict__ scale,
+                                             const float* __restrict__ shift, int mod_ld, int ctid) {
+  for (int idx = ctid; idx < nsamp * D; idx += NCW * 32) {
+    const int sl = idx >> 9, c = idx & (D - 1);
+    const int s = min(s_first + sl, batch - 1);
+    const float sc = 1.f + __ldg(scale + (size_t)s * mod_ld + c);
+    const float sh = __ldg(shift + (size_t)s * mod_ld + c);
+    dst[sl * 1024 + c] = __ldg(w + c) * sc;
+    dst[sl * 1024 + D + c] = fmaf(__ldg(b + c), sc, sh);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ FbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NSLOT];
+  __shared__ __align__(8) uint64_t empty_bar[NSLOT];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t hid_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[NCW][32];
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t opa = smem_base, ring = smem_base + OPA_BYTES, stg = ring + RING_BYTES;
+  uint8_t* const stg_gen = smem_raw + (stg - smem_u32(smem_raw));
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+  const int last = p.stop ? p.stop : 7;      // number of compute phases executed per tile (debug truncation)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.wq); tma_prefetch_desc(&tm.ctx); tma_prefetch_desc(&tm.wo); tma_prefetch_desc(&tm.w1);
+    tma_prefetch_desc(&tm.hida); tma_prefetch_desc(&tm.w2); tma_prefetch_desc(&tm.wo2);
+  }
+  if (warp == 2 && lane == 0) {
+    tma_prefetch_desc(&tm.hred); tma_prefetch_desc(&tm.hidst);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSLOT; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&tfull_bar[s]), 1);
+        mbar_init(smem_u32(&tempty_bar[s]), 2u * NCW);       // every compute warp of both CTAs
+      }
+      mbar_init(smem_u32(&hid_bar), NCW);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(smem_u32(&tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer (both CTAs)
+    int slot = 0, it = 0;
+    uint32_t ph = 0;
+    auto push = [&](const CUtensorMap* m, int c0, int c1, int c2, uint32_t bytes) {
+      mbar_wait(smem_u32(&empty_bar[slot]), ph ^ 1u);
+      const uint32_t bar = smem_u32(&full_bar[slot]);
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(bar, 2u * bytes);
+        tma_load_3d_2sm(m, bar, ring + (uint32_t)slot * SLAB, c0, c1, c2);
+      }
+      __syncwarp();
+      if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+    };
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
+      const int g0 = tile * 2 * ROWS;
+      const int s_first = g0 / p.T;
+      const int s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
+      if (last >= 2)
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < D / 64; ++kb) push(&tm.wq, kb * 64, n * 256 + rank * 128, 0, SLAB);
+      if (last >= 3)
+        for (int s = s_first; s <= s_last; ++s)
+          for (int hd = 0; hd < H; ++hd)
+            for (int kb = 0; kb < HD / 64; ++kb) push(&tm.ctx, kb * 64, rank * 64, s * H + hd, SLAB / 2);
+      if (last >= 4)
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < D / 64; ++kb) push(&tm.wo, kb * 64, n * 256 + rank * 128, 0, SLAB);
+      if (last >= 5)
+        for (int q = 0; q < 4; ++q)
+          for (int kb = 0; kb < D / 64; ++kb) push(&tm.w1, kb * 64, q * 256 + rank * 128, 0, SLAB);
+      if (last >= 6) {
+        mbar_wait(smem_u32(&hid_bar), (uint32_t)it & 1u);      // this CTA's hidden rows are in global memory
+        fence_proxy_async_all();
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < F / 64; ++kb) {
+            push(&tm.hida, kb * 64, (int)blockIdx.x * ROWS, 0, SLAB);
+            push(&tm.w2, kb * 64, n * 256 + rank * 128, 0, SLAB);
+          }
+      }
+      if (last >= 7)
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < D / 64; ++kb) push(&tm.wo2, kb * 64, n * 256 + rank * 128, 0, SLAB);
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer (leader CTA only)
+    if (rank == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      uint32_t te_par[2] = {0u, 0u};
+      // instruction descriptors: fp32 accumulate, fp16 A/B, K-major, N >> 3, M = 256 >> 4
+      const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      auto wait_te = [&](int hh) {
+        mbar_wait(smem_u32(&tempty_bar[hh]), te_par[hh]);
+        te_par[hh] ^= 1u;
+        tc_fence_after();
+      };
+      auto commit_tf = [&](int hh) {
+        if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[hh]), (uint16_t)3);
+        __syncwarp();
+      };
+      // one ring slab as the B operand against the resident A slab `a_addr`
+      auto step = [&](uint32_t a_addr, uint32_t dcol, uint32_t idesc, bool fresh) {
+        mbar_wait(smem_u32(&full_bar[slot]), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_addr = ring + (uint32_t)slot * SLAB;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(tmem_base + dcol, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                         (fresh && k == 0) ? 0u : 1u);
+          umma_commit_2sm(smem_u32(&empty_bar[slot]), (uint16_t)3);
+        }
+        __syncwarp();
+        if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+      };
+      // a full-width GEMM out of the resident operand tile: D[128(x2) x 512] = OPA[.. x 512] W[512 x 512]^T
+      auto gemm_opa_512 = [&]() {
+        for (int n = 0; n < 2; ++n)
+          for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)(n * 256), idesc256, kb == 0);
+      };
+      for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+        const int g0 = tile * 2 * ROWS;
+        const int s_first = g0 / p.T;
+        const int s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
+        if (last >= 2) {                                     // G1
+          wait_te(0); wait_te(1);
+          gemm_opa_512();
+          commit_tf(0); commit_tf(1);
+        }
+        if (last >= 3) {                                     // G2, one round per sample
+          for (int s = s_first; s <= s_last; ++s) {
+            wait_te(0); wait_te(1);
+            for (int hd = 0; hd < H; ++hd)
+              for (int kb = 0; kb < HD / 64; ++kb)
+                step(opa + (uint32_t)(hd * 2 + kb) * SLAB, (uint32_t)(hd * HD), idesc128, kb == 0);
+            commit_tf(0); commit_tf(1);
+          }
+        }
+        if (last >= 4) {                                     // G3
+          wait_te(0); wait_te(1);
+          gemm_opa_512();
+          commit_tf(0); commit_tf(1);
+        }
+        if (last >= 5) {                                     // G4: four 256-column quarters, alternating TMEM halves
+          for (int q = 0; q < 4; ++q) {
+            wait_te(q & 1);
+            for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)((q & 1) * 256), idesc256, kb == 0);
+            commit_tf(q & 1);
+          }
+        }
+        if (last >= 6) {                                     // G5: A (hidden) and B (W2) both stream through the ring
+          wait_te(0); wait_te(1);
+          for (int n = 0; n < 2; ++n)
+            for (int kb = 0; kb < F / 64; ++kb) {
+              const int sa = slot;
+              mbar_wait(smem_u32(&full_bar[sa]), ph);
+              if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+              const int sb = slot;
+              mbar_wait(smem_u32(&full_bar[sb]), ph);
+              if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_addr = ring + (uint32_t)sa * SLAB, b_addr = ring + (uint32_t)sb * SLAB;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_2sm(tmem_base + (uint32_t)(n * 256), make_smem_desc_sw128(a_addr + k * 32),
+                               make_smem_desc_sw128(b_addr + k * 32), idesc256, (kb == 0 && k == 0) ? 0u : 1u);
+                umma_commit_2sm(smem_u32(&empty_bar[sa]), (uint16_t)3);
+                umma_commit_2sm(smem_u32(&empty_bar[sb]), (uint16_t)3);
+              }
+              __syncwarp();
+            }
+          commit_tf(0); commit_tf(1);
+        }
+        if (last >= 7) {                                     // G6
+          wait_te(0); wait_te(1);
+          gemm_opa_512();
+          commit_tf(0); commit_tf(1);
+        }
+      }
+    }
+  } else {
+    // ================================================================== compute warps
+    const int ew = warp - 2;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int hf = ew >> 2;                    // which 256-column half of the accumulator this warp owns
+    const int row = quad * 32 + lane;          // this thread's row in thread-per-row phases
+    const int ctid = ew * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t stgw = stg + (uint32_t)ew * 4096u;
+    float* const bslot = bias_s[ew];
+    float* const prm_all = reinterpret_cast<float*>(stg_gen);
+    float* const xch = reinterpret_cast<float*>(stg_gen + XCH_OFF);
+    uint32_t tf_par[2] = {0u, 0u};
+    bool pending = false;                      // a bulk store / reduction of this warp may still read its staging slot
+    auto wait_tf = [&](int hh) {
+      mbar_wait(smem_u32(&tfull_bar[hh]), tf_par[hh]);
+      tf_par[hh] ^= 1u;
+      tc_fence_after();
+    };
+    // operand tile written / accumulator drained: tell the leader's MMA warp
+    auto arrive_te = [&](bool h0, bool h1) {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (h0) mbar_arrive_remote(smem_u32(&tempty_bar[0]), 0u);
+        if (h1) mbar_arrive_remote(smem_u32(&tempty_bar[1]), 0u);
+      }
+    };
+    auto drain_stores = [&](bool full) {       // staging slot reusable (reads done) or stores globally complete
+      if (pending) {
+        if (lane == 0) { if (full) tma_wait_all0(); else tma_wait_read0(); }
+        __syncwarp();
+        pending = false;
+      }
+    };
+
+    int it = 0;
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
+      const int g0 = tile * 2 * ROWS;                       // first row of the pair's tile
+      const int gc = g0 + rank * ROWS;                      // first row of this CTA
+      const int s_first = g0 / p.T;
+      const int s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
+      const int nsamp = s_last - s_first + 1;
+      const int grow = gc + row;
+      const int s_row = grow / p.T;
+      const int slot_row = min(max(s_row - s_first, 0), nsamp - 1);
+      int done = 0;                                          // compute phases finished for this tile
+
+      // ---- P0
+      drain_stores(false);
+      rows_to_opa<true>(p.h, p.rows, gc, opa, ew, lane, p.ca_ln_w, p.ca_ln_b);
+      if (++done < last) arrive_te(true, true);
+      if (done < last) {
+        // ---- E1
+        float bp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.ca_bq + hf * 256 + k * 32 + lane);
+        wait_tf(0); wait_tf(1);
+        epi_softmax(trow, hf, row, opa, bslot, lane, bp);
+        if (++done < last) arrive_te(true, true);
+      }
+      if (done < last) {
+        // ---- E2 (one round per sample of the tile)
+        stage_params(prm_all, nsamp, s_first, p.batch, p.ca_pn_w, p.ca_pn_b, p.ca_scale, p.ca_shift, p.mod_ld, ctid);
+        bar_sync(5, NCW * 32);
+        float bp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ++done;
+        for (int s = s_first; s <= s_last; ++s) {
+          wait_tf(0); wait_tf(1);
+          const bool act = (s_row == s) && (grow < p.rows);
+          if (__any_sync(0xffffffffu, act))
+            epi_lnmod<false>(trow, hf, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, bp);
+          if (s < s_last || done < last) arrive_te(true, true);
+        }
+      }
+      if (done < last) {
+        // ---- E3: h += d + bo, then OPA = fp16(h)
+        float bp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.ca_bo + hf * 256 + k * 32 + lane);
+        wait_tf(0); wait_tf(1);
+        epi_reduce_h(trow, hf, stgw, &tm.hred, gc + quad * 32, bslot, lane, bp, pending);
+        tc_fence_before();
+        drain_stores(true);
+        bar_sync(5, NCW * 32);                               // every reduction into this CTA's rows has been performed
+        rows_to_opa<false>(p.h, p.rows, gc, opa, ew, lane, nullptr, nullptr);
+        if (++done < last) arrive_te(true, true);
+      }
+      if (done < last) {
+        // ---- E4: hidden = GELU(u + b1) -> fp16 -> hidden scratch (this CTA's private rows)
+        float bp16[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) bp16[k] = __ldg(p.f_b1 + (k >> 2) * 256 + hf * 128 + (k & 3) * 32 + lane);
+        ++done;
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          wait_tf(q & 1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c, ++cnt) {
+            float v[32];
+            tmem_ld_32x32(trow + (uint32_t)((q & 1) * 256 + hf * 128 + c * 32), v);
+            tmem_ld_wait();
+            add_bias32(bslot, lane, bp16[q * 4 + c], v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            const uint32_t sl = stgw + (uint32_t)(cnt & 1) * 2048u;
+            if (cnt >= 2) {
+              if (lane == 0) tma_wait_read1();
+              __syncwarp();
+            }
+            const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq)
+              st_shared_v4u(sl + (uint32_t)lane * 64u + (((uint32_t)qq ^ sw) << 4), pack_f16x2_sat(v[8 * qq], v[8 * qq + 1]),
+                            pack_f16x2_sat(v[8 * qq + 2], v[8 * qq + 3]), pack_f16x2_sat(v[8 * qq + 4], v[8 * qq + 5]),
+                            pack_f16x2_sat(v[8 * qq + 6], v[8 * qq + 7]));
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tm.hidst, sl, q * 256 + hf * 128 + c * 32, (int)blockIdx.x * ROWS + quad * 32, 0);
+              tma_commit();
+            }
+          }
+          if (q < 2 || done < last) arrive_te((q & 1) == 0, (q & 1) == 1);
+        }
+        pending = true;
+        tc_fence_before();
+        drain_stores(true);                                  // hidden rows are in global memory
+        if (done < last && lane == 0) mbar_arrive(smem_u32(&hid_bar));
+      }
+      if (done < last) {
+        // ---- E5
+        bar_sync(5, NCW * 32);                               // all warps' staging slots are free
+        stage_params(prm_all, nsamp, s_first, p.batch, p.f_pn_w, p.f_pn_b, p.f_scale, p.f_shift, p.mod_ld, ctid);
+        bar_sync(5, NCW * 32);
+        float bp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.f_b2 + hf * 256 + k * 32 + lane);
+        wait_tf(0); wait_tf(1);
+        epi_lnmod<true>(trow, hf, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, bp);
+        if (++done < last) arrive_te(true, true);
+      }
+      if (done < last) {
+        // ---- E6
+        float bp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.f_bo + hf * 256 + k * 32 + lane);
+        bar_sync(5, NCW * 32);                               // nobody still reads the staged parameters / statistics
+        wait_tf(0); wait_tf(1);
+        epi_reduce_h(trow, hf, stgw, &tm.hred, gc + quad * 32, bslot, lane, bp, pending);
+        tc_fence_before();
+        ++done;
+      }
+      if (p.stop != 0 && p.dbg != nullptr) {
+        // debug: dump the operand tile (un-swizzled) after the last executed phase
+        fence_async_smem();
+        bar_sync(5, NCW * 32);
+        for (int idx = ctid; idx < ROWS * 64; idx += NCW * 32) {
+          const int r = idx >> 6, col = (idx & 63) * 8;
+          if (gc + r < p.rows) {
+            const float4 w4 = ld_shared_v4(opa_addr(opa, r, col));
+            *reinterpret_cast<float4*>(p.dbg + (size_t)(gc + r) * D + col) = w4;
+          }
+        }
+        bar_sync(5, NCW * 32);
+      }
+    }
+    drain_stores(true);                                      // bulk operations complete before the CTA exits
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // the peer may still arrive on / multicast into this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+std::atomic<unsigned long long> g_fb_launches{0};
+int g_fb_max_pairs = -1;
+
+int fb_init() {
+  if (g_fb_max_pairs >= 0) return 0;
+  MCM_TRY(gemm_tc_init());
+  MCM_CUDA(cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tc_num_sms() / 2 * 2);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, fused_block_kernel, &cfg));
+  MCM_CHECK(n > 0, "fused_block_kernel does not fit on this device");
+  g_fb_max_pairs = n;
+  return 0;
+}
+
+}  // namespace
+
+bool fused_block_supported(int T, int Dm, int Fm, int Hm) {
+  return Dm == D && Fm == F && Hm == H && (2 * ROWS - 1) / T + 2 <= MAX_SAMPLES;
+}
+size_t fused_block_hid_bytes() { return (size_t)160 * ROWS * F * 2; }
+unsigned long long fused_block_launch_count() { return g_fb_launches.load(); }
+void fused_block_count_replayed(unsigned long long n) { g_fb_launches.fetch_add(n); }
+
+int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
+  MCM_TRY(fb_init());
+  MCM_CHECK(a.h && a.hid && a.rows > 0 && a.T > 0 && a.batch > 0 && a.rows == a.batch * a.T, "fused block: bad arguments");
+  MCM_CHECK((2 * ROWS - 1) / a.T + 2 <= MAX_SAMPLES, "fused block: sequence too short for the fused kernel");
+  MCM_CHECK(a.ca_wq.ld == D && a.ca_wo.ld == D && a.f_w1.ld == D && a.f_w2.ld == F && a.f_wo.ld == D && a.ca_ctxT.ld == HD,
+            "fused block: unexpected operand pitch");
+  MCM_CHECK(a.mod_ld % 4 == 0, "fused block: modulation pitch");
+  const int n_tiles = (a.rows + 2 * ROWS - 1) / (2 * ROWS);
+  const int n_pairs = std::min(n_tiles, g_fb_max_pairs);
+  const int grid = 2 * n_pairs;
+  MCM_CHECK((size_t)grid * ROWS * F * 2 <= fused_block_hid_bytes(), "fused block: hidden scratch too small");
+
+  FbMaps tm;
+  std::memset(&tm, 0, sizeof(tm));
+  MCM_TRY(tc_make_operand_map(&tm.wq, a.ca_wq.hi, OP_F16, D, D, 1, D, 128));
+  MCM_TRY(tc_make_operand_map(&tm.ctx, a.ca_ctxT.hi, OP_F16, HD, HD, a.batch * H, HD, 64));
+  MCM_TRY(tc_make_operand_map(&tm.wo, a.ca_wo.hi, OP_F16, D, D, 1, D, 128));
+  MCM_TRY(tc_make_operand_map(&tm.w1, a.f_w1.hi, OP_F16, D, F, 1, D, 128));
+  MCM_TRY(tc_make_operand_map(&tm.hida, a.hid, OP_F16, F, grid * ROWS, 1, F, 128));
+  MCM_TRY(tc_make_operand_map(&tm.w2, a.f_w2.hi, OP_F16, F, D, 1, F, 128));
+  MCM_TRY(tc_make_operand_map(&tm.wo2, a.f_wo.hi, OP_F16, D, D, 1, D, 128));
+  MCM_TRY(tc_make_tile_map(&tm.hred, a.h, 0, D, a.rows, 1, D, (long long)a.rows * D, 128));
+  MCM_TRY(tc_make_tile_map(&tm.hidst, a.hid, 1, F, (long long)grid * ROWS, 1, F, (long long)grid * ROWS * F, 64));
+
+  FbParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.h = a.h; p.rows = a.rows; p.T = a.T; p.batch = a.batch; p.n_tiles = n_tiles; p.mod_ld = a.mod_ld; p.stop = a.stop;
+  p.ca_ln_w = a.ca_ln_w; p.ca_ln_b = a.ca_ln_b; p.ca_bq = a.ca_bq; p.ca_pn_w = a.ca_pn_w; p.ca_pn_b = a.ca_pn_b;
+  p.ca_scale = a.ca_scale; p.ca_shift = a.ca_shift; p.ca_bo = a.ca_bo;
+  p.f_b1 = a.f_b1; p.f_b2 = a.f_b2; p.f_pn_w = a.f_pn_w; p.f_pn_b = a.f_pn_b; p.f_scale = a.f_scale; p.f_shift = a.f_shift;
+  p.f_bo = a.f_bo;
+  p.dbg = reinterpret_cast<uint16_t*>(a.dbg);
+
+  // algorithmic flops of the two sub-blocks (AdaLN emb GEMM is not in this kernel)
+  const double flops = 2.0 * (double)a.rows * ((double)D * D * 2 + (double)D * HD + 2.0 * D * F + (double)D * D);
+  {
+    LaunchTimer lt(LK_GEMM, stream, flops);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    MCM_CUDA(cudaLaunchKernelEx(&cfg, fused_block_kernel, tm, p));
+  }
+  MCM_CUDA(cudaGetLastError());
+  g_fb_launches.fetch_add(1);
+  return 0;
+}
+
+}  // namespace mcm

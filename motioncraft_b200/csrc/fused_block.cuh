@@ -1,0 +1,46 @@
+// motioncraft_b200 -- the fused token kernel: EfficientCrossAttention + FFN of one DecoderLayer
+// (efficient_attention.py:64-92, diffusion_transformer.py:25-28, stylization_block.py:29-40; called from
+// mcm.py:35-40) for a tile of 256 token rows per CTA pair, in ONE persistent kernel.
+//
+// Every op of the two sub-blocks is row-local (LayerNorm / per-head softmax / AdaLN / SiLU / GELU over the 512 or
+// 1024 features of one token) or a GEMM against weights shared by all tokens, so a tile of rows can run the whole
+// chain on-chip: activations live in shared memory (as the next GEMM's A operand) and TMEM (accumulators); only the
+// fp32 residual stream h is read and written in HBM (2 reads + 2 reduce-adds per row), weights stream from L2.
+// The unfused path round-trips ~12 h-sized tensors per layer through HBM for the same work.
+#pragma once
+#include "common.cuh"
+
+namespace mcm {
+
+struct FusedBlockArgs {
+  float* h;                 // [rows, 512] fp32 residual stream, updated in place
+  int rows;                 // B * T
+  int T;                    // rows per sample
+  int batch;                // B
+  // cross attention
+  const float *ca_ln_w, *ca_ln_b;      // ca_block.norm
+  OpPtr ca_wq;  const float* ca_bq;    // ca_block.query
+  OpPtr ca_ctxT;                       // [B*4, 128, 128] fp16 per-(sample, head) context, transposed (first sample of this launch)
+  const float *ca_pn_w, *ca_pn_b;      // ca_block.proj_out.norm
+  const float *ca_scale, *ca_shift;    // AdaLN modulation of this block, row b at + b * mod_ld
+  OpPtr ca_wo;  const float* ca_bo;    // ca_block.proj_out.out_layers.2
+  // FFN
+  OpPtr f_w1;   const float* f_b1;
+  OpPtr f_w2;   const float* f_b2;
+  const float *f_pn_w, *f_pn_b;
+  const float *f_scale, *f_shift;
+  OpPtr f_wo;   const float* f_bo;
+  int mod_ld;
+  void* hid;                // scratch for the GELU'd hidden activations: fused_block_hid_bytes() bytes, private to one stream
+  int stop;                 // debug: run only the first `stop` phases of every tile (0 = all) and dump the operand tile
+  void* dbg;                // debug: [rows, 512] fp16 dump of the shared-memory operand tile after phase `stop`
+};
+
+// true if the fused kernel covers this architecture (latent 512, ffn 1024, 4 heads, T >= 52)
+bool fused_block_supported(int T, int D, int F, int H);
+size_t fused_block_hid_bytes();
+int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream);
+unsigned long long fused_block_launch_count();
+void fused_block_count_replayed(unsigned long long n);
+
+}  // namespace mcm

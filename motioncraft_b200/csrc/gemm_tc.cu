@@ -8,6 +8,7 @@
 //                                activation / mask, fp32 and/or 16-bit operand stores
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "gemm_tc.cuh"
+#include "ptx_extra.cuh"
 #include "timing.cuh"
 
 #include <atomic>
@@ -52,119 +53,6 @@ struct EpiMaps {        // [segment][0 = fp32 out, 1 = fp32 addend, 2 = op hi, 3
 };
 
 enum { TM_TMA = 1, TM_RED = 2, TM_LDADD = 4, TM_BCAST = 8 };
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// B slice load, delivered to the same smem offset (and signalled on the same mbarrier offset) in every CTA of `mask`
-__device__ __forceinline__ void tma_load_3d_mc(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_3d(const void* desc, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-               ::"l"(desc), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-// ---- cta_group::2 (CTA pair) forms.  In a cluster, 32-bit shared addresses carry the CTA rank in bit 24, so
-// clearing it makes a barrier operand refer to the pair's leader (rank 0) -- the CUTLASS Sm100MmaPeerBitMask idiom.
-__device__ __forceinline__ void tma_load_3d_2sm(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(desc), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(bar), "r"(rank) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-
-__device__ __forceinline__ void tma_store_3d(const void* desc, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(desc), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_3d(const void* desc, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(desc), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void st_shared_v4(uint32_t a, float x, float y, float z, float w) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t a) {
-  float4 r;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
-  return r;
-}
-// two floats -> packed fp16x2 (lo half = a), saturating at +-65504
-__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-// erf-GELU with the Abramowitz-Stegun 7.1.26 rational erf (|abs err| < 5e-7, below the fp16 rounding of the
-// result); the bf16x2 ("precise") operand path keeps erff().
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float pe = poly * e;
-  return 0.5f * x * (x >= 0.f ? 2.f - pe : pe);
-}
 
 template <bool WITH_GENERIC, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -966,6 +854,21 @@ int gemm_tc_debug_read(unsigned long long* out, int reset) {
   if (reset) MCM_CUDA(cudaMemset(g_dbg, 0, 16 * sizeof(unsigned long long)));
   return 0;
 }
+
+// exported map builders (the fused block kernel builds its own tensor maps with the same rules)
+int tc_make_operand_map(CUtensorMap* m, const void* ptr, int fmt, int k_dim, int rows, int batches, int ld, int box_rows) {
+  MCM_TRY(gemm_tc_init());
+  return make_map(m, ptr, fmt, k_dim, rows, batches, ld, box_rows);
+}
+int tc_make_tile_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
+                     long long stride1_elems, long long stride2_elems, int swizzle_bytes) {
+  MCM_TRY(gemm_tc_init());
+  const CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return make_epi_map(m, ptr, dt, dtype == 0 ? 4 : 2, d0, d1, d2, stride1_elems, stride2_elems, sw);
+}
+int tc_num_sms() { return gemm_tc_init() == 0 ? g_num_sms : 0; }
 
 int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   MCM_TRY(gemm_tc_init());

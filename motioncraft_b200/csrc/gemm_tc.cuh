@@ -63,6 +63,14 @@ int gemm_tc_launch(const GemmProblem& prob, cudaStream_t stream);
 // device-wide one-time init (driver entry point for cuTensorMapEncodeTiled, smem attribute, SM count)
 int gemm_tc_init();
 
+// tensor-map builders shared with the fused block kernel.
+//   operand map: 16-bit K-major rows (fmt = OpFormat), dims {k_dim, rows, batches}, pitch ld, box {64, box_rows, 1}, 128B swizzle
+//   tile map:    dims {d0, d1, d2} (d0 contiguous), 32 x 32 x 1 boxes; dtype 0 = fp32, 1 = fp16; swizzle 128 / 64 / 0 bytes
+int tc_make_operand_map(CUtensorMap* m, const void* ptr, int fmt, int k_dim, int rows, int batches, int ld, int box_rows);
+int tc_make_tile_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
+                     long long stride1_elems, long long stride2_elems, int swizzle_bytes);
+int tc_num_sms();
+
 // number of tcgen05 GEMM launches since process start (bench.py's gpu_launches evidence)
 unsigned long long gemm_tc_launch_count();
 void gemm_tc_count_replayed(unsigned long long n);   // kernels executed by a CUDA-graph replay

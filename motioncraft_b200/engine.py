@@ -89,6 +89,13 @@ class DenoiserEngine:
         """Scheduling knobs ("dual", "graph", "chunk"); results are bit-identical in every mode."""
         _lib.check(self.lib.mcm_set_option(self._ctx, name.encode(), int(value)))
 
+    def debug_copy(self, what, numel):
+        """Development aid: fp16 dump of the fused kernel's operand tile (what=0) or hidden scratch (what=1)."""
+        out = torch.empty(numel, device=self.device, dtype=torch.float16)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mcm_debug_copy(self._ctx, int(what), _ptr(out), out.numel() * 2))
+        return out
+
     # ------------------------------------------------------------------ conditions
     def prepare_conditions(self, xf_out, xf_proj, c=None):
         xf_out = _f32c(xf_out, self.device)
