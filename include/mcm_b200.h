@@ -131,6 +131,8 @@ int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops);
 int mcm_debug_copy(mcm_ctx* ctx, int what, void* dst_dev, long long bytes);
 /* Development aid (MCM_DEBUG_EPI=3): summed clock cycles of the GEMM epilogue warps per phase; out[16]. */
 int mcm_debug_read(unsigned long long* out, int reset);
+/* Development aid (MCM_FUSED_PROF=1): summed clock cycles of the fused kernel per phase; out[32]. */
+int mcm_debug_read32(unsigned long long* out, int reset);
 
 const char* mcm_last_error(void);
 /* kernels launched by this library since process start (tcgen05 GEMMs, all kernels) */

@@ -52,6 +52,7 @@ SIGNATURES = {
                                 ctypes.POINTER(ctypes.c_double)]),
     "mcm_debug_read": (_I, [ctypes.POINTER(ctypes.c_ulonglong), _I]),
     "mcm_debug_copy": (_I, [_VP, _I, _VP, _LL]),
+    "mcm_debug_read32": (_I, [ctypes.POINTER(ctypes.c_ulonglong), _I]),
     "mcm_last_error": (ctypes.c_char_p, []),
     "mcm_gemm_launches": (ctypes.c_ulonglong, []),
     "mcm_kernel_launches": (ctypes.c_ulonglong, []),

@@ -604,7 +604,19 @@ const char* mcm_version(void) { return "motioncraft_b200 0.1.0 (sm_100a, tcgen05
 unsigned long long mcm_gemm_launches(void) { return gemm_tc_launch_count() + fused_block_launch_count(); }
 unsigned long long mcm_kernel_launches(void) { return gemm_tc_launch_count() + fused_block_launch_count() + elementwise_launch_count(); }
 
-int mcm_debug_read(unsigned long long* out, int reset) { return gemm_tc_debug_read(out, reset); }
+int mcm_debug_read(unsigned long long* out, int reset) {
+  // out[0..16): GEMM epilogue phases (MCM_DEBUG_EPI=3); when MCM_FUSED_PROF=1 the fused kernel's phase clocks instead
+  unsigned long long f[32];
+  MCM_TRY(fused_block_prof_read(f, reset));
+  bool any = false;
+  for (int i = 0; i < 32; ++i) any = any || f[i] != 0;
+  if (any) {
+    for (int i = 0; i < 16; ++i) out[i] = f[i];
+    return 0;
+  }
+  return gemm_tc_debug_read(out, reset);
+}
+int mcm_debug_read32(unsigned long long* out, int reset) { return fused_block_prof_read(out, reset); }
 int mcm_debug_copy(mcm_ctx* c, int what, void* dst_dev, long long bytes) {
   MCM_CHECK(c != nullptr && dst_dev != nullptr && bytes > 0, "bad argument");
   const void* src = what == 0 ? c->fused_dbg : c->ws[0].hid;

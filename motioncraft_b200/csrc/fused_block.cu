@@ -23,6 +23,7 @@
 #include "fused_block.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm_tc.cuh"
@@ -57,6 +58,7 @@ struct FbParams {
   const float *ca_ln_w, *ca_ln_b, *ca_bq, *ca_pn_w, *ca_pn_b, *ca_scale, *ca_shift, *ca_bo;
   const float *f_b1, *f_b2, *f_pn_w, *f_pn_b, *f_scale, *f_shift, *f_bo;
   uint16_t* dbg;
+  unsigned long long* prof;   // MCM_FUSED_PROF=1: summed cycles per phase (compute warps: [0,16), MMA warp: [16,24))
 };
 
 __device__ __forceinline__ void st_shared_v2u(uint32_t a, uint32_t x, uint32_t y) {
@@ -94,6 +96,8 @@ __device__ __forceinline__ void add_bias32(float* slot, int lane, float mine, fl
 }
 
 // ---- P phase: 128 rows of h -> (LayerNorm) -> fp16 -> OPA.  Warp per row, the reduction order of ln_rows_kernel.
+// Two rows per iteration; the next iteration's rows are requested before the current ones are reduced (there is
+// next to no L1 beside 225 KB of shared memory, so every row is an L2 / HBM round trip).
 template <bool LN>
 __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int rows, long long g0, uint32_t opa, int ew,
                                             int lane, const float* __restrict__ lnw, const float* __restrict__ lnb) {
@@ -105,16 +109,25 @@ __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int row
       gb[j] = __ldg(reinterpret_cast<const float4*>(lnb) + j * 32 + lane);
     }
   }
-#pragma unroll 1
-  for (int i = 0; i < ROWS / NCW; i += 2) {
-    float4 x[2][4];
+  float4 nx[2][4];
+  auto fetch = [&](int i) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const long long g = g0 + ew + NCW * (i + u);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        x[u][j] = g < rows ? __ldcg(reinterpret_cast<const float4*>(h + g * D) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nx[u][j] = g < rows ? __ldcg(reinterpret_cast<const float4*>(h + g * D) + j * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  fetch(0);
+#pragma unroll 1
+  for (int i = 0; i < ROWS / NCW; i += 2) {
+    float4 x[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[u][j] = nx[u][j];
+    if (i + 2 < ROWS / NCW) fetch(i + 2);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int r = ew + NCW * (i + u);
@@ -148,58 +161,86 @@ __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int row
   }
 }
 
-// ---- E1: per-head softmax of (acc + bq) over the 128 columns of each of this warp's two heads -> OPA
+// The chunk loops of the E phases are deliberately NOT unrolled: the first version of this kernel unrolled them into
+// ~300 KB of straight-line SASS that every warp executed once per tile, and ran instruction-fetch bound (10x slower).
+
+// ---- E1: per-head softmax numerator of (acc + bq) over the 128 columns of each of this warp's two heads -> OPA.
+// OPA receives the UN-normalised exp(q - max) (in (0, 1], the same relative fp16 rounding as the normalised value);
+// the 1 / sum of each head is returned in inv0 / inv1 and applied to the fp32 accumulator of q * ctx by the same thread
+// in E2 (y = softmax(q) ctx is linear in the scale of q per head).  Two streaming passes over TMEM, 32 live values.
 __device__ __forceinline__ void epi_softmax(uint32_t trow, int hf, int row, uint32_t opa, float* bslot, int lane,
-                                            const float (&bp)[8]) {
-#pragma unroll
+                                            const float* __restrict__ bias, float& inv0, float& inv1) {
+#pragma unroll 1
   for (int i = 0; i < 2; ++i) {
     const int col0 = hf * 256 + i * 128;
-    float v[128];
+    float m = -INFINITY;
+    float bcur = __ldg(bias + col0 + lane);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+      tmem_ld_32x32(trow + (uint32_t)(col0 + c * 32), v);
+      const float bnxt = __ldg(bias + col0 + ((c + 1) & 3) * 32 + lane);
+      tmem_ld_wait();
+      add_bias32(bslot, lane, bcur, v);
+      bcur = bnxt;
+      float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld_32x32(trow + (uint32_t)(col0 + c * 32), v + 32 * c);
-    tmem_ld_wait();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) add_bias32(bslot, lane, bp[i * 4 + c], v + 32 * c);
-    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
-#pragma unroll
-    for (int j = 4; j < 128; j += 4) {
-      m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+      for (int j = 4; j < 32; j += 4) {
+        m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+      }
+      m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     }
-    const float ml = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * L2E;
+    const float ml = m * L2E;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {       // bcur holds chunk 0's bias again (the prefetch index wraps)
+      float v[32];
+      tmem_ld_32x32(trow + (uint32_t)(col0 + c * 32), v);
+      const float bnxt = __ldg(bias + col0 + ((c + 1) & 3) * 32 + lane);
+      tmem_ld_wait();
+      add_bias32(bslot, lane, bcur, v);
+      bcur = bnxt;
 #pragma unroll
-    for (int j = 0; j < 128; j += 4) {
-      v[j] = ex2_fast(fmaf(v[j], L2E, -ml));         s0 += v[j];
-      v[j + 1] = ex2_fast(fmaf(v[j + 1], L2E, -ml)); s1 += v[j + 1];
-      v[j + 2] = ex2_fast(fmaf(v[j + 2], L2E, -ml)); s2 += v[j + 2];
-      v[j + 3] = ex2_fast(fmaf(v[j + 3], L2E, -ml)); s3 += v[j + 3];
+      for (int j = 0; j < 32; j += 4) {
+        v[j] = ex2_fast(fmaf(v[j], L2E, -ml));         s0 += v[j];
+        v[j + 1] = ex2_fast(fmaf(v[j + 1], L2E, -ml)); s1 += v[j + 1];
+        v[j + 2] = ex2_fast(fmaf(v[j + 2], L2E, -ml)); s2 += v[j + 2];
+        v[j + 3] = ex2_fast(fmaf(v[j + 3], L2E, -ml)); s3 += v[j + 3];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4u(opa_addr(opa, row, col0 + c * 32 + 8 * q), pack_f16x2_sat(v[8 * q], v[8 * q + 1]),
+                      pack_f16x2_sat(v[8 * q + 2], v[8 * q + 3]), pack_f16x2_sat(v[8 * q + 4], v[8 * q + 5]),
+                      pack_f16x2_sat(v[8 * q + 6], v[8 * q + 7]));
     }
-    const float inv = 1.f / ((s0 + s1) + (s2 + s3));
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-      st_shared_v4u(opa_addr(opa, row, col0 + 8 * q), pack_f16x2_sat(v[8 * q] * inv, v[8 * q + 1] * inv),
-                    pack_f16x2_sat(v[8 * q + 2] * inv, v[8 * q + 3] * inv), pack_f16x2_sat(v[8 * q + 4] * inv, v[8 * q + 5] * inv),
-                    pack_f16x2_sat(v[8 * q + 6] * inv, v[8 * q + 7] * inv));
+    const float r = 1.f / ((s0 + s1) + (s2 + s3));
+    if (i == 0) inv0 = r; else inv1 = r;
   }
 }
 
-// ---- E2 / E5: OPA = SiLU(LN_512(acc [+ bias]) * gamma' + beta') for the rows with act = true.
+// ---- E2 / E5: OPA = SiLU(LN_512(acc [* inv] [+ bias]) * gamma' + beta') for the rows with act = true.
 // gamma' = w (1 + scale), beta' = b (1 + scale) + shift were staged per sample in shared memory (prm: [gamma' 512 | beta' 512]).
-// The two warps of a lane quadrant each own 256 columns and exchange (mean, M2) partial statistics.
-template <bool BIAS>
+// The two warps of a lane quadrant each own 256 columns and exchange (mean, M2) partial statistics; the statistics
+// are accumulated about the row's first element so that one pass suffices without cancellation.
+template <bool BIAS, bool SCALE>
 __device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool act, const float* prm, float* xch, int ew,
-                                          int quad, uint32_t opa, float* bslot, int lane, const float (&bp)[8]) {
+                                          int quad, uint32_t opa, float* bslot, int lane, const float* __restrict__ bias,
+                                          float inv0, float inv1) {
   float K = 0.f, sd = 0.f, sq = 0.f;
-#pragma unroll
+  float bcur = BIAS ? __ldg(bias + hf * 256 + lane) : 0.f;
+#pragma unroll 1
   for (int c = 0; c < 8; ++c) {
     float v[32];
     tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
+    const float bnxt = BIAS ? __ldg(bias + hf * 256 + ((c + 1) & 7) * 32 + lane) : 0.f;
     tmem_ld_wait();
-    if (BIAS) add_bias32(bslot, lane, bp[c], v);
-    if (c == 0) K = v[0];
+    if (BIAS) add_bias32(bslot, lane, bcur, v);
+    bcur = bnxt;
+    const float sc = SCALE ? ((c >> 2) ? inv1 : inv0) : 1.f;
+    if (c == 0) K = v[0] * sc;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float d = v[j] - K;
+      const float d = SCALE ? fmaf(v[j], sc, -K) : v[j] - K;
       sd += d;
       sq = fmaf(d, d, sq);
     }
@@ -215,12 +256,17 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool a
   const float mean = 0.5f * (mean_w + mean_o);
   const float m2 = (m2_w + m2_o) + delta * delta * 128.f;
   const float rstd = rsqrtf(m2 * (1.f / (float)D) + 1e-5f);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {          // bcur holds chunk 0's bias again
     float v[32];
     tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
+    const float bnxt = BIAS ? __ldg(bias + hf * 256 + ((c + 1) & 7) * 32 + lane) : 0.f;
     tmem_ld_wait();
-    if (BIAS) add_bias32(bslot, lane, bp[c], v);
+    if (BIAS) add_bias32(bslot, lane, bcur, v);
+    bcur = bnxt;
+    // (x sc - mean) rstd = x A + B
+    const float A = SCALE ? ((c >> 2) ? inv1 : inv0) * rstd : rstd;
+    const float Bc = -mean * rstd;
     const int col = hf * 256 + c * 32;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -228,32 +274,41 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool a
       const float4 gb = *reinterpret_cast<const float4*>(prm + col + 8 * q + 4);
       const float4 ba = *reinterpret_cast<const float4*>(prm + D + col + 8 * q);
       const float4 bb = *reinterpret_cast<const float4*>(prm + D + col + 8 * q + 4);
-      const float y0 = silu_fast(fmaf((v[8 * q] - mean) * rstd, ga.x, ba.x));
-      const float y1 = silu_fast(fmaf((v[8 * q + 1] - mean) * rstd, ga.y, ba.y));
-      const float y2 = silu_fast(fmaf((v[8 * q + 2] - mean) * rstd, ga.z, ba.z));
-      const float y3 = silu_fast(fmaf((v[8 * q + 3] - mean) * rstd, ga.w, ba.w));
-      const float y4 = silu_fast(fmaf((v[8 * q + 4] - mean) * rstd, gb.x, bb.x));
-      const float y5 = silu_fast(fmaf((v[8 * q + 5] - mean) * rstd, gb.y, bb.y));
-      const float y6 = silu_fast(fmaf((v[8 * q + 6] - mean) * rstd, gb.z, bb.z));
-      const float y7 = silu_fast(fmaf((v[8 * q + 7] - mean) * rstd, gb.w, bb.w));
+      float y[8];
+      y[0] = silu_fast(fmaf(fmaf(v[8 * q], A, Bc), ga.x, ba.x));
+      y[1] = silu_fast(fmaf(fmaf(v[8 * q + 1], A, Bc), ga.y, ba.y));
+      y[2] = silu_fast(fmaf(fmaf(v[8 * q + 2], A, Bc), ga.z, ba.z));
+      y[3] = silu_fast(fmaf(fmaf(v[8 * q + 3], A, Bc), ga.w, ba.w));
+      y[4] = silu_fast(fmaf(fmaf(v[8 * q + 4], A, Bc), gb.x, bb.x));
+      y[5] = silu_fast(fmaf(fmaf(v[8 * q + 5], A, Bc), gb.y, bb.y));
+      y[6] = silu_fast(fmaf(fmaf(v[8 * q + 6], A, Bc), gb.z, bb.z));
+      y[7] = silu_fast(fmaf(fmaf(v[8 * q + 7], A, Bc), gb.w, bb.w));
       if (act)
-        st_shared_v4u(opa_addr(opa, row, col + 8 * q), pack_f16x2_sat(y0, y1), pack_f16x2_sat(y2, y3), pack_f16x2_sat(y4, y5),
-                      pack_f16x2_sat(y6, y7));
+        st_shared_v4u(opa_addr(opa, row, col + 8 * q), pack_f16x2_sat(y[0], y[1]), pack_f16x2_sat(y[2], y[3]),
+                      pack_f16x2_sat(y[4], y[5]), pack_f16x2_sat(y[6], y[7]));
     }
   }
 }
 
 // ---- E3 / E6: h[rows, 256 columns of this warp] += acc + bias, 32 x 32 fp32 tiles through the warp's staging slot
-__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int hf, uint32_t stgw, const CUtensorMap* map, int grow0,
-                                             float* bslot, int lane, const float (&bp)[8], bool& pending) {
-#pragma unroll
+// (two 4 KB halves... the slot is 4 KB, so a tile waits for the previous reduction to have READ the slot)
+__device__ __forceinline__ void tma_wait_read3() { asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); }
+// `stg4`: 16 KB of the (idle) operand tile private to this warp = 4 rotating 4 KB slots, so a tile only waits for the
+// reduction issued 4 tiles earlier to have read its slot.
+__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int hf, uint32_t stg4, const CUtensorMap* map, int grow0,
+                                             float* bslot, int lane, const float* __restrict__ bias, bool& pending) {
+  float bcur = __ldg(bias + hf * 256 + lane);
+#pragma unroll 1
   for (int c = 0; c < 8; ++c) {
     float v[32];
     tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
+    const float bnxt = __ldg(bias + hf * 256 + ((c + 1) & 7) * 32 + lane);
     tmem_ld_wait();
-    add_bias32(bslot, lane, bp[c], v);
-    if (pending) {
-      if (lane == 0) tma_wait_read0();
+    add_bias32(bslot, lane, bcur, v);
+    bcur = bnxt;
+    const uint32_t stgw = stg4 + (uint32_t)(c & 3) * 4096u;
+    if (c >= 4) {
+      if (lane == 0) tma_wait_read3();
       __syncwarp();
     }
 #pragma unroll
@@ -290,6 +345,8 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t hid_bar;
+  __shared__ __align__(8) uint64_t afull_bar[8];    // G5: hidden (A) slabs stream through the idle operand tile
+  __shared__ __align__(8) uint64_t aempty_bar[8];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[NCW][32];
 
@@ -321,6 +378,10 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         mbar_init(smem_u32(&tempty_bar[s]), 2u * NCW);       // every compute warp of both CTAs
       }
       mbar_init(smem_u32(&hid_bar), NCW);
+      for (int s = 0; s < 8; ++s) {
+        mbar_init(smem_u32(&afull_bar[s]), 1);
+        mbar_init(smem_u32(&aempty_bar[s]), 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -347,34 +408,56 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       __syncwarp();
       if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
     };
+#pragma unroll 1
     for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
       const int g0 = tile * 2 * ROWS;
       const int s_first = g0 / p.T;
       const int s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
       if (last >= 2)
+#pragma unroll 1
         for (int n = 0; n < 2; ++n)
+#pragma unroll 1
           for (int kb = 0; kb < D / 64; ++kb) push(&tm.wq, kb * 64, n * 256 + rank * 128, 0, SLAB);
       if (last >= 3)
+#pragma unroll 1
         for (int s = s_first; s <= s_last; ++s)
+#pragma unroll 1
           for (int hd = 0; hd < H; ++hd)
+#pragma unroll 1
             for (int kb = 0; kb < HD / 64; ++kb) push(&tm.ctx, kb * 64, rank * 64, s * H + hd, SLAB / 2);
       if (last >= 4)
+#pragma unroll 1
         for (int n = 0; n < 2; ++n)
+#pragma unroll 1
           for (int kb = 0; kb < D / 64; ++kb) push(&tm.wo, kb * 64, n * 256 + rank * 128, 0, SLAB);
       if (last >= 5)
+#pragma unroll 1
         for (int q = 0; q < 4; ++q)
+#pragma unroll 1
           for (int kb = 0; kb < D / 64; ++kb) push(&tm.w1, kb * 64, q * 256 + rank * 128, 0, SLAB);
       if (last >= 6) {
         mbar_wait(smem_u32(&hid_bar), (uint32_t)it & 1u);      // this CTA's hidden rows are in global memory
         fence_proxy_async_all();
-        for (int n = 0; n < 2; ++n)
-          for (int kb = 0; kb < F / 64; ++kb) {
-            push(&tm.hida, kb * 64, (int)blockIdx.x * ROWS, 0, SLAB);
-            push(&tm.w2, kb * 64, n * 256 + rank * 128, 0, SLAB);
+        // the operand tile is idle between G4 and E5: the 16 hidden slabs stream through it as an 8-slot ring
+        // (each slab feeds both N halves), the W2 slabs through the ordinary ring
+#pragma unroll 1
+        for (int kb = 0; kb < F / 64; ++kb) {
+          const int sa = kb & 7;
+          mbar_wait(smem_u32(&aempty_bar[sa]), (uint32_t)((kb >> 3) ^ 1));
+          const uint32_t abar = smem_u32(&afull_bar[sa]);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(abar, 2u * SLAB);
+            tma_load_3d_2sm(&tm.hida, abar, opa + (uint32_t)sa * SLAB, kb * 64, (int)blockIdx.x * ROWS, 0);
           }
+          __syncwarp();
+          push(&tm.w2, kb * 64, rank * 128, 0, SLAB);
+          push(&tm.w2, kb * 64, 256 + rank * 128, 0, SLAB);
+        }
       }
       if (last >= 7)
+#pragma unroll 1
         for (int n = 0; n < 2; ++n)
+#pragma unroll 1
           for (int kb = 0; kb < D / 64; ++kb) push(&tm.wo2, kb * 64, n * 256 + rank * 128, 0, SLAB);
     }
   } else if (warp == 1) {
@@ -386,8 +469,13 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       // instruction descriptors: fp32 accumulate, fp16 A/B, K-major, N >> 3, M = 256 >> 4
       const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const bool prof = p.prof != nullptr;
+      long long m_te = 0, m_full = 0;
+      const long long m_t0 = prof ? clock64() : 0;
       auto wait_te = [&](int hh) {
+        const long long t0 = prof ? clock64() : 0;
         mbar_wait(smem_u32(&tempty_bar[hh]), te_par[hh]);
+        if (prof) m_te += clock64() - t0;
         te_par[hh] ^= 1u;
         tc_fence_after();
       };
@@ -397,7 +485,9 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       };
       // one ring slab as the B operand against the resident A slab `a_addr`
       auto step = [&](uint32_t a_addr, uint32_t dcol, uint32_t idesc, bool fresh) {
+        const long long t0 = prof ? clock64() : 0;
         mbar_wait(smem_u32(&full_bar[slot]), ph);
+        if (prof) m_full += clock64() - t0;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t b_addr = ring + (uint32_t)slot * SLAB;
@@ -412,9 +502,12 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       };
       // a full-width GEMM out of the resident operand tile: D[128(x2) x 512] = OPA[.. x 512] W[512 x 512]^T
       auto gemm_opa_512 = [&]() {
+#pragma unroll 1
         for (int n = 0; n < 2; ++n)
+#pragma unroll 1
           for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)(n * 256), idesc256, kb == 0);
       };
+#pragma unroll 1
       for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
         const int g0 = tile * 2 * ROWS;
         const int s_first = g0 / p.T;
@@ -425,9 +518,12 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           commit_tf(0); commit_tf(1);
         }
         if (last >= 3) {                                     // G2, one round per sample
+#pragma unroll 1
           for (int s = s_first; s <= s_last; ++s) {
             wait_te(0); wait_te(1);
+#pragma unroll 1
             for (int hd = 0; hd < H; ++hd)
+#pragma unroll 1
               for (int kb = 0; kb < HD / 64; ++kb)
                 step(opa + (uint32_t)(hd * 2 + kb) * SLAB, (uint32_t)(hd * HD), idesc128, kb == 0);
             commit_tf(0); commit_tf(1);
@@ -439,34 +535,27 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           commit_tf(0); commit_tf(1);
         }
         if (last >= 5) {                                     // G4: four 256-column quarters, alternating TMEM halves
+#pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             wait_te(q & 1);
+#pragma unroll 1
             for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)((q & 1) * 256), idesc256, kb == 0);
             commit_tf(q & 1);
           }
         }
-        if (last >= 6) {                                     // G5: A (hidden) and B (W2) both stream through the ring
+        if (last >= 6) {                                     // G5: hidden slabs (A) from the operand-tile ring, W2 from the ring
           wait_te(0); wait_te(1);
-          for (int n = 0; n < 2; ++n)
-            for (int kb = 0; kb < F / 64; ++kb) {
-              const int sa = slot;
-              mbar_wait(smem_u32(&full_bar[sa]), ph);
-              if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
-              const int sb = slot;
-              mbar_wait(smem_u32(&full_bar[sb]), ph);
-              if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t a_addr = ring + (uint32_t)sa * SLAB, b_addr = ring + (uint32_t)sb * SLAB;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16_2sm(tmem_base + (uint32_t)(n * 256), make_smem_desc_sw128(a_addr + k * 32),
-                               make_smem_desc_sw128(b_addr + k * 32), idesc256, (kb == 0 && k == 0) ? 0u : 1u);
-                umma_commit_2sm(smem_u32(&empty_bar[sa]), (uint16_t)3);
-                umma_commit_2sm(smem_u32(&empty_bar[sb]), (uint16_t)3);
-              }
-              __syncwarp();
-            }
+#pragma unroll 1
+          for (int kb = 0; kb < F / 64; ++kb) {
+            const int sa = kb & 7;
+            const long long t0 = prof ? clock64() : 0;
+            mbar_wait(smem_u32(&afull_bar[sa]), (uint32_t)(kb >> 3));
+            if (prof) m_full += clock64() - t0;
+            step(opa + (uint32_t)sa * SLAB, 0u, idesc256, kb == 0);
+            step(opa + (uint32_t)sa * SLAB, 256u, idesc256, kb == 0);
+            if (elect_one()) umma_commit_2sm(smem_u32(&aempty_bar[sa]), (uint16_t)3);
+            __syncwarp();
+          }
           commit_tf(0); commit_tf(1);
         }
         if (last >= 7) {                                     // G6
@@ -474,6 +563,11 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           gemm_opa_512();
           commit_tf(0); commit_tf(1);
         }
+      }
+      if (prof && lane == 0) {
+        atomicAdd(p.prof + 16, (unsigned long long)m_te);
+        atomicAdd(p.prof + 17, (unsigned long long)m_full);
+        atomicAdd(p.prof + 18, (unsigned long long)(clock64() - m_t0));
       }
     }
   } else {
@@ -513,6 +607,12 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       }
     };
 
+    long long tph[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tph[i] = 0;
+    const bool prof = p.prof != nullptr;
+    long long tlast = prof ? clock64() : 0;
+#define FB_TICK(i) do { if (prof) { const long long _n = clock64(); tph[i] += _n - tlast; tlast = _n; } } while (0)
     int it = 0;
     for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
       const int g0 = tile * 2 * ROWS;                       // first row of the pair's tile
@@ -524,112 +624,131 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       const int s_row = grow / p.T;
       const int slot_row = min(max(s_row - s_first, 0), nsamp - 1);
       int done = 0;                                          // compute phases finished for this tile
+      float qinv0 = 1.f, qinv1 = 1.f;                        // 1 / softmax denominators of this thread's two heads
 
       // ---- P0
       drain_stores(false);
+      bar_sync(5, NCW * 32);                                 // every warp's E6 reductions have read their slice of the operand tile
       rows_to_opa<true>(p.h, p.rows, gc, opa, ew, lane, p.ca_ln_w, p.ca_ln_b);
       if (++done < last) arrive_te(true, true);
+      {
+        // pull the NEXT tile's rows of h into L2 while this tile computes (P0 is otherwise an HBM round trip per row pair)
+        const long long gn = (long long)(tile + n_clusters) * 2 * ROWS + rank * ROWS;
+        if (tile + n_clusters < p.n_tiles) {
+#pragma unroll
+          for (int k = 0; k < (ROWS * D * 4 / 128) / (NCW * 32); ++k) {
+            const int line = ctid + k * NCW * 32;              // 128-byte line of this CTA's 128 x 2 KB rows
+            const long long r = gn + (line >> 4);
+            if (r < p.rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.h + r * D + (line & 15) * 32));
+          }
+        }
+      }
+      FB_TICK(0);
       if (done < last) {
         // ---- E1
-        float bp[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.ca_bq + hf * 256 + k * 32 + lane);
         wait_tf(0); wait_tf(1);
-        epi_softmax(trow, hf, row, opa, bslot, lane, bp);
+        FB_TICK(1);
+        epi_softmax(trow, hf, row, opa, bslot, lane, p.ca_bq, qinv0, qinv1);
         if (++done < last) arrive_te(true, true);
+        FB_TICK(2);
       }
       if (done < last) {
         // ---- E2 (one round per sample of the tile)
         stage_params(prm_all, nsamp, s_first, p.batch, p.ca_pn_w, p.ca_pn_b, p.ca_scale, p.ca_shift, p.mod_ld, ctid);
         bar_sync(5, NCW * 32);
-        float bp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         ++done;
         for (int s = s_first; s <= s_last; ++s) {
           wait_tf(0); wait_tf(1);
+          FB_TICK(3);
           const bool act = (s_row == s) && (grow < p.rows);
           if (__any_sync(0xffffffffu, act))
-            epi_lnmod<false>(trow, hf, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, bp);
+            epi_lnmod<false, true>(trow, hf, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, nullptr, qinv0, qinv1);
           if (s < s_last || done < last) arrive_te(true, true);
+          FB_TICK(4);
         }
       }
       if (done < last) {
         // ---- E3: h += d + bo, then OPA = fp16(h)
-        float bp[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.ca_bo + hf * 256 + k * 32 + lane);
         wait_tf(0); wait_tf(1);
-        epi_reduce_h(trow, hf, stgw, &tm.hred, gc + quad * 32, bslot, lane, bp, pending);
+        FB_TICK(5);
+        epi_reduce_h(trow, hf, opa + (uint32_t)ew * SLAB, &tm.hred, gc + quad * 32, bslot, lane, p.ca_bo, pending);
         tc_fence_before();
+        FB_TICK(6);
         drain_stores(true);
         bar_sync(5, NCW * 32);                               // every reduction into this CTA's rows has been performed
+        FB_TICK(7);
         rows_to_opa<false>(p.h, p.rows, gc, opa, ew, lane, nullptr, nullptr);
         if (++done < last) arrive_te(true, true);
+        FB_TICK(8);
       }
       if (done < last) {
         // ---- E4: hidden = GELU(u + b1) -> fp16 -> hidden scratch (this CTA's private rows)
-        float bp16[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) bp16[k] = __ldg(p.f_b1 + (k >> 2) * 256 + hf * 128 + (k & 3) * 32 + lane);
         ++done;
-        int cnt = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          wait_tf(q & 1);
-#pragma unroll
-          for (int c = 0; c < 4; ++c, ++cnt) {
-            float v[32];
-            tmem_ld_32x32(trow + (uint32_t)((q & 1) * 256 + hf * 128 + c * 32), v);
-            tmem_ld_wait();
-            add_bias32(bslot, lane, bp16[q * 4 + c], v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-            const uint32_t sl = stgw + (uint32_t)(cnt & 1) * 2048u;
-            if (cnt >= 2) {
-              if (lane == 0) tma_wait_read1();
-              __syncwarp();
-            }
-            const uint32_t sw = (uint32_t)((lane >> 1) & 3);
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq)
-              st_shared_v4u(sl + (uint32_t)lane * 64u + (((uint32_t)qq ^ sw) << 4), pack_f16x2_sat(v[8 * qq], v[8 * qq + 1]),
-                            pack_f16x2_sat(v[8 * qq + 2], v[8 * qq + 3]), pack_f16x2_sat(v[8 * qq + 4], v[8 * qq + 5]),
-                            pack_f16x2_sat(v[8 * qq + 6], v[8 * qq + 7]));
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tm.hidst, sl, q * 256 + hf * 128 + c * 32, (int)blockIdx.x * ROWS + quad * 32, 0);
-              tma_commit();
-            }
+        float bcur = __ldg(p.f_b1 + hf * 128 + lane);
+#pragma unroll 1
+        for (int idx = 0; idx < 16; ++idx) {
+          const int q = idx >> 2, c = idx & 3;
+          if (c == 0) {
+            wait_tf(q & 1);
+            FB_TICK(9);
           }
-          if (q < 2 || done < last) arrive_te((q & 1) == 0, (q & 1) == 1);
+          float v[32];
+          tmem_ld_32x32(trow + (uint32_t)((q & 1) * 256 + hf * 128 + c * 32), v);
+          const int nidx = (idx + 1) & 15;
+          const float bnxt = __ldg(p.f_b1 + (nidx >> 2) * 256 + hf * 128 + (nidx & 3) * 32 + lane);
+          tmem_ld_wait();
+          add_bias32(bslot, lane, bcur, v);
+          bcur = bnxt;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          const uint32_t sl = stgw + (uint32_t)(idx & 1) * 2048u;
+          if (idx >= 2) {
+            if (lane == 0) tma_wait_read1();
+            __syncwarp();
+          }
+          const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            st_shared_v4u(sl + (uint32_t)lane * 64u + (((uint32_t)qq ^ sw) << 4), pack_f16x2_sat(v[8 * qq], v[8 * qq + 1]),
+                          pack_f16x2_sat(v[8 * qq + 2], v[8 * qq + 3]), pack_f16x2_sat(v[8 * qq + 4], v[8 * qq + 5]),
+                          pack_f16x2_sat(v[8 * qq + 6], v[8 * qq + 7]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tm.hidst, sl, q * 256 + hf * 128 + c * 32, (int)blockIdx.x * ROWS + quad * 32, 0);
+            tma_commit();
+          }
+          if (c == 3) {
+            if (q < 2 || done < last) arrive_te((q & 1) == 0, (q & 1) == 1);
+            FB_TICK(10);
+          }
         }
         pending = true;
         tc_fence_before();
         drain_stores(true);                                  // hidden rows are in global memory
         if (done < last && lane == 0) mbar_arrive(smem_u32(&hid_bar));
+        FB_TICK(11);
       }
       if (done < last) {
         // ---- E5
         bar_sync(5, NCW * 32);                               // all warps' staging slots are free
         stage_params(prm_all, nsamp, s_first, p.batch, p.f_pn_w, p.f_pn_b, p.f_scale, p.f_shift, p.mod_ld, ctid);
         bar_sync(5, NCW * 32);
-        float bp[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.f_b2 + hf * 256 + k * 32 + lane);
         wait_tf(0); wait_tf(1);
-        epi_lnmod<true>(trow, hf, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, bp);
+        FB_TICK(12);
+        epi_lnmod<true, false>(trow, hf, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, p.f_b2, 1.f, 1.f);
         if (++done < last) arrive_te(true, true);
+        FB_TICK(13);
       }
       if (done < last) {
         // ---- E6
-        float bp[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bp[k] = __ldg(p.f_bo + hf * 256 + k * 32 + lane);
         bar_sync(5, NCW * 32);                               // nobody still reads the staged parameters / statistics
         wait_tf(0); wait_tf(1);
-        epi_reduce_h(trow, hf, stgw, &tm.hred, gc + quad * 32, bslot, lane, bp, pending);
+        FB_TICK(14);
+        epi_reduce_h(trow, hf, opa + (uint32_t)ew * SLAB, &tm.hred, gc + quad * 32, bslot, lane, p.f_bo, pending);
         tc_fence_before();
         ++done;
+        FB_TICK(15);
       }
       if (p.stop != 0 && p.dbg != nullptr) {
         // debug: dump the operand tile (un-swizzled) after the last executed phase
@@ -646,6 +765,11 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       }
     }
     drain_stores(true);                                      // bulk operations complete before the CTA exits
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) atomicAdd(p.prof + i, (unsigned long long)tph[i]);
+    }
+#undef FB_TICK
   }
 
   tc_fence_before();
@@ -659,6 +783,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
 
 std::atomic<unsigned long long> g_fb_launches{0};
 int g_fb_max_pairs = -1;
+unsigned long long* g_fb_prof = nullptr;
 
 int fb_init() {
   if (g_fb_max_pairs >= 0) return 0;
@@ -676,6 +801,12 @@ int fb_init() {
   MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, fused_block_kernel, &cfg));
   MCM_CHECK(n > 0, "fused_block_kernel does not fit on this device");
   g_fb_max_pairs = n;
+  if (const char* e = getenv("MCM_FUSED_PROF")) {
+    if (e[0] == '1') {
+      MCM_CUDA(cudaMalloc(&g_fb_prof, 32 * sizeof(unsigned long long)));
+      MCM_CUDA(cudaMemset(g_fb_prof, 0, 32 * sizeof(unsigned long long)));
+    }
+  }
   return 0;
 }
 
@@ -686,6 +817,14 @@ bool fused_block_supported(int T, int Dm, int Fm, int Hm) {
 }
 size_t fused_block_hid_bytes() { return (size_t)160 * ROWS * F * 2; }
 unsigned long long fused_block_launch_count() { return g_fb_launches.load(); }
+int fused_block_prof_read(unsigned long long* out, int reset) {
+  for (int i = 0; i < 32; ++i) out[i] = 0;
+  if (g_fb_prof == nullptr) return 0;
+  MCM_CUDA(cudaDeviceSynchronize());
+  MCM_CUDA(cudaMemcpy(out, g_fb_prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) MCM_CUDA(cudaMemset(g_fb_prof, 0, 32 * sizeof(unsigned long long)));
+  return 0;
+}
 void fused_block_count_replayed(unsigned long long n) { g_fb_launches.fetch_add(n); }
 
 int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
@@ -720,6 +859,7 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
   p.f_b1 = a.f_b1; p.f_b2 = a.f_b2; p.f_pn_w = a.f_pn_w; p.f_pn_b = a.f_pn_b; p.f_scale = a.f_scale; p.f_shift = a.f_shift;
   p.f_bo = a.f_bo;
   p.dbg = reinterpret_cast<uint16_t*>(a.dbg);
+  p.prof = g_fb_prof;
 
   // algorithmic flops of the two sub-blocks (AdaLN emb GEMM is not in this kernel)
   const double flops = 2.0 * (double)a.rows * ((double)D * D * 2 + (double)D * HD + 2.0 * D * F + (double)D * D);

@@ -42,5 +42,7 @@ size_t fused_block_hid_bytes();
 int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream);
 unsigned long long fused_block_launch_count();
 void fused_block_count_replayed(unsigned long long n);
+// MCM_FUSED_PROF=1: summed clock cycles per phase (development aid); out[32]
+int fused_block_prof_read(unsigned long long* out, int reset);
 
 }  // namespace mcm

@@ -62,7 +62,9 @@ def main():
     y2 = Fn.linear(hid, d[fn + ".linear2.weight"], d[fn + ".linear2.bias"])
     a5 = styl(y2, fn + ".proj_out")
     h_out = h_ca + Fn.linear(a5, d[fn + ".proj_out.out_layers.2.weight"], d[fn + ".proj_out.out_layers.2.bias"])
-    want = {1: ln, 2: qs, 3: a2, 4: h_ca, 6: a5}
+    qh = q.view(B, T, 4, 128)
+    qe = torch.exp(qh - qh.max(dim=-1, keepdim=True).values).reshape(B, T, 512)   # the kernel keeps q un-normalised
+    want = {1: ln, 2: qe, 3: a2, 4: h_ca, 6: a5}
 
     eng.set_option("fused", 0)
     ref_block = eng.block_forward(0, 0, h0, emb)
