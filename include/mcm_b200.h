@@ -120,8 +120,8 @@ int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const f
 
 /* Measurement aid for bench.py's roofline leg: when enabled, every kernel launch of the library is
  * bracketed by CUDA events on its stream; collect() synchronises the device and returns, for class 0
- * (tcgen05 GEMM) and class 1 (row kernels), the summed device time [ms], launch count and algorithmic
- * flops, then clears the record.  Arrays have 2 entries. */
+ * (tcgen05 GEMM), class 1 (row kernels) and class 2 (fused cross-attention + FFN kernel), the summed device time
+ * [ms], launch count and algorithmic flops, then clears the record.  Arrays have 3 entries. */
 void mcm_timing_enable(int on);
 int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops);
 

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcm_b200.so")
+# MCM_LIB_PATH: development aid -- load an alternative build of the same library (kernel variant A/B runs)
+LIB_PATH = os.environ.get("MCM_LIB_PATH") or os.path.join(_HERE, "libmcm_b200.so")
 
 
 class McmError(RuntimeError):
@@ -100,9 +101,10 @@ def timing_enable(on):
 
 def timing_collect():
     """-> dict(gemm=dict(ms, launches, flops), row=dict(...)); clears the record."""
-    ms = (ctypes.c_double * 2)()
-    n = (ctypes.c_ulonglong * 2)()
-    fl = (ctypes.c_double * 2)()
+    ms = (ctypes.c_double * 3)()
+    n = (ctypes.c_ulonglong * 3)()
+    fl = (ctypes.c_double * 3)()
     check(load().mcm_timing_collect(ms, n, fl))
     return {"gemm": dict(ms=ms[0], launches=int(n[0]), flops=fl[0]),
-            "row": dict(ms=ms[1], launches=int(n[1]), flops=fl[1])}
+            "row": dict(ms=ms[1], launches=int(n[1]), flops=fl[1]),
+            "fused": dict(ms=ms[2], launches=int(n[2]), flops=fl[2])}

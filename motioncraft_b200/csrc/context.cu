@@ -689,7 +689,8 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   if (!lo && fused_block_supported(c->T, c->D, c->F, c->H)) {
     if (dev_alloc(c, &c->ws[0].hid, fused_block_hid_bytes())) return fail(0);
   }
-  if (const char* e = getenv("MCM_DUAL")) c->dual = atoi(e);
+  int dual_env = -1;                     // MCM_DUAL only picks the default; the second scratch set always exists
+  if (const char* e = getenv("MCM_DUAL")) dual_env = atoi(e);
   if (const char* e = getenv("MCM_GRAPH")) c->use_graph = atoi(e);
   if (dev_alloc(c, reinterpret_cast<void**>(&c->t_buf), (size_t)c->Bmax * sizeof(long long))) return fail(0);
   if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess ||
@@ -725,6 +726,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
       return fail(0);
     }
   }
+  if (c->dual && dual_env >= 0) c->dual = dual_env ? 1 : 0;
   *out = c;
   return 0;
 }

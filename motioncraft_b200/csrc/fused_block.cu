@@ -37,14 +37,24 @@ constexpr int D = 512, F = 1024, H = 4, HD = 128;
 constexpr int ROWS = 128;                  // rows per CTA
 constexpr int SLAB = 16384;                // 128 rows x 64 fp16
 constexpr int NSLOT = 4;
-constexpr int NCW = 8;                     // compute warps
+#ifndef MCM_FB_NCW
+#define MCM_FB_NCW 8
+#endif
+constexpr int NCW = MCM_FB_NCW;            // compute warps: 8 or 16 (2 or 4 per TMEM lane quadrant)
+constexpr int WPQ = NCW / 4;               // warps sharing a lane quadrant; each owns CPW accumulator columns
+constexpr int CPW = D / WPQ;               // 256 or 128
+constexpr int NCH = CPW / 32;              // 32-column chunks per warp and phase
+constexpr int QCH = 256 / WPQ / 32;        // chunks per warp of one 256-column quarter of the FFN hidden layer
 constexpr int THREADS = 64 + 32 * NCW;
 constexpr int OPA_BYTES = (D / 64) * SLAB;
 constexpr int RING_BYTES = NSLOT * SLAB;
-constexpr int STG_BYTES = NCW * 4096;
+constexpr int STG_BYTES = 32768;
+constexpr int STG_PER_WARP = STG_BYTES / NCW;        // 4096 or 2048: E4's fp16 store staging (2 KB tiles)
+constexpr int RED_SLOTS = OPA_BYTES / NCW / 4096;    // 4 or 2 rotating fp32 staging tiles per warp for the reductions into h
+constexpr int BIAS_OFF = 28672;            // per-warp 128-byte bias broadcast slots (not during E4, which owns the staging region)
 constexpr int SMEM_BYTES = OPA_BYTES + RING_BYTES + STG_BYTES + 1024;
 constexpr int MAX_SAMPLES = 6;             // samples a 256-row tile may span (4 KB of staged AdaLN parameters each)
-constexpr int XCH_OFF = MAX_SAMPLES * 4096;   // LayerNorm partial statistics, inside the staging region
+constexpr int XCH_OFF = MAX_SAMPLES * 4096;   // LayerNorm partial statistics (NCW x 32 x 2 floats <= 4 KB), inside the staging region
 constexpr int TMEM_COLS = 512;
 constexpr float L2E = 1.4426950408889634f;
 
@@ -109,10 +119,11 @@ __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int row
       gb[j] = __ldg(reinterpret_cast<const float4*>(lnb) + j * 32 + lane);
     }
   }
-  float4 nx[2][4];
+  constexpr int RPI = NCW == 8 ? 2 : 1;      // rows in flight per iteration (register budget: 168 / 96 per thread)
+  float4 nx[RPI][4];
   auto fetch = [&](int i) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RPI; ++u) {
       const long long g = g0 + ew + NCW * (i + u);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -121,15 +132,15 @@ __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int row
   };
   fetch(0);
 #pragma unroll 1
-  for (int i = 0; i < ROWS / NCW; i += 2) {
-    float4 x[2][4];
+  for (int i = 0; i < ROWS / NCW; i += RPI) {
+    float4 x[RPI][4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < RPI; ++u)
 #pragma unroll
       for (int j = 0; j < 4; ++j) x[u][j] = nx[u][j];
-    if (i + 2 < ROWS / NCW) fetch(i + 2);
+    if (i + RPI < ROWS / NCW) fetch(i + RPI);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RPI; ++u) {
       const int r = ew + NCW * (i + u);
       float mean = 0.f, rstd = 1.f;
       if (LN) {
@@ -168,11 +179,11 @@ __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int row
 // OPA receives the UN-normalised exp(q - max) (in (0, 1], the same relative fp16 rounding as the normalised value);
 // the 1 / sum of each head is returned in inv0 / inv1 and applied to the fp32 accumulator of q * ctx by the same thread
 // in E2 (y = softmax(q) ctx is linear in the scale of q per head).  Two streaming passes over TMEM, 32 live values.
-__device__ __forceinline__ void epi_softmax(uint32_t trow, int hf, int row, uint32_t opa, float* bslot, int lane,
+__device__ __forceinline__ void epi_softmax(uint32_t trow, int part, int row, uint32_t opa, float* bslot, int lane,
                                             const float* __restrict__ bias, float& inv0, float& inv1) {
 #pragma unroll 1
-  for (int i = 0; i < 2; ++i) {
-    const int col0 = hf * 256 + i * 128;
+  for (int i = 0; i < CPW / HD; ++i) {
+    const int col0 = part * CPW + i * 128;
     float m = -INFINITY;
     float bcur = __ldg(bias + col0 + lane);
 #pragma unroll 1
@@ -223,16 +234,16 @@ __device__ __forceinline__ void epi_softmax(uint32_t trow, int hf, int row, uint
 // The two warps of a lane quadrant each own 256 columns and exchange (mean, M2) partial statistics; the statistics
 // are accumulated about the row's first element so that one pass suffices without cancellation.
 template <bool BIAS, bool SCALE>
-__device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool act, const float* prm, float* xch, int ew,
+__device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool act, const float* prm, float* xch, int ew,
                                           int quad, uint32_t opa, float* bslot, int lane, const float* __restrict__ bias,
                                           float inv0, float inv1) {
   float K = 0.f, sd = 0.f, sq = 0.f;
-  float bcur = BIAS ? __ldg(bias + hf * 256 + lane) : 0.f;
+  float bcur = BIAS ? __ldg(bias + part * CPW + lane) : 0.f;
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     float v[32];
-    tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
-    const float bnxt = BIAS ? __ldg(bias + hf * 256 + ((c + 1) & 7) * 32 + lane) : 0.f;
+    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
+    const float bnxt = BIAS ? __ldg(bias + part * CPW + ((c + 1) & (NCH - 1)) * 32 + lane) : 0.f;
     tmem_ld_wait();
     if (BIAS) add_bias32(bslot, lane, bcur, v);
     bcur = bnxt;
@@ -245,29 +256,36 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool a
       sq = fmaf(d, d, sq);
     }
   }
-  const float mean_w = fmaf(sd, 1.f / 256.f, K);
-  const float m2_w = fmaf(-sd * (1.f / 256.f), sd, sq);
+  const float mean_w = fmaf(sd, 1.f / (float)CPW, K);
+  const float m2_w = fmaf(-sd * (1.f / (float)CPW), sd, sq);
   xch[(ew * 32 + lane) * 2] = mean_w;
   xch[(ew * 32 + lane) * 2 + 1] = m2_w;
-  bar_sync(1 + quad, 64);
-  const float mean_o = xch[((ew ^ 4) * 32 + lane) * 2];
-  const float m2_o = xch[((ew ^ 4) * 32 + lane) * 2 + 1];
-  const float delta = mean_o - mean_w;
-  const float mean = 0.5f * (mean_w + mean_o);
-  const float m2 = (m2_w + m2_o) + delta * delta * 128.f;
+  bar_sync(1 + quad, 32 * WPQ);
+  // combine the WPQ partial (mean, M2) pairs of this row (equal counts): Chan et al.
+  float msum = 0.f, m2 = 0.f;
+  float mj[WPQ];
+#pragma unroll
+  for (int j = 0; j < WPQ; ++j) {
+    mj[j] = xch[(((ew & 3) + 4 * j) * 32 + lane) * 2];
+    m2 += xch[(((ew & 3) + 4 * j) * 32 + lane) * 2 + 1];
+    msum += mj[j];
+  }
+  const float mean = msum * (1.f / (float)WPQ);
+#pragma unroll
+  for (int j = 0; j < WPQ; ++j) m2 = fmaf((mj[j] - mean) * (mj[j] - mean), (float)CPW, m2);
   const float rstd = rsqrtf(m2 * (1.f / (float)D) + 1e-5f);
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {          // bcur holds chunk 0's bias again
+  for (int c = 0; c < NCH; ++c) {        // bcur holds chunk 0's bias again
     float v[32];
-    tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
-    const float bnxt = BIAS ? __ldg(bias + hf * 256 + ((c + 1) & 7) * 32 + lane) : 0.f;
+    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
+    const float bnxt = BIAS ? __ldg(bias + part * CPW + ((c + 1) & (NCH - 1)) * 32 + lane) : 0.f;
     tmem_ld_wait();
     if (BIAS) add_bias32(bslot, lane, bcur, v);
     bcur = bnxt;
     // (x sc - mean) rstd = x A + B
     const float A = SCALE ? ((c >> 2) ? inv1 : inv0) * rstd : rstd;
     const float Bc = -mean * rstd;
-    const int col = hf * 256 + c * 32;
+    const int col = part * CPW + c * 32;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 ga = *reinterpret_cast<const float4*>(prm + col + 8 * q);
@@ -295,20 +313,20 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int hf, int row, bool a
 __device__ __forceinline__ void tma_wait_read3() { asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); }
 // `stg4`: 16 KB of the (idle) operand tile private to this warp = 4 rotating 4 KB slots, so a tile only waits for the
 // reduction issued 4 tiles earlier to have read its slot.
-__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int hf, uint32_t stg4, const CUtensorMap* map, int grow0,
+__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int part, uint32_t stg4, const CUtensorMap* map, int grow0,
                                              float* bslot, int lane, const float* __restrict__ bias, bool& pending) {
-  float bcur = __ldg(bias + hf * 256 + lane);
+  float bcur = __ldg(bias + part * CPW + lane);
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     float v[32];
-    tmem_ld_32x32(trow + (uint32_t)(hf * 256 + c * 32), v);
-    const float bnxt = __ldg(bias + hf * 256 + ((c + 1) & 7) * 32 + lane);
+    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
+    const float bnxt = __ldg(bias + part * CPW + ((c + 1) & (NCH - 1)) * 32 + lane);
     tmem_ld_wait();
     add_bias32(bslot, lane, bcur, v);
     bcur = bnxt;
-    const uint32_t stgw = stg4 + (uint32_t)(c & 3) * 4096u;
-    if (c >= 4) {
-      if (lane == 0) tma_wait_read3();
+    const uint32_t stgw = stg4 + (uint32_t)(c & (RED_SLOTS - 1)) * 4096u;
+    if (c >= RED_SLOTS) {
+      if (lane == 0) { if (RED_SLOTS == 4) tma_wait_read3(); else tma_wait_read1(); }
       __syncwarp();
     }
 #pragma unroll
@@ -317,7 +335,7 @@ __device__ __forceinline__ void epi_reduce_h(uint32_t trow, int hf, uint32_t stg
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_reduce_add_3d(map, stgw, hf * 256 + c * 32, grow0, 0);
+      tma_reduce_add_3d(map, stgw, part * CPW + c * 32, grow0, 0);
       tma_commit();
     }
     pending = true;
@@ -348,7 +366,6 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
   __shared__ __align__(8) uint64_t afull_bar[8];    // G5: hidden (A) slabs stream through the idle operand tile
   __shared__ __align__(8) uint64_t aempty_bar[8];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float bias_s[NCW][32];
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5;
@@ -574,12 +591,12 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
     // ================================================================== compute warps
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int hf = ew >> 2;                    // which 256-column half of the accumulator this warp owns
+    const int part = ew >> 2;                  // which CPW-column slice of the accumulator this warp owns
     const int row = quad * 32 + lane;          // this thread's row in thread-per-row phases
     const int ctid = ew * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t stgw = stg + (uint32_t)ew * 4096u;
-    float* const bslot = bias_s[ew];
+    const uint32_t stgw = stg + (uint32_t)ew * STG_PER_WARP;
+    float* const bslot = reinterpret_cast<float*>(stg_gen + BIAS_OFF) + ew * 32;
     float* const prm_all = reinterpret_cast<float*>(stg_gen);
     float* const xch = reinterpret_cast<float*>(stg_gen + XCH_OFF);
     uint32_t tf_par[2] = {0u, 0u};
@@ -607,9 +624,9 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       }
     };
 
-    long long tph[16];
+    long long tph[20];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) tph[i] = 0;
+    for (int i = 0; i < 20; ++i) tph[i] = 0;
     const bool prof = p.prof != nullptr;
     long long tlast = prof ? clock64() : 0;
 #define FB_TICK(i) do { if (prof) { const long long _n = clock64(); tph[i] += _n - tlast; tlast = _n; } } while (0)
@@ -632,23 +649,22 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       rows_to_opa<true>(p.h, p.rows, gc, opa, ew, lane, p.ca_ln_w, p.ca_ln_b);
       if (++done < last) arrive_te(true, true);
       {
-        // pull the NEXT tile's rows of h into L2 while this tile computes (P0 is otherwise an HBM round trip per row pair)
+        // pull the NEXT tile's rows of h (one contiguous 256 KB block per CTA) into L2 while this tile computes:
+        // P0 is otherwise an HBM round trip per row pair, and all CTAs issue theirs at the same moment
         const long long gn = (long long)(tile + n_clusters) * 2 * ROWS + rank * ROWS;
-        if (tile + n_clusters < p.n_tiles) {
-#pragma unroll
-          for (int k = 0; k < (ROWS * D * 4 / 128) / (NCW * 32); ++k) {
-            const int line = ctid + k * NCW * 32;              // 128-byte line of this CTA's 128 x 2 KB rows
-            const long long r = gn + (line >> 4);
-            if (r < p.rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.h + r * D + (line & 15) * 32));
-          }
+        if (tile + n_clusters < p.n_tiles && lane == 0) {
+          const long long r0 = gn + ew * (ROWS / NCW);
+          const long long nrow = min((long long)(ROWS / NCW), (long long)p.rows - r0);
+          if (nrow > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h + r0 * D), "r"((uint32_t)(nrow * D * 4)) : "memory");
         }
       }
-      FB_TICK(0);
+      if (it == 0) FB_TICK(15 + 4); else FB_TICK(0);
       if (done < last) {
         // ---- E1
         wait_tf(0); wait_tf(1);
         FB_TICK(1);
-        epi_softmax(trow, hf, row, opa, bslot, lane, p.ca_bq, qinv0, qinv1);
+        epi_softmax(trow, part, row, opa, bslot, lane, p.ca_bq, qinv0, qinv1);
         if (++done < last) arrive_te(true, true);
         FB_TICK(2);
       }
@@ -662,7 +678,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           FB_TICK(3);
           const bool act = (s_row == s) && (grow < p.rows);
           if (__any_sync(0xffffffffu, act))
-            epi_lnmod<false, true>(trow, hf, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, nullptr, qinv0, qinv1);
+            epi_lnmod<false, true>(trow, part, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, nullptr, qinv0, qinv1);
           if (s < s_last || done < last) arrive_te(true, true);
           FB_TICK(4);
         }
@@ -671,7 +687,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         // ---- E3: h += d + bo, then OPA = fp16(h)
         wait_tf(0); wait_tf(1);
         FB_TICK(5);
-        epi_reduce_h(trow, hf, opa + (uint32_t)ew * SLAB, &tm.hred, gc + quad * 32, bslot, lane, p.ca_bo, pending);
+        epi_reduce_h(trow, part, opa + (uint32_t)ew * (OPA_BYTES / NCW), &tm.hred, gc + quad * 32, bslot, lane, p.ca_bo, pending);
         tc_fence_before();
         FB_TICK(6);
         drain_stores(true);
@@ -684,26 +700,28 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       if (done < last) {
         // ---- E4: hidden = GELU(u + b1) -> fp16 -> hidden scratch (this CTA's private rows)
         ++done;
-        float bcur = __ldg(p.f_b1 + hf * 128 + lane);
+        constexpr int QW = 256 / WPQ;          // columns of one quarter owned by this warp
+        constexpr int E4_SLOTS = STG_PER_WARP / 2048;
+        float bcur = __ldg(p.f_b1 + part * QW + lane);
 #pragma unroll 1
-        for (int idx = 0; idx < 16; ++idx) {
-          const int q = idx >> 2, c = idx & 3;
+        for (int idx = 0; idx < 4 * QCH; ++idx) {
+          const int q = idx / QCH, c = idx % QCH;
           if (c == 0) {
             wait_tf(q & 1);
             FB_TICK(9);
           }
           float v[32];
-          tmem_ld_32x32(trow + (uint32_t)((q & 1) * 256 + hf * 128 + c * 32), v);
-          const int nidx = (idx + 1) & 15;
-          const float bnxt = __ldg(p.f_b1 + (nidx >> 2) * 256 + hf * 128 + (nidx & 3) * 32 + lane);
+          tmem_ld_32x32(trow + (uint32_t)((q & 1) * 256 + part * QW + c * 32), v);
+          const int nidx = (idx + 1) % (4 * QCH);
+          const float bnxt = __ldg(p.f_b1 + (nidx / QCH) * 256 + part * QW + (nidx % QCH) * 32 + lane);
           tmem_ld_wait();
-          add_bias32(bslot, lane, bcur, v);
-          bcur = bnxt;
+          // the staging region belongs to the hidden-tile stores in this phase: bias is broadcast by shuffles
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-          const uint32_t sl = stgw + (uint32_t)(idx & 1) * 2048u;
-          if (idx >= 2) {
-            if (lane == 0) tma_wait_read1();
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j] + __shfl_sync(0xffffffffu, bcur, j));
+          bcur = bnxt;
+          const uint32_t sl = stgw + (uint32_t)(idx & (E4_SLOTS - 1)) * 2048u;
+          if (idx >= E4_SLOTS) {
+            if (lane == 0) { if (E4_SLOTS == 2) tma_wait_read1(); else tma_wait_read0(); }
             __syncwarp();
           }
           const uint32_t sw = (uint32_t)((lane >> 1) & 3);
@@ -715,10 +733,10 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tm.hidst, sl, q * 256 + hf * 128 + c * 32, (int)blockIdx.x * ROWS + quad * 32, 0);
+            tma_store_3d(&tm.hidst, sl, q * 256 + part * QW + c * 32, (int)blockIdx.x * ROWS + quad * 32, 0);
             tma_commit();
           }
-          if (c == 3) {
+          if (c == QCH - 1) {
             if (q < 2 || done < last) arrive_te((q & 1) == 0, (q & 1) == 1);
             FB_TICK(10);
           }
@@ -736,7 +754,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         bar_sync(5, NCW * 32);
         wait_tf(0); wait_tf(1);
         FB_TICK(12);
-        epi_lnmod<true, false>(trow, hf, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, p.f_b2, 1.f, 1.f);
+        epi_lnmod<true, false>(trow, part, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, p.f_b2, 1.f, 1.f);
         if (++done < last) arrive_te(true, true);
         FB_TICK(13);
       }
@@ -745,7 +763,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         bar_sync(5, NCW * 32);                               // nobody still reads the staged parameters / statistics
         wait_tf(0); wait_tf(1);
         FB_TICK(14);
-        epi_reduce_h(trow, hf, opa + (uint32_t)ew * SLAB, &tm.hred, gc + quad * 32, bslot, lane, p.f_bo, pending);
+        epi_reduce_h(trow, part, opa + (uint32_t)ew * (OPA_BYTES / NCW), &tm.hred, gc + quad * 32, bslot, lane, p.f_bo, pending);
         tc_fence_before();
         ++done;
         FB_TICK(15);
@@ -768,6 +786,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
     if (prof && lane == 0) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) atomicAdd(p.prof + i, (unsigned long long)tph[i]);
+      atomicAdd(p.prof + 19, (unsigned long long)tph[19]);
     }
 #undef FB_TICK
   }
@@ -864,7 +883,7 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
   // algorithmic flops of the two sub-blocks (AdaLN emb GEMM is not in this kernel)
   const double flops = 2.0 * (double)a.rows * ((double)D * D * 2 + (double)D * HD + 2.0 * D * F + (double)D * D);
   {
-    LaunchTimer lt(LK_GEMM, stream, flops);
+    LaunchTimer lt(LK_FUSED, stream, flops);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(THREADS);

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 
 namespace mcm {
-enum LaunchKind : int { LK_GEMM = 0, LK_ROW = 1, LK_COUNT = 2 };
+enum LaunchKind : int { LK_GEMM = 0, LK_ROW = 1, LK_FUSED = 2, LK_COUNT = 3 };
 
 class LaunchTimer {
  public:

@@ -38,33 +38,10 @@ def main():
     eng.set_option("dual", 0)
     eng.set_option("graph", 0)
 
-    # ---- float64 evaluation of the block, stage by stage (channel attention first, unfused on both sides)
-    P = "temporal_decoder_blocks.0."
-    d = {k: v.double() for k, v in sd.items()}
-    # the oracle's decoder layer in pieces (mcm.py:25-41)
-    xt = h0.double().transpose(1, 2)
-    xt = O.efficient_self_attention(xt, emb.double(), d, P + "sa_block", 4)
-    h_sa = xt.transpose(1, 2).contiguous()
-    ca = P + "ca_block"
-    ln = Fn.layer_norm(h_sa, (512,), d[ca + ".norm.weight"], d[ca + ".norm.bias"])
-    q = Fn.linear(ln, d[ca + ".query.weight"], d[ca + ".query.bias"])
-    qs = torch.softmax(q.view(B, T, 4, 128), dim=-1).reshape(B, T, 512)
-    ctx = O.cross_attention_context(xf_out.double(), d, ca, 4)         # (B, H, 128, 128)
-    y = torch.einsum("bnhd,bhdl->bnhl", qs.view(B, T, 4, 128), ctx).reshape(B, T, 512)
-    def styl(yy, pfx):
-        eo = Fn.linear(Fn.silu(emb.double()), d[pfx + ".emb_layers.1.weight"], d[pfx + ".emb_layers.1.bias"]).unsqueeze(1)
-        sc, sh = eo.chunk(2, dim=2)
-        return Fn.silu(Fn.layer_norm(yy, (512,), d[pfx + ".norm.weight"], d[pfx + ".norm.bias"]) * (1 + sc) + sh)
-    a2 = styl(y, ca + ".proj_out")
-    h_ca = h_sa + Fn.linear(a2, d[ca + ".proj_out.out_layers.2.weight"], d[ca + ".proj_out.out_layers.2.bias"])
-    fn = P + "ffn_temporal"
-    hid = Fn.gelu(Fn.linear(h_ca, d[fn + ".linear1.weight"], d[fn + ".linear1.bias"]))
-    y2 = Fn.linear(hid, d[fn + ".linear2.weight"], d[fn + ".linear2.bias"])
-    a5 = styl(y2, fn + ".proj_out")
-    h_out = h_ca + Fn.linear(a5, d[fn + ".proj_out.out_layers.2.weight"], d[fn + ".proj_out.out_layers.2.bias"])
-    qh = q.view(B, T, 4, 128)
-    qe = torch.exp(qh - qh.max(dim=-1, keepdim=True).values).reshape(B, T, 512)   # the kernel keeps q un-normalised
-    want = {1: ln, 2: qe, 3: a2, 4: h_ca, 6: a5}
+    from tests import common as C
+    st = C.block_stages(sd, h0, emb, xf_out)
+    want = {k: st[k] for k in (1, 2, 3, 4, 6)}
+    h_ca, hid, h_out = st[4], st["hid"], st["out"]
 
     eng.set_option("fused", 0)
     ref_block = eng.block_forward(0, 0, h0, emb)

@@ -24,10 +24,13 @@ lib.mcm_debug_read32(out, 1)
 names = ["P0 LN->OPA", "wait G1", "E1 softmax", "wait G2 (rounds)", "E2 lnmod (rounds)", "wait G3", "E3 reduce", "E3 drain+bar",
          "P_CVT", "wait G4 (4 q)", "E4 gelu (4 q)", "E4 drain", "wait G5 (+stage)", "E5 lnmod", "wait G6", "E6 reduce"]
 tiles = (B * T + 255) // 256
-nw = 8 * 2 * tiles       # compute warps x CTAs x tiles contributing
+NCW = int(os.environ.get("MCM_FB_NCW", "8"))
+nw = NCW * 2 * tiles     # compute warps x CTAs x tiles contributing
 tot = sum(out[i] for i in range(16))
 print(f"block_forward (incl. SA) {e0.elapsed_time(e1):.3f} ms; {tiles} pair tiles; per-warp-per-tile cycles by phase:")
 for i, n in enumerate(names):
     print(f"  {n:22s} {out[i]/nw:10.0f} cyc  {100*out[i]/tot:5.1f}%")
-print(f"  total per tile {tot/nw:10.0f} cyc")
+print(f"  total per tile {(tot + out[19])/nw:10.0f} cyc")
+first = min(tiles, 74)
+print(f"  P0 of a CTA's FIRST tile: {out[19]/(NCW*2*first):.0f} cyc; later tiles: {out[0]/max(1,NCW*2*(tiles-first)):.0f} cyc")
 print(f"MMA warp per tile: wait tempty {out[16]/tiles:.0f}, wait full {out[17]/tiles:.0f}, total {out[18]/tiles:.0f}")

@@ -30,4 +30,5 @@ _lib.timing_enable(True)
 eng.denoise(x, 500)
 tm = _lib.timing_collect()
 _lib.timing_enable(False)
-print("   gemm ms", round(tm['gemm']['ms'], 3), "row ms", round(tm['row']['ms'], 3))
+print("   gemm ms", round(tm['gemm']['ms'], 3), "row ms", round(tm['row']['ms'], 3), "fused ms", round(tm['fused']['ms'], 3),
+      "fused TFLOP/s", round(tm['fused']['flops'] / max(tm['fused']['ms'], 1e-9) / 1e9, 1))
