@@ -62,6 +62,7 @@ struct mcm_ctx {
   mcm_config cfg;
   int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
   int fused = 1;          // MCM_FUSED=0: run cross-attention + FFN as separate GEMM / row kernels (the round-1 path)
+  int fused_sa = 1;       // MCM_FUSED_SA=0: keep the channel-attention tail as separate kernels
   int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
   void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
@@ -291,6 +292,16 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     g.algo_flops = 2.0 * T * hdT * D * B;      // only the per-head diagonal blocks are algorithmic work
     MCM_TRY(gemm_tc_launch(g, st));
   }
+  if (c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D)) {
+    // ---- y = softmax(q) ctx -> AdaLN_T -> SiLU -> Linear(T,T) -> h^T += : one persistent kernel (fused_block.cu)
+    SaTailArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.h = h; a.T = T; a.batch = B;
+    a.qs = opC_t; a.ctxT = view(w.ctxT_sa, Tp); a.wo = k.sa_wo;
+    a.pn_w = k.sa_pn_w; a.pn_b = k.sa_pn_b; a.scale = mod + k.mod_off; a.shift = mod + k.mod_off + T; a.bo = k.sa_bo;
+    a.mod_ld = mod_ld;
+    MCM_TRY(sa_tail_launch(a, st));
+  } else {
   {  // y^T[b] = softmax(q) ctx                                 -> f32A [B*D, T]
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));
@@ -320,6 +331,7 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     g.seg[0].flags = EPI_TRANSPOSED;
     MCM_TRY(gemm_tc_launch(g, st));
   }
+  }   // unfused channel-attention tail
 
   if (c->fused && ff == OP_F16 && w.hid != nullptr && fused_block_supported(T, D, F, H)) {
     // ---- cross attention + FFN in ONE persistent kernel (fused_block.cu) ----
@@ -526,7 +538,7 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
   MCM_TRY(fill_timesteps_launch(c->t_buf, (long long)t, B, gs));
   cudaGraphExec_t exec = nullptr;
   for (auto& g : c->graphs)
-    if (g.B == B && g.have_c == c->have_c && g.fused == c->fused) {
+    if (g.B == B && g.have_c == c->have_c && g.fused == c->fused + 2 * c->fused_sa) {
       exec = g.exec;
       gemm_tc_count_replayed(g.n_gemm);          // keep the library's launch counters truthful under graph replay
       elementwise_count_replayed(g.n_row);
@@ -547,7 +559,7 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     MCM_CUDA(ie);
-    c->graphs.push_back({B, c->have_c, c->fused, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
+    c->graphs.push_back({B, c->have_c, c->fused + 2 * c->fused_sa, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
                          fused_block_launch_count() - f0});
   }
   MCM_CUDA(cudaGraphLaunch(exec, gs));
@@ -685,6 +697,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
     if (alloc_op(c, &c->ws[0].c_op, R1 * c->D, c->D, lo)) return fail(0);
   }
   if (const char* e = getenv("MCM_FUSED")) c->fused = atoi(e);
+  if (const char* e = getenv("MCM_FUSED_SA")) c->fused_sa = atoi(e);
   c->ws[0].hid = nullptr;
   if (!lo && fused_block_supported(c->T, c->D, c->F, c->H)) {
     if (dev_alloc(c, &c->ws[0].hid, fused_block_hid_bytes())) return fail(0);
@@ -745,6 +758,8 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     c->chunk = value;
   } else if (n == "fused") {
     c->fused = value;
+  } else if (n == "fused_sa") {
+    c->fused_sa = value;
   } else if (n == "fused_stop") {
     MCM_CHECK(value >= 0 && value <= 7, "fused_stop must be 0..7");
     c->fused_stop = value;

@@ -800,6 +800,300 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
   }
 }
 
+// =================================================================================================================
+// sa_tail_kernel -- the tail of the channel attention (EfficientSelfAttention on x^T, efficient_attention.py:40-45 with
+// stylization_block.py:29-40, called from mcm.py:28-32) for 256 channel-tokens (half a sample) per CTA pair:
+//   G_a  y = softmax(q) ctx[b]            (A: 256 rows of the fp16 softmax(q) operand, resident in the operand tile;
+//                                          B: this sample's block-diagonal context, transposed)
+//   E_a  OPA = SiLU(LN_T(y) (1 + scale_b) + shift_b)          thread = channel row, statistics over the T features
+//   G_b  d = OPA Wo^T
+//   E_b  h[b, t, n] += d[n, t] + bo[t]    transposed 32 x 32 tiles, TMA reduce-add into the [B, T, 512] residual stream
+// G_a of the next tile runs while E_b of this one drains (different TMEM halves, A slabs are re-loaded after G_b).
+// =================================================================================================================
+struct StMaps {
+  CUtensorMap qs, ctx, wo, hred;
+};
+struct StParams {
+  int T, Np, nkb, nch, batch, n_tiles, mod_ld;
+  const float *pn_w, *pn_b, *scale, *shift, *bo;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NSLOT];
+  __shared__ __align__(8) uint64_t empty_bar[NSLOT];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t afull_bar, aempty_bar;
+  __shared__ uint32_t tmem_slot;
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t opa = smem_base, ring = smem_base + OPA_BYTES, stg = ring + RING_BYTES;
+  uint8_t* const stg_gen = smem_raw + (stg - smem_u32(smem_raw));
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+  const uint32_t slab_b = (uint32_t)(p.Np / 2) * 128u;       // bytes of this CTA's half of a B slab
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.qs); tma_prefetch_desc(&tm.ctx); tma_prefetch_desc(&tm.wo); tma_prefetch_desc(&tm.hred);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSLOT; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&tfull_bar[s]), 1);
+        mbar_init(smem_u32(&tempty_bar[s]), 2u * NCW);
+      }
+      mbar_init(smem_u32(&afull_bar), 1);
+      mbar_init(smem_u32(&aempty_bar), 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(smem_u32(&tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    int slot = 0, it = 0;
+    uint32_t ph = 0;
+    auto push = [&](const CUtensorMap* m, int c0, int c1, int c2, uint32_t bytes) {
+      mbar_wait(smem_u32(&empty_bar[slot]), ph ^ 1u);
+      const uint32_t bar = smem_u32(&full_bar[slot]);
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(bar, 2u * bytes);
+        tma_load_3d_2sm(m, bar, ring + (uint32_t)slot * SLAB, c0, c1, c2);
+      }
+      __syncwarp();
+      if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+    };
+#pragma unroll 1
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
+      const int b = tile >> 1;
+      const int r0 = tile * 2 * ROWS + rank * ROWS;            // first row of this CTA in the [B*512, T] token space
+      mbar_wait(smem_u32(&aempty_bar), ((uint32_t)it & 1u) ^ 1u);   // G_b of the previous tile has read the operand tile
+      const uint32_t abar = smem_u32(&afull_bar);
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(abar, 2u * (uint32_t)p.nkb * SLAB);
+        for (int kb = 0; kb < p.nkb; ++kb) tma_load_3d_2sm(&tm.qs, abar, opa + (uint32_t)kb * SLAB, kb * 64, r0, 0);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int kb = 0; kb < p.nkb; ++kb) push(&tm.ctx, kb * 64, rank * (p.Np / 2), b, slab_b);
+#pragma unroll 1
+      for (int kb = 0; kb < p.nkb; ++kb) push(&tm.wo, kb * 64, rank * (p.Np / 2), 0, slab_b);
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader)
+    if (rank == 0) {
+      int slot = 0, it = 0;
+      uint32_t ph = 0;
+      uint32_t te_par[2] = {0u, 0u};
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      auto step = [&](uint32_t a_addr, uint32_t dcol, bool fresh) {
+        mbar_wait(smem_u32(&full_bar[slot]), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_addr = ring + (uint32_t)slot * SLAB;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(tmem_base + dcol, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                         (fresh && k == 0) ? 0u : 1u);
+          umma_commit_2sm(smem_u32(&empty_bar[slot]), (uint16_t)3);
+        }
+        __syncwarp();
+        if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+      };
+#pragma unroll 1
+      for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
+        // G_a: needs the A slabs and TMEM half 0 drained (E_a of the previous tile, already awaited by its G_b)
+        mbar_wait(smem_u32(&afull_bar), (uint32_t)it & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < p.nkb; ++kb) step(opa + (uint32_t)kb * SLAB, 0u, kb == 0);
+        if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[0]), (uint16_t)3);
+        __syncwarp();
+        // G_b: operand tile rewritten by E_a (tempty 0), TMEM half 1 drained by E_b of the previous tile (tempty 1)
+        mbar_wait(smem_u32(&tempty_bar[0]), te_par[0]); te_par[0] ^= 1u;
+        mbar_wait(smem_u32(&tempty_bar[1]), te_par[1]); te_par[1] ^= 1u;
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < p.nkb; ++kb) step(opa + (uint32_t)kb * SLAB, 256u, kb == 0);
+        if (elect_one()) {
+          umma_commit_2sm(smem_u32(&tfull_bar[1]), (uint16_t)3);
+          umma_commit_2sm(smem_u32(&aempty_bar), (uint16_t)3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int part = ew >> 2;                                 // NCW == 8: two warps per lane quadrant
+    const int row = quad * 32 + lane;
+    const int ctid = ew * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* const prm = reinterpret_cast<float*>(stg_gen);              // gamma'[Tq] | beta'[Tq] | bo[Tq]   (Tq = nch * 32)
+    float* const xch = reinterpret_cast<float*>(stg_gen + 16384);      // [NCW][32][2]
+    float* const bslot = reinterpret_cast<float*>(stg_gen + 16384 + 4096) + ew * 32;
+    const uint32_t stg2 = opa + 4u * SLAB + (uint32_t)ew * 8192u;      // two 4 KB transposed staging tiles in the unused slabs
+    const int Tq = p.nch * 32;
+    const int c_split = (p.nch + 1) / 2;                      // part 0: chunks [0, c_split), part 1: [c_split, nch)
+    const int c_lo = part == 0 ? 0 : c_split, c_hi = part == 0 ? c_split : p.nch;
+    const float n_mine = (float)(min(p.T, c_hi * 32) - c_lo * 32);
+    uint32_t tf_par[2] = {0u, 0u};
+    bool pending = false;
+    int nstore = 0;
+    auto arrive = [&](int hh) {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(smem_u32(&tempty_bar[hh]), 0u);
+    };
+    arrive(1);                                                // TMEM half 1 starts out free
+    int prev_b = -1;
+#pragma unroll 1
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+      const int b = tile >> 1;
+      const int n0 = (tile & 1) * 2 * ROWS + rank * ROWS;     // first channel of this CTA
+      if (b != prev_b) {
+        // stage this sample's folded AdaLN parameters over the T features (everybody is past E_a of the previous tile:
+        // the barrier below is also crossed only after every warp arrived on tempty 0)
+        bar_sync(5, NCW * 32);
+        for (int t = ctid; t < Tq; t += NCW * 32) {
+          float g = 0.f, be = 0.f, bo = 0.f;
+          if (t < p.T) {
+            const float sc = 1.f + __ldg(p.scale + (size_t)b * p.mod_ld + t);
+            g = __ldg(p.pn_w + t) * sc;
+            be = fmaf(__ldg(p.pn_b + t), sc, __ldg(p.shift + (size_t)b * p.mod_ld + t));
+            bo = __ldg(p.bo + t);
+          }
+          prm[t] = g; prm[Tq + t] = be; prm[2 * Tq + t] = bo;
+        }
+        bar_sync(5, NCW * 32);
+        prev_b = b;
+      }
+      // ---- E_a
+      mbar_wait(smem_u32(&tfull_bar[0]), tf_par[0]); tf_par[0] ^= 1u;
+      tc_fence_after();
+      {
+        float K = 0.f, sd = 0.f, sq = 0.f;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          float v[32];
+          tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (c == c_lo) K = v[0];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = (c * 32 + j < p.T) ? v[j] - K : 0.f;    // columns >= T hold stale TMEM contents
+            sd += d;
+            sq = fmaf(d, d, sq);
+          }
+        }
+        const float mean_w = K + sd / n_mine;
+        const float m2_w = sq - sd * sd / n_mine;
+        xch[(ew * 32 + lane) * 2] = mean_w;
+        xch[(ew * 32 + lane) * 2 + 1] = m2_w;
+        bar_sync(1 + quad, 64);
+        const float mean_o = xch[((ew ^ 4) * 32 + lane) * 2];
+        const float m2_o = xch[((ew ^ 4) * 32 + lane) * 2 + 1];
+        const float n_o = (float)p.T - n_mine;
+        const float delta = mean_o - mean_w;
+        const float mean = mean_w + delta * (n_o / (float)p.T);
+        const float m2 = (m2_w + m2_o) + delta * delta * (n_mine * n_o / (float)p.T);
+        const float rstd = rsqrtf(m2 / (float)p.T + 1e-5f);
+        const float Bc = -mean * rstd;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          float v[32];
+          tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          const int col = c * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ga = *reinterpret_cast<const float4*>(prm + col + 8 * q);
+            const float4 gb = *reinterpret_cast<const float4*>(prm + col + 8 * q + 4);
+            const float4 ba = *reinterpret_cast<const float4*>(prm + Tq + col + 8 * q);
+            const float4 bb = *reinterpret_cast<const float4*>(prm + Tq + col + 8 * q + 4);
+            float y[8];
+            y[0] = silu_fast(fmaf(fmaf(v[8 * q], rstd, Bc), ga.x, ba.x));
+            y[1] = silu_fast(fmaf(fmaf(v[8 * q + 1], rstd, Bc), ga.y, ba.y));
+            y[2] = silu_fast(fmaf(fmaf(v[8 * q + 2], rstd, Bc), ga.z, ba.z));
+            y[3] = silu_fast(fmaf(fmaf(v[8 * q + 3], rstd, Bc), ga.w, ba.w));
+            y[4] = silu_fast(fmaf(fmaf(v[8 * q + 4], rstd, Bc), gb.x, bb.x));
+            y[5] = silu_fast(fmaf(fmaf(v[8 * q + 5], rstd, Bc), gb.y, bb.y));
+            y[6] = silu_fast(fmaf(fmaf(v[8 * q + 6], rstd, Bc), gb.z, bb.z));
+            y[7] = silu_fast(fmaf(fmaf(v[8 * q + 7], rstd, Bc), gb.w, bb.w));
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (col + 8 * q + e >= p.T) y[e] = 0.f;           // K padding of the next GEMM must be exactly zero
+            st_shared_v4u(opa_addr(opa, row, col + 8 * q), pack_f16x2_sat(y[0], y[1]), pack_f16x2_sat(y[2], y[3]),
+                          pack_f16x2_sat(y[4], y[5]), pack_f16x2_sat(y[6], y[7]));
+          }
+        }
+      }
+      arrive(0);
+      // ---- E_b
+      mbar_wait(smem_u32(&tfull_bar[1]), tf_par[1]); tf_par[1] ^= 1u;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; ++c) {
+        float v[32];
+        tmem_ld_32x32(trow + (uint32_t)(256 + c * 32), v);
+        tmem_ld_wait();
+        const uint32_t sl = stg2 + (uint32_t)(nstore & 1) * 4096u;
+        if (nstore >= 2) {
+          if (lane == 0) tma_wait_read1();
+          __syncwarp();
+        }
+        // transposed tile: [t][n], lanes (= channels n) contiguous; the output bias bo[t] is a broadcast read
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float o = v[j] + prm[2 * Tq + c * 32 + j];
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sl + (uint32_t)(j * 32 + lane) * 4u), "f"(o) : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_3d(&tm.hred, sl, n0 + quad * 32, c * 32, b);
+          tma_commit();
+        }
+        ++nstore;
+        pending = true;
+      }
+      arrive(1);
+    }
+    if (pending) {
+      if (lane == 0) tma_wait_all0();
+      __syncwarp();
+    }
+    (void)bslot;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+
 std::atomic<unsigned long long> g_fb_launches{0};
 int g_fb_max_pairs = -1;
 unsigned long long* g_fb_prof = nullptr;
@@ -896,6 +1190,62 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MCM_CUDA(cudaLaunchKernelEx(&cfg, fused_block_kernel, tm, p));
+  }
+  MCM_CUDA(cudaGetLastError());
+  g_fb_launches.fetch_add(1);
+  return 0;
+}
+
+bool sa_tail_supported(int T, int Dm) { return NCW == 8 && Dm == D && T >= 40 && T <= 256 && T % 4 == 0; }
+
+int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
+  MCM_TRY(fb_init());
+  MCM_CHECK(a.h && a.qs.hi && a.ctxT.hi && a.wo.hi && a.batch > 0 && sa_tail_supported(a.T, D), "sa tail: bad arguments");
+  static int max_pairs = -1;
+  if (max_pairs < 0) {
+    MCM_CUDA(cudaFuncSetAttribute(sa_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    cudaLaunchConfig_t oc = {};
+    oc.gridDim = dim3(tc_num_sms() / 2 * 2);
+    oc.blockDim = dim3(THREADS);
+    oc.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute oa[1];
+    oa[0].id = cudaLaunchAttributeClusterDimension;
+    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+    oc.attrs = oa; oc.numAttrs = 1;
+    int n = 0;
+    MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, sa_tail_kernel, &oc));
+    MCM_CHECK(n > 0, "sa_tail_kernel does not fit on this device");
+    max_pairs = n;
+  }
+  const int T = a.T, Tp = a.qs.ld;
+  const int Np = (T + 15) / 16 * 16;
+  MCM_CHECK(a.ctxT.ld == Tp && a.wo.ld == Tp && Tp % 8 == 0 && Tp >= T, "sa tail: operand pitch");
+  StMaps tm;
+  std::memset(&tm, 0, sizeof(tm));
+  MCM_TRY(tc_make_operand_map(&tm.qs, a.qs.hi, OP_F16, Tp, a.batch * D, 1, Tp, 128));
+  MCM_TRY(tc_make_operand_map(&tm.ctx, a.ctxT.hi, OP_F16, Tp, T, a.batch, Tp, Np / 2));
+  MCM_TRY(tc_make_operand_map(&tm.wo, a.wo.hi, OP_F16, Tp, T, 1, Tp, Np / 2));
+  MCM_TRY(tc_make_tile_map(&tm.hred, a.h, 0, D, T, a.batch, D, (long long)T * D, 0));
+  StParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.T = T; p.Np = Np; p.nkb = (T + 63) / 64; p.nch = (T + 31) / 32; p.batch = a.batch; p.n_tiles = a.batch * 2;
+  p.mod_ld = a.mod_ld; p.pn_w = a.pn_w; p.pn_b = a.pn_b; p.scale = a.scale; p.shift = a.shift; p.bo = a.bo;
+  const int n_pairs = std::min(p.n_tiles, max_pairs);
+  const double flops = 2.0 * (double)a.batch * D * ((double)T * (T / 4) + (double)T * T);   // q ctx (per head) + out
+  {
+    LaunchTimer lt(LK_FUSED, stream, flops);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_tail_kernel, tm, p));
   }
   MCM_CUDA(cudaGetLastError());
   g_fb_launches.fetch_add(1);

@@ -36,6 +36,20 @@ struct FusedBlockArgs {
   void* dbg;                // debug: [rows, 512] fp16 dump of the shared-memory operand tile after phase `stop`
 };
 
+// The tail of the channel attention (y = softmax(q) ctx -> AdaLN over T -> SiLU -> Linear(T, T) -> residual into h^T) as
+// one persistent kernel; see sa_tail_kernel in fused_block.cu.
+struct SaTailArgs {
+  float* h;             // [B, T, 512] fp32 residual stream (updated in place, transposed accumulation)
+  int T, batch;
+  OpPtr qs;             // [B*512, Tp] fp16 softmax(q) operand (pad columns zero)
+  OpPtr ctxT;           // [B, T, Tp] fp16 block-diagonal per-sample context, transposed
+  OpPtr wo;             // [T, Tp] fp16 sa_block.proj_out.out_layers.2.weight
+  const float *pn_w, *pn_b, *scale, *shift, *bo;   // proj_out.norm, AdaLN modulation over T (row b at + b * mod_ld), out bias
+  int mod_ld;
+};
+bool sa_tail_supported(int T, int D);
+int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream);
+
 // true if the fused kernel covers this architecture (latent 512, ffn 1024, 4 heads, T >= 52)
 bool fused_block_supported(int T, int D, int F, int H);
 size_t fused_block_hid_bytes();

@@ -18,17 +18,18 @@ def load(path):
     return data
 
 
-def labels(n_layers=8, n_ctrl=0):
+def labels(n_layers=8, n_ctrl=0, fused=False):
     head = ["packx", "tsemb", "te0", "te2", "packemb", "mod", "embed"]
-    blk = ["lnT", "qkv", "smq", "smk", "ctx", "apply", "lnmod", "saout", "ln", "caq", "smq2", "caapply", "lnmod2",
-           "caout", "lin1", "lin2", "lnmod3", "ffnout"]
-    return head + [b + str(i) for i in range(n_layers) for b in blk] + ["out"]
+    blk = ["lnT", "qkv", "smq", "smk", "ctx", "apply", "lnmod", "saout"]
+    blk += ["fused_ca_ffn"] if fused else ["ln", "caq", "smq2", "caapply", "lnmod2", "caout", "lin1", "lin2", "lnmod3", "ffnout"]
+    tail = ["packh", "out"] if fused else ["out"]
+    return head + [b + str(i) for i in range(n_layers) for b in blk] + tail
 
 
 def main():
     data = load(sys.argv[1])
     verbose = len(sys.argv) > 2
-    labs = labels()
+    labs = labels(fused=any("fused_block" in d["name"] for d in data.values()))
     tot = 0.0
     agg = collections.defaultdict(lambda: [0.0, 0, 0.0, 0.0])
     for i, d in enumerate(data.values()):
@@ -39,7 +40,7 @@ def main():
         a = agg[base]
         a[0] += t; a[1] += 1
         a[2] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
-        a[3] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0)
+        a[3] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0))
         if verbose and (i < 25 or i == len(data) - 1):
             print(f"{lab:10s} {d['name'][:24]:24s} {t:9.1f} us")
     print(f"launches {len(data)}  total {tot:.1f} us")
