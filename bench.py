@@ -34,6 +34,8 @@ WORKLOADS = {
     "m2d": dict(B=64, T=1024, n_ctrl=4, c_feats=35, c_len=1024),
 }
 RESPACE = "15,15,8,6,6"
+# ncu (--set full, single stream, B=256 x T=196): dram__bytes_read.sum + dram__bytes_write.sum of one fused_block_kernel launch
+FUSED_DRAM_BYTES_PER_LAUNCH = 441e6
 N_STEPS = 50
 
 
@@ -292,12 +294,13 @@ def main():
     # ---- roofline leg: separate instrumented run (events around every launch), not part of the numbers above
     # (single stream, eager launches: with the two-stream schedule of the timed region kernels of different streams
     # share the SMs, so per-kernel event times would no longer be times of a kernel running alone)
+    dual_default = os.environ.get("MCM_DUAL", "1") != "0"
     eng.set_option("dual", 0)
     _lib.timing_enable(True)
     one_run_device()
     tm = _lib.timing_collect()
     _lib.timing_enable(False)
-    eng.set_option("dual", 1)
+    eng.set_option("dual", 1 if dual_default else 0)
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
@@ -311,9 +314,25 @@ def main():
         per_step, once = algorithmic_flops(T, wl["n_ctrl"], c_feats=wl["c_feats"], c_len=wl["c_len"])
         flops_run = B * (N_STEPS * per_step + once)            # per GPU per sampling run
         peaks = measured_peaks()
-        gemm_ms = tm["gemm"]["ms"]
-        achieved = flops_run / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        gemm_ms = tm["gemm"]["ms"] + tm["fused"]["ms"]          # every tcgen05 kernel of the run
+        all_tc = flops_run / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         whole = flops_run / (ms_dev / args.steps * 1e-3) / 1e12
+        fz = tm["fused"]
+        if fz["launches"] > 0:
+            # dominant kernel: the fused cross-attention + FFN token kernel (one launch per decoder layer and step).
+            # achieved = its ALGORITHMIC flops (SURVEY.md 8a rows a9 + a10 without the AdaLN emb GEMM:
+            # 2 * rows * (2*512*512 + 512*128 + 2*512*1024 + 512*512) per launch) / its CUDA-event device time
+            kernel = ("fused_block_kernel (cross-attention + FFN of one decoder layer, tcgen05 cta_group::2; all launches of "
+                      "one sampling run, timed single-stream with CUDA events around every launch)")
+            achieved = fz["flops"] / (fz["ms"] * 1e-3) / 1e12
+            dom_ms, dom_n = fz["ms"], fz["launches"]
+            # dram__bytes_read + dram__bytes_write per launch, ncu --set full (profiles/r01_fused_block_kernel_metrics.csv);
+            # algorithmic minimum is one read + one write of h = 2 * B*T*512*4 bytes
+            traffic = FUSED_DRAM_BYTES_PER_LAUNCH if (args.workload == "t2m" and B == 256) else None
+            algo_bytes = 2.0 * B * T * 512 * 4
+        else:
+            kernel = "gemm_tc_kernel (tcgen05, all launches of one sampling run; timed single-stream, eager)"
+            achieved, dom_ms, dom_n, traffic, algo_bytes = all_tc, tm["gemm"]["ms"], tm["gemm"]["launches"], None, None
         line = {
             "metric": "sampled motion frames/sec (50-step DDIM)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -323,15 +342,15 @@ def main():
                     "d2h_bytes_per_step": int(out_pin.numel() * 4), "api": "mcm_sample_host (pinned host x_T -> x_0)"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all launches of one sampling run; timed single-stream, eager)",
+            "roofline": {"bound": "tensor", "kernel": kernel,
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None,
-                         # dram__bytes_read+write summed over the 85 GEMM launches of one denoise step (ncu, profiles/
-                         # r01_launches_step_t2m_final.csv: 13.4 GB) x 50 steps; only measured for the t2m workload
-                         "traffic": 13.406e9 * N_STEPS if (args.workload == "t2m" and B == 256) else None,
-                         "traffic_unit": "bytes per sampling run (all gemm_tc_kernel launches)",
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "algorithmic_bytes_per_launch": algo_bytes,
                          "peak_source": peaks["source"], "algorithmic_gflop_per_frame": flops_run / (B * T) / 1e9,
-                         "gemm_ms_per_run": gemm_ms, "gemm_launches_per_run": tm["gemm"]["launches"],
+                         "kernel_ms_per_run": dom_ms, "kernel_launches_per_run": dom_n,
+                         "kernel_share_of_device_time": dom_ms / (gemm_ms + tm["row"]["ms"]) if gemm_ms > 0 else None,
+                         "all_tcgen05_kernels_ms_per_run": gemm_ms, "all_tcgen05_kernels_achieved": all_tc,
+                         "other_tcgen05_launches_per_run": tm["gemm"]["launches"],
                          "row_kernel_ms_per_run": tm["row"]["ms"], "row_kernel_launches_per_run": tm["row"]["launches"],
                          "whole_step_achieved": whole, "whole_step_frac": whole / peaks["tflops"]},
         }

@@ -62,7 +62,8 @@ struct mcm_ctx {
   mcm_config cfg;
   int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
   int fused = 1;          // MCM_FUSED=0: run cross-attention + FFN as separate GEMM / row kernels (the round-1 path)
-  int fused_sa = 1;       // MCM_FUSED_SA=0: keep the channel-attention tail as separate kernels
+  int fused_sa = 1;       // MCM_FUSED_SA: 0 = channel attention as separate kernels, 1 = fused tail (default),
+                          // 2 = fused head and tail (correct, but its head kernel is still slower than the kernels it replaces)
   int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
   void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
@@ -257,6 +258,16 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
   const OpPtr hop = view(w.hop, D);
 
   // ---- channel attention (EfficientSelfAttention on x^T, efficient_attention.py:25-46) ----
+  const bool sa_fused = c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D) && H == 4 && 32 * Tp * 2 <= 16384;
+  if (sa_fused && c->fused_sa >= 2) {
+    // ---- LN_T(h^T) -> q | k | v -> softmax(q): one persistent kernel (fused_block.cu); k (fp32) and v go back to [B, T', D]
+    SaFrontArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.h = h; a.T = T; a.batch = B; a.heads = H;
+    a.ln_w = k.sa_ln_w; a.ln_b = k.sa_ln_b; a.w = k.sa_wqkv; a.bqkv = k.sa_bqkv;
+    a.qs = opC_t; a.k32 = w.f32B; a.v16 = opB_d;
+    MCM_TRY(sa_front_launch(a, st));
+  } else {
   // xn^T = LayerNorm_T(h^T)                                   -> opA [B*D, Tp]
   MCM_TRY(ln_transpose_launch(h, B, T, D, k.sa_ln_w, k.sa_ln_b, opA_t, ff, st));
   {  // q | k | v = xn^T W^T + b ; q stays row-major fp32, k and v go back to the [B, T', D] layout
@@ -277,6 +288,7 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
   }
   // q: softmax over each head's T/H features; k: softmax over the D channel-tokens (a row in [B,T',D])
   MCM_TRY(softmax_seg_launch(w.f32A, B * D, T, T, hdT, opC_t, ff, st));
+  }   // unfused channel-attention head
   MCM_TRY(softmax_seg_launch(w.f32B, B * T, D, D, D, opD_d, ff, st));
   {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, stored transposed: ctxT[b][l][dk]
     GemmProblem g;
@@ -292,7 +304,7 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     g.algo_flops = 2.0 * T * hdT * D * B;      // only the per-head diagonal blocks are algorithmic work
     MCM_TRY(gemm_tc_launch(g, st));
   }
-  if (c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D)) {
+  if (sa_fused) {
     // ---- y = softmax(q) ctx -> AdaLN_T -> SiLU -> Linear(T,T) -> h^T += : one persistent kernel (fused_block.cu)
     SaTailArgs a;
     std::memset(&a, 0, sizeof(a));

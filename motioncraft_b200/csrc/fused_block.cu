@@ -1094,6 +1094,353 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
 }
 
 
+// =================================================================================================================
+// sa_front_kernel -- the head of the channel attention (EfficientSelfAttention on x^T, efficient_attention.py:29-36,
+// called from mcm.py:28-32) for 256 channel-tokens (half a sample) per CTA pair:
+//   P    OPA = LN_T(h^T)        thread = channel, statistics over the T frames read straight out of h[b, :, n] (coalesced
+//                               across channels), so the transposed tensor is never materialised
+//   G_q  q = OPA Wq^T    G_k  k = OPA Wk^T    (TMEM halves 0 / 1)      G_v  v = OPA Wv^T (half 0 again, after E_q)
+//   E_q  softmax over each head's T/H features -> fp16 rows -> one TMA store per warp       (warps 0..3 of the 8)
+//   E_k  k + bk -> fp32, stored TRANSPOSED into [B, T, 512] (the token softmax and k^T v stay separate kernels: they
+//        reduce over all 512 channels of a sample, i.e. across tiles)                        (warps 4..7)
+//   E_v  v + bv -> fp16, stored transposed into [B, T, 512]
+// =================================================================================================================
+struct SfMaps {
+  CUtensorMap w, qs, k32, v16;
+};
+struct SfParams {
+  const float* h;
+  int T, Tp, Np, nkb, nch, hd, batch, n_tiles;
+  const float *ln_w, *ln_b, *bqkv;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NSLOT];
+  __shared__ __align__(8) uint64_t empty_bar[NSLOT];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t pa_bar, qd_bar;           // operand tile written (16 warps) / q accumulator drained (8 warps)
+  __shared__ uint32_t tmem_slot;
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t opa = smem_base, ring = smem_base + OPA_BYTES, stg = ring + RING_BYTES;
+  uint8_t* const stg_gen = smem_raw + (stg - smem_u32(smem_raw));
+  uint8_t* const opa_gen = smem_raw + (opa - smem_u32(smem_raw));
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+  const uint32_t slab_b = (uint32_t)(p.Np / 2) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.w); tma_prefetch_desc(&tm.qs); tma_prefetch_desc(&tm.k32); tma_prefetch_desc(&tm.v16);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSLOT; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(&tfull_bar[0]), 1);
+      mbar_init(smem_u32(&tfull_bar[1]), 1);
+      mbar_init(smem_u32(&pa_bar), 2u * NCW);
+      mbar_init(smem_u32(&qd_bar), NCW);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(smem_u32(&tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: q | k | v weight slabs
+    int slot = 0;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+#pragma unroll 1
+      for (int seg = 0; seg < 3; ++seg)
+#pragma unroll 1
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[slot]), ph ^ 1u);
+          const uint32_t bar = smem_u32(&full_bar[slot]);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(bar, 2u * slab_b);
+            tma_load_3d_2sm(&tm.w, bar, ring + (uint32_t)slot * SLAB, kb * 64, seg * p.T + rank * (p.Np / 2), 0);
+          }
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader)
+    if (rank == 0) {
+      int slot = 0, it = 0;
+      uint32_t ph = 0;
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      auto gemm = [&](uint32_t dcol) {
+#pragma unroll 1
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[slot]), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = opa + (uint32_t)kb * SLAB, b_addr = ring + (uint32_t)slot * SLAB;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(tmem_base + dcol, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                           (kb == 0 && k == 0) ? 0u : 1u);
+            umma_commit_2sm(smem_u32(&empty_bar[slot]), (uint16_t)3);
+          }
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+        }
+      };
+#pragma unroll 1
+      for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
+        mbar_wait(smem_u32(&pa_bar), (uint32_t)it & 1u);    // operand tile written; every warp is past E_v of the previous tile
+        tc_fence_after();
+        gemm(0u);
+        if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[0]), (uint16_t)3);
+        __syncwarp();
+        gemm(256u);
+        if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[1]), (uint16_t)3);
+        __syncwarp();
+        mbar_wait(smem_u32(&qd_bar), (uint32_t)it & 1u);    // E_q has drained TMEM half 0
+        tc_fence_after();
+        gemm(0u);
+        if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[0]), (uint16_t)3);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int part = ew >> 2;
+    const int row = quad * 32 + lane;
+    const int ctid = ew * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int Tq = p.nch * 32;
+    float* const prm = reinterpret_cast<float*>(stg_gen);             // ln_w | ln_b | bq | bk | bv, Tq floats each (<= 5 KB)
+    float* const xch = reinterpret_cast<float*>(stg_gen + 6144);      // [NCW][32][2]
+    // staging: E_q rows (32 x Tp fp16 <= 16 KB) / E_v tiles of warps 0..3 in operand-tile slabs 4..7; E_k / E_v tiles of
+    // warps 4..7 in the staging region
+    const uint32_t stg_q = opa + 4u * SLAB + (uint32_t)(ew & 3) * SLAB;
+    uint16_t* const stg_q_gen = reinterpret_cast<uint16_t*>(opa_gen + 4 * SLAB + (ew & 3) * SLAB);
+    const uint32_t stg_k = stg + 8192u + (uint32_t)(ew & 3) * 4096u;
+    const uint32_t stg_mine = part == 0 ? stg_q : stg_k;
+    const int c_split = (p.nch + 1) / 2;
+    uint32_t tf_par[2] = {0u, 0u};
+    auto wait_tf = [&](int hh) {
+      mbar_wait(smem_u32(&tfull_bar[hh]), tf_par[hh]);
+      tf_par[hh] ^= 1u;
+      tc_fence_after();
+    };
+    bool pending = false;
+    auto drain = [&]() {
+      if (pending) {
+        if (lane == 0) tma_wait_read0();
+        __syncwarp();
+        pending = false;
+      }
+    };
+    // parameters do not depend on the sample: staged once
+    for (int t = ctid; t < Tq; t += NCW * 32) {
+      const bool ok = t < p.T;
+      prm[t] = ok ? __ldg(p.ln_w + t) : 0.f;
+      prm[Tq + t] = ok ? __ldg(p.ln_b + t) : 0.f;
+      prm[2 * Tq + t] = ok ? __ldg(p.bqkv + t) : 0.f;
+      prm[3 * Tq + t] = ok ? __ldg(p.bqkv + p.T + t) : 0.f;
+      prm[4 * Tq + t] = ok ? __ldg(p.bqkv + 2 * p.T + t) : 0.f;
+    }
+    bar_sync(5, NCW * 32);
+    const int T2 = ((p.T + 1) / 2 + 7) / 8 * 8;               // frames [0, T2) to warps 0..3, [T2, T) to warps 4..7
+    const int t_lo = part * T2, t_hi = part == 0 ? T2 : p.T;
+    const int t_end = part == 0 ? T2 : p.nkb * 64;            // warps 4..7 also write the zero K padding
+#pragma unroll 1
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+      const int b = tile >> 1;
+      const int n0 = (tile & 1) * 2 * ROWS + rank * ROWS;
+      // ---- P: LayerNorm over the T frames of channel n0 + row, written as row `row` of the operand tile
+      {
+        const float* __restrict__ src = p.h + ((size_t)b * p.T) * D + n0 + row;
+        // 32 independent loads in flight per thread: with ~no L1 every frame row is an L2 / HBM round trip
+        float K = __ldcg(src + (size_t)t_lo * D), sd = 0.f, sq = 0.f;
+#pragma unroll 1
+        for (int t0 = t_lo; t0 < t_hi; t0 += 32) {
+          float x[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = (t0 + e < t_hi) ? __ldcg(src + (size_t)(t0 + e) * D) : K;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float d = x[e] - K;
+            sd += d;
+            sq = fmaf(d, d, sq);
+          }
+        }
+        const float n_mine = (float)(t_hi - t_lo), n_o = (float)p.T - n_mine;
+        const float mean_w = K + sd / n_mine;
+        const float m2_w = sq - sd * sd / n_mine;
+        xch[(ew * 32 + lane) * 2] = mean_w;
+        xch[(ew * 32 + lane) * 2 + 1] = m2_w;
+        bar_sync(1 + quad, 64);
+        const float mean_o = xch[((ew ^ 4) * 32 + lane) * 2];
+        const float m2_o = xch[((ew ^ 4) * 32 + lane) * 2 + 1];
+        const float delta = mean_o - mean_w;
+        const float mean = mean_w + delta * (n_o / (float)p.T);
+        const float m2 = (m2_w + m2_o) + delta * delta * (n_mine * n_o / (float)p.T);
+        const float rstd = rsqrtf(m2 / (float)p.T + 1e-5f);
+#pragma unroll 1
+        for (int t0 = t_lo; t0 < t_end; t0 += 32) {
+          float x[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = (t0 + e < p.T) ? __ldcg(src + (size_t)(t0 + e) * D) : 0.f;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int t8 = t0 + 8 * g8;
+            if (t8 < t_end) {
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int t = t8 + e;
+                y[e] = (t < p.T) ? fmaf((x[8 * g8 + e] - mean) * rstd, prm[t], prm[Tq + t]) : 0.f;
+              }
+              st_shared_v4u(opa_addr(opa, row, t8), pack_f16x2_sat(y[0], y[1]), pack_f16x2_sat(y[2], y[3]),
+                            pack_f16x2_sat(y[4], y[5]), pack_f16x2_sat(y[6], y[7]));
+            }
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(smem_u32(&pa_bar), 0u);
+      }
+      wait_tf(0);                                             // q complete
+      if (part == 0) {
+        // ---- E_q: per-head softmax of q + bq (three passes over the head's chunks), rows staged as [32][Tp] fp16
+        drain();
+#pragma unroll 1
+        for (int hh = 0; hh < H; ++hh) {
+          const int lo = hh * p.hd, hi = lo + p.hd;
+          const int c0 = lo >> 5, c1 = (hi - 1) >> 5;
+          float m = -INFINITY;
+#pragma unroll 1
+          for (int c = c0; c <= c1; ++c) {
+            float v[32];
+            tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = c * 32 + j;
+              if (col >= lo && col < hi) m = fmaxf(m, v[j] + prm[2 * Tq + col]);
+            }
+          }
+          const float ml = m * L2E;
+          float ssum = 0.f;
+#pragma unroll 1
+          for (int c = c0; c <= c1; ++c) {
+            float v[32];
+            tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = c * 32 + j;
+              if (col >= lo && col < hi) ssum += ex2_fast(fmaf(v[j] + prm[2 * Tq + col], L2E, -ml));
+            }
+          }
+          const float inv = 1.f / ssum;
+#pragma unroll 1
+          for (int c = c0; c <= c1; ++c) {
+            float v[32];
+            tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = c * 32 + j;
+              if (col >= lo && col < hi)
+                stg_q_gen[lane * p.Tp + col] = f32_to_f16_bits(ex2_fast(fmaf(v[j] + prm[2 * Tq + col], L2E, -ml)) * inv);
+            }
+          }
+        }
+        for (int col = p.T; col < p.Tp; ++col) stg_q_gen[lane * p.Tp + col] = 0;   // operand pad columns
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_remote(smem_u32(&qd_bar), 0u);
+          tma_store_3d(&tm.qs, stg_q, 0, b * D + n0 + quad * 32, 0);
+          tma_commit();
+        }
+        pending = true;
+        wait_tf(1);                                           // (k is handled by warps 4..7; keep the phase count in step)
+      } else {
+        // ---- E_k: k + bk, fp32, transposed 32 x 32 tiles into [B, T, 512]
+        wait_tf(1);
+#pragma unroll 1
+        for (int c = 0; c < p.nch; ++c) {
+          float v[32];
+          tmem_ld_32x32(trow + (uint32_t)(256 + c * 32), v);
+          tmem_ld_wait();
+          drain();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float o = v[j] + prm[3 * Tq + c * 32 + j];
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg_k + (uint32_t)(j * 32 + lane) * 4u), "f"(o) : "memory");
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tm.k32, stg_k, n0 + quad * 32, c * 32, b);
+            tma_commit();
+          }
+          pending = true;
+        }
+        tc_fence_before();
+      }
+      // ---- E_v: v + bv, fp16, transposed 32 x 32 tiles into [B, T, 512]; chunks split between the quadrant's two warps
+      wait_tf(0);
+#pragma unroll 1
+      for (int c = (part == 0 ? 0 : c_split); c < (part == 0 ? c_split : p.nch); ++c) {
+        float v[32];
+        tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        drain();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint16_t o = f32_to_f16_bits(v[j] + prm[4 * Tq + c * 32 + j]);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg_mine + (uint32_t)(j * 32 + lane) * 2u), "h"(o) : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tm.v16, stg_mine, n0 + quad * 32, c * 32, b);
+          tma_commit();
+        }
+        pending = true;
+      }
+      tc_fence_before();
+    }
+    if (lane == 0) tma_wait_all0();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+
 std::atomic<unsigned long long> g_fb_launches{0};
 int g_fb_max_pairs = -1;
 unsigned long long* g_fb_prof = nullptr;
@@ -1233,7 +1580,7 @@ int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
   const int n_pairs = std::min(p.n_tiles, max_pairs);
   const double flops = 2.0 * (double)a.batch * D * ((double)T * (T / 4) + (double)T * T);   // q ctx (per head) + out
   {
-    LaunchTimer lt(LK_FUSED, stream, flops);
+    LaunchTimer lt(LK_GEMM, stream, flops);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_pairs);
     cfg.blockDim = dim3(THREADS);
@@ -1246,6 +1593,62 @@ int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_tail_kernel, tm, p));
+  }
+  MCM_CUDA(cudaGetLastError());
+  g_fb_launches.fetch_add(1);
+  return 0;
+}
+
+// generic [d0 contiguous, d1, d2] tensor map with an explicit box (the E_q row store: box {Tp, 32, 1}, no swizzle)
+int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream) {
+  MCM_TRY(fb_init());
+  MCM_CHECK(a.h && a.w.hi && a.qs.hi && a.k32 && a.v16.hi && a.batch > 0 && sa_tail_supported(a.T, D), "sa front: bad arguments");
+  static int max_pairs = -1;
+  if (max_pairs < 0) {
+    MCM_CUDA(cudaFuncSetAttribute(sa_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    cudaLaunchConfig_t oc = {};
+    oc.gridDim = dim3(tc_num_sms() / 2 * 2);
+    oc.blockDim = dim3(THREADS);
+    oc.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute oa[1];
+    oa[0].id = cudaLaunchAttributeClusterDimension;
+    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+    oc.attrs = oa; oc.numAttrs = 1;
+    int n = 0;
+    MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, sa_front_kernel, &oc));
+    MCM_CHECK(n > 0, "sa_front_kernel does not fit on this device");
+    max_pairs = n;
+  }
+  const int T = a.T, Tp = a.w.ld;
+  const int Np = (T + 15) / 16 * 16;
+  MCM_CHECK(a.qs.ld == Tp && Tp % 8 == 0 && Tp >= T && a.v16.ld == D && a.heads == H && T % H == 0 && 32 * Tp * 2 <= SLAB,
+            "sa front: operand layout");
+  SfMaps tm;
+  std::memset(&tm, 0, sizeof(tm));
+  MCM_TRY(tc_make_operand_map(&tm.w, a.w.hi, OP_F16, Tp, 3 * T, 1, Tp, Np / 2));
+  MCM_TRY(tc_make_box_map(&tm.qs, a.qs.hi, 1, Tp, (long long)a.batch * D, 1, Tp, (long long)a.batch * D * Tp, Tp, 32));
+  MCM_TRY(tc_make_tile_map(&tm.k32, a.k32, 0, D, T, a.batch, D, (long long)T * D, 0));
+  MCM_TRY(tc_make_tile_map(&tm.v16, a.v16.hi, 1, D, T, a.batch, D, (long long)T * D, 0));
+  SfParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.h = a.h; p.T = T; p.Tp = Tp; p.Np = Np; p.nkb = (T + 63) / 64; p.nch = (T + 31) / 32; p.hd = T / H; p.batch = a.batch;
+  p.n_tiles = a.batch * 2; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.bqkv = a.bqkv;
+  const int n_pairs = std::min(p.n_tiles, max_pairs);
+  const double flops = 2.0 * (double)a.batch * D * (double)T * 3.0 * T;
+  {
+    LaunchTimer lt(LK_GEMM, stream, flops);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_front_kernel, tm, p));
   }
   MCM_CUDA(cudaGetLastError());
   g_fb_launches.fetch_add(1);

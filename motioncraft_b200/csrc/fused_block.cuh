@@ -50,6 +50,20 @@ struct SaTailArgs {
 bool sa_tail_supported(int T, int D);
 int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream);
 
+// The head of the channel attention (LN_T(h^T) -> q | k | v -> per-head softmax(q); k, v written back transposed) as one
+// persistent kernel; see sa_front_kernel in fused_block.cu.  Same shape support as the tail (sa_tail_supported).
+struct SaFrontArgs {
+  const float* h;       // [B, T, 512] fp32 residual stream (read only)
+  int T, batch, heads;
+  const float *ln_w, *ln_b;   // sa_block.norm over T
+  OpPtr w;              // [3T, Tp] fp16 query | key | value weights
+  const float* bqkv;    // [3T]
+  OpPtr qs;             // out: [B*512, Tp] fp16 softmax(q) operand
+  float* k32;           // out: [B, T, 512] fp32 key (input of the token softmax)
+  OpPtr v16;            // out: [B, T, 512] fp16 value operand
+};
+int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream);
+
 // true if the fused kernel covers this architecture (latent 512, ffn 1024, 4 heads, T >= 52)
 bool fused_block_supported(int T, int D, int F, int H);
 size_t fused_block_hid_bytes();

@@ -868,6 +868,23 @@ int tc_make_tile_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, l
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
   return make_epi_map(m, ptr, dt, dtype == 0 ? 4 : 2, d0, d1, d2, stride1_elems, stride2_elems, sw);
 }
+int tc_make_box_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
+                    long long stride1_elems, long long stride2_elems, int box0, int box1) {
+  MCM_TRY(gemm_tc_init());
+  const int esize = dtype == 0 ? 4 : 2;
+  cuuint64_t gdim[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t gstr[2] = {(cuuint64_t)stride1_elems * esize, (cuuint64_t)stride2_elems * esize};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                        const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (box map) failed with CUresult " + std::to_string((int)r));
+    return 1;
+  }
+  return 0;
+}
 int tc_num_sms() { return gemm_tc_init() == 0 ? g_num_sms : 0; }
 
 int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {

@@ -69,6 +69,9 @@ int gemm_tc_init();
 int tc_make_operand_map(CUtensorMap* m, const void* ptr, int fmt, int k_dim, int rows, int batches, int ld, int box_rows);
 int tc_make_tile_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
                      long long stride1_elems, long long stride2_elems, int swizzle_bytes);
+//   box map:     like the tile map but with an explicit {box0, box1, 1} box and no swizzle (row-staged stores)
+int tc_make_box_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
+                    long long stride1_elems, long long stride2_elems, int box0, int box1);
 int tc_num_sms();
 
 // number of tcgen05 GEMM launches since process start (bench.py's gpu_launches evidence)

@@ -67,11 +67,13 @@ def test_fused_matches_unfused_on_ragged_tiles(T, B):
     eng.set_option("fused", 0)
     unfused = eng.block_forward(0, 0, h0, emb)
     eng.set_option("fused", 1)
-    fused = eng.block_forward(0, 0, h0, emb)
     assert C.rel_l2(unfused, want) < TOL
-    assert C.rel_l2(fused, want) < TOL
-    assert C.rel_l2(fused, unfused) < 5e-4
-    assert torch.isfinite(fused).all()
+    for sa_level in (0, 1, 2):      # channel attention: separate kernels / fused tail / fused head and tail
+        eng.set_option("fused_sa", sa_level)
+        fused = eng.block_forward(0, 0, h0, emb)
+        assert C.rel_l2(fused, want) < TOL, sa_level
+        assert C.rel_l2(fused, unfused) < 5e-4, sa_level
+        assert torch.isfinite(fused).all()
     eng.close()
 
 

@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
 # Developer aid (GPU box): bench.py under a few scheduling variants; prints value / ms per run / e2e.
 cd "$(dirname "$0")/.."
-for v in "MCM_DUAL=0" "MCM_DUAL=1" "MCM_FUSED=0 MCM_DUAL=1"; do
+IFS=";" read -ra VS <<< "${VARIANTS:-MCM_DUAL=0;MCM_DUAL=1;MCM_FUSED=0}"
+for v in "${VS[@]}"; do
   env $v python bench.py --steps 3 --warmup 3 > /tmp/bv.json 2> /tmp/bv.err || { echo "$v FAILED"; tail -3 /tmp/bv.err; continue; }
   python - "$v" <<'PY'
 import json, sys

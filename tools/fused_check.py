@@ -67,10 +67,10 @@ def main():
     eng.set_option("fused_stop", 0)
     out = eng.block_forward(0, 0, h0, emb)
     print(f"fused block vs fp64: {rel(out, h_out):.3e}   vs unfused: {rel(out, ref_block):.3e}", flush=True)
-    eng.set_option("fused_sa", 0)
-    out_nosa = eng.block_forward(0, 0, h0, emb)
-    eng.set_option("fused_sa", 1)
-    print(f"fused CA/FFN with unfused SA tail vs fp64: {rel(out_nosa, h_out):.3e}", flush=True)
+    for lvl in (0, 1, 2):
+        eng.set_option("fused_sa", lvl)
+        o = eng.block_forward(0, 0, h0, emb)
+        print(f"fused CA/FFN, channel-attention fusion level {lvl} vs fp64: {rel(o, h_out):.3e}", flush=True)
     out2 = eng.block_forward(0, 0, h0, emb)
     print("fused deterministic:", torch.equal(out, out2), flush=True)
     eng.close()
