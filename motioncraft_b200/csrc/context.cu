@@ -62,8 +62,7 @@ struct mcm_ctx {
   mcm_config cfg;
   int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
   int fused = 1;          // MCM_FUSED=0: run cross-attention + FFN as separate GEMM / row kernels (the round-1 path)
-  int fused_sa = 1;       // MCM_FUSED_SA: 0 = channel attention as separate kernels, 1 = fused tail (default),
-                          // 2 = fused head and tail (correct, but its head kernel is still slower than the kernels it replaces)
+  int fused_sa = 2;       // MCM_FUSED_SA: 0 = channel attention as separate kernels, 1 = fused tail, 2 = fused head and tail
   int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
   void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK

@@ -65,6 +65,7 @@ struct FbMaps {
 struct FbParams {
   const float* h;
   int rows, T, batch, n_tiles, mod_ld, stop;
+  int stagger;          // clock cycles by which the pairs that get one tile fewer start late (de-synchronises the phases)
   const float *ca_ln_w, *ca_ln_b, *ca_bq, *ca_pn_w, *ca_pn_b, *ca_scale, *ca_shift, *ca_bo;
   const float *f_b1, *f_b2, *f_pn_w, *f_pn_b, *f_scale, *f_shift, *f_bo;
   uint16_t* dbg;
@@ -88,6 +89,19 @@ __device__ __forceinline__ float silu_fast(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + ex2_fast(-x * L2E)));
   return x * r;
+}
+// erf-GELU as relu(x) - 0.5 |x| erfc(|x| / sqrt 2) with the Abramowitz-Stegun 7.1.26 erfc (|abs err| < 5e-7, far below
+// the fp16 rounding of the result): 13 FP32 ops + 2 MUFU, no select
+__device__ __forceinline__ float gelu_relu_erfc(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float e = ex2_fast(ax * ax * (-0.5f * L2E));
+  return fmaf(-0.5f * ax, poly * t * e, fmaxf(x, 0.f));
 }
 // shared-memory address of the 16-byte chunk holding columns [col, col + 8) of row `row` of the operand tile
 __device__ __forceinline__ uint32_t opa_addr(uint32_t opa, int row, int col) {
@@ -239,23 +253,37 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
                                           float inv0, float inv1) {
   float K = 0.f, sd = 0.f, sq = 0.f;
   float bcur = BIAS ? __ldg(bias + part * CPW + lane) : 0.f;
+  float bcur2 = BIAS ? __ldg(bias + part * CPW + 32 + lane) : 0.f;
+  float sd2 = 0.f, sq2 = 0.f;                 // second accumulator chain (tile pairs: two TMEM loads in flight)
 #pragma unroll 1
-  for (int c = 0; c < NCH; ++c) {
-    float v[32];
+  for (int c = 0; c < NCH; c += 2) {
+    float v[32], w[32];
     tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
-    const float bnxt = BIAS ? __ldg(bias + part * CPW + ((c + 1) & (NCH - 1)) * 32 + lane) : 0.f;
+    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32 + 32), w);
+    const int cn = (c + 2) & (NCH - 1);
+    const float bnxt = BIAS ? __ldg(bias + part * CPW + cn * 32 + lane) : 0.f;
+    const float bnxt2 = BIAS ? __ldg(bias + part * CPW + cn * 32 + 32 + lane) : 0.f;
     tmem_ld_wait();
-    if (BIAS) add_bias32(bslot, lane, bcur, v);
-    bcur = bnxt;
-    const float sc = SCALE ? ((c >> 2) ? inv1 : inv0) : 1.f;
+    if (BIAS) {
+      add_bias32(bslot, lane, bcur, v);
+      add_bias32(bslot, lane, bcur2, w);
+    }
+    bcur = bnxt; bcur2 = bnxt2;
+    const float sc = SCALE ? ((c >> 2) ? inv1 : inv0) : 1.f;     // a pair of tiles never straddles a head (128 columns)
     if (c == 0) K = v[0] * sc;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float d = SCALE ? fmaf(v[j], sc, -K) : v[j] - K;
+      const float d2 = SCALE ? fmaf(w[j], sc, -K) : w[j] - K;
       sd += d;
       sq = fmaf(d, d, sq);
+      sd2 += d2;
+      sq2 = fmaf(d2, d2, sq2);
     }
   }
+  sd += sd2;
+  sq += sq2;
+  bcur = BIAS ? __ldg(bias + part * CPW + lane) : 0.f;
   const float mean_w = fmaf(sd, 1.f / (float)CPW, K);
   const float m2_w = fmaf(-sd * (1.f / (float)CPW), sd, sq);
   xch[(ew * 32 + lane) * 2] = mean_w;
@@ -315,27 +343,35 @@ __device__ __forceinline__ void tma_wait_read3() { asm volatile("cp.async.bulk.w
 // reduction issued 4 tiles earlier to have read its slot.
 __device__ __forceinline__ void epi_reduce_h(uint32_t trow, int part, uint32_t stg4, const CUtensorMap* map, int grow0,
                                              float* bslot, int lane, const float* __restrict__ bias, bool& pending) {
-  float bcur = __ldg(bias + part * CPW + lane);
+  // two 32-column tiles per iteration: both TMEM loads are in flight together and one bulk group carries both reductions
+  static_assert(NCH % 2 == 0 && RED_SLOTS % 2 == 0, "tile pairs");
+  float b0 = __ldg(bias + part * CPW + lane), b1 = __ldg(bias + part * CPW + 32 + lane);
 #pragma unroll 1
-  for (int c = 0; c < NCH; ++c) {
-    float v[32];
+  for (int c = 0; c < NCH; c += 2) {
+    float v[32], w[32];
     tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
-    const float bnxt = __ldg(bias + part * CPW + ((c + 1) & (NCH - 1)) * 32 + lane);
+    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32 + 32), w);
+    const int cn = (c + 2) & (NCH - 1);
+    const float n0 = __ldg(bias + part * CPW + cn * 32 + lane), n1 = __ldg(bias + part * CPW + cn * 32 + 32 + lane);
     tmem_ld_wait();
-    add_bias32(bslot, lane, bcur, v);
-    bcur = bnxt;
-    const uint32_t stgw = stg4 + (uint32_t)(c & (RED_SLOTS - 1)) * 4096u;
+    add_bias32(bslot, lane, b0, v);
+    add_bias32(bslot, lane, b1, w);
+    b0 = n0; b1 = n1;
+    const uint32_t sa = stg4 + (uint32_t)(c & (RED_SLOTS - 1)) * 4096u, sb = sa + 4096u;
     if (c >= RED_SLOTS) {
-      if (lane == 0) { if (RED_SLOTS == 4) tma_wait_read3(); else tma_wait_read1(); }
+      if (lane == 0) { if (RED_SLOTS == 4) tma_wait_read1(); else tma_wait_read0(); }
       __syncwarp();
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      st_shared_v4(stgw + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 8; ++q) {
+      st_shared_v4(sa + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      st_shared_v4(sb + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    }
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_reduce_add_3d(map, stgw, part * CPW + c * 32, grow0, 0);
+      tma_reduce_add_3d(map, sa, part * CPW + c * 32, grow0, 0);
+      tma_reduce_add_3d(map, sb, part * CPW + c * 32 + 32, grow0, 0);
       tma_commit();
     }
     pending = true;
@@ -365,6 +401,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
   __shared__ __align__(8) uint64_t hid_bar;
   __shared__ __align__(8) uint64_t afull_bar[8];    // G5: hidden (A) slabs stream through the idle operand tile
   __shared__ __align__(8) uint64_t aempty_bar[8];
+  __shared__ __align__(16) float bias4_s[NCW == 8 ? NCW : 1][32];   // E4's bias broadcast slots (the staging region is full then)
   __shared__ uint32_t tmem_slot;
 
   pdl_trigger();
@@ -410,6 +447,13 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem_base = tmem_slot;
+  // All pairs run the same phase program on same-sized tiles, so they hit the chip-level resources (L2 -> SM weight
+  // stream in the MMA phases, L2 reductions in E3 / E6, h reads in the P phases) in lock-step.  Pairs that own one tile
+  // fewer than the others have a whole tile time of slack: they start late, which shifts their phases for free.
+  if (p.stagger > 0 && p.n_tiles > n_clusters && cluster_id >= p.n_tiles % n_clusters && p.n_tiles % n_clusters != 0 && warp != 1) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)p.stagger) __nanosleep(2000);
+  }
 
   if (warp == 0) {
     // ================================================================== TMA producer (both CTAs)
@@ -715,9 +759,15 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           const int nidx = (idx + 1) % (4 * QCH);
           const float bnxt = __ldg(p.f_b1 + (nidx / QCH) * 256 + part * QW + (nidx % QCH) * 32 + lane);
           tmem_ld_wait();
-          // the staging region belongs to the hidden-tile stores in this phase: bias is broadcast by shuffles
+          // the staging region belongs to the hidden-tile stores in this phase: bias goes through a static slot
+          if (NCW == 8) {
+            add_bias32(bias4_s[NCW == 8 ? ew : 0], lane, bcur, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j] + __shfl_sync(0xffffffffu, bcur, j));
+            for (int j = 0; j < 32; ++j) v[j] = gelu_relu_erfc(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_relu_erfc(v[j] + __shfl_sync(0xffffffffu, bcur, j));
+          }
           bcur = bnxt;
           const uint32_t sl = stgw + (uint32_t)(idx & (E4_SLOTS - 1)) * 2048u;
           if (idx >= E4_SLOTS) {
@@ -1112,6 +1162,7 @@ struct SfParams {
   const float* h;
   int T, Tp, Np, nkb, nch, hd, batch, n_tiles;
   const float *ln_w, *ln_b, *bqkv;
+  unsigned long long* prof;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -1146,7 +1197,7 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
       mbar_init(smem_u32(&tfull_bar[0]), 1);
       mbar_init(smem_u32(&tfull_bar[1]), 1);
       mbar_init(smem_u32(&pa_bar), 2u * NCW);
-      mbar_init(smem_u32(&qd_bar), NCW);
+      mbar_init(smem_u32(&qd_bar), 2u * NCW);
       fence_mbar_init();
     }
     __syncwarp();
@@ -1230,6 +1281,7 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
     const int Tq = p.nch * 32;
     float* const prm = reinterpret_cast<float*>(stg_gen);             // ln_w | ln_b | bq | bk | bv, Tq floats each (<= 5 KB)
     float* const xch = reinterpret_cast<float*>(stg_gen + 6144);      // [NCW][32][2]
+    float* const bslot = reinterpret_cast<float*>(stg_gen + 5120) + ew * 32;   // per-warp bias broadcast slot
     // staging: E_q rows (32 x Tp fp16 <= 16 KB) / E_v tiles of warps 0..3 in operand-tile slabs 4..7; E_k / E_v tiles of
     // warps 4..7 in the staging region
     const uint32_t stg_q = opa + 4u * SLAB + (uint32_t)(ew & 3) * SLAB;
@@ -1261,6 +1313,12 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
       prm[4 * Tq + t] = ok ? __ldg(p.bqkv + 2 * p.T + t) : 0.f;
     }
     bar_sync(5, NCW * 32);
+    long long tph[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tph[i] = 0;
+    const bool prof = p.prof != nullptr;
+    long long tlast = prof ? clock64() : 0;
+#define SF_TICK(i) do { if (prof) { const long long _n = clock64(); tph[i] += _n - tlast; tlast = _n; } } while (0)
     const int T2 = ((p.T + 1) / 2 + 7) / 8 * 8;               // frames [0, T2) to warps 0..3, [T2, T) to warps 4..7
     const int t_lo = part * T2, t_hi = part == 0 ? T2 : p.T;
     const int t_end = part == 0 ? T2 : p.nkb * 64;            // warps 4..7 also write the zero K padding
@@ -1285,6 +1343,7 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
             sq = fmaf(d, d, sq);
           }
         }
+        SF_TICK(0);
         const float n_mine = (float)(t_hi - t_lo), n_o = (float)p.T - n_mine;
         const float mean_w = K + sd / n_mine;
         const float m2_w = sq - sd * sd / n_mine;
@@ -1321,70 +1380,85 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(smem_u32(&pa_bar), 0u);
+        {
+          // pull the next tile's [T x 128 channels] slab of h into L2 (one 512-byte row segment per thread)
+          const int nt = tile + n_clusters;
+          if (nt < p.n_tiles) {
+            const float* nsrc = p.h + ((size_t)(nt >> 1) * p.T) * D + (nt & 1) * 2 * ROWS + rank * ROWS;
+            for (int t = ctid; t < p.T; t += NCW * 32)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + (size_t)t * D) : "memory");
+          }
+        }
+        SF_TICK(1);
       }
       wait_tf(0);                                             // q complete
-      if (part == 0) {
-        // ---- E_q: per-head softmax of q + bq (three passes over the head's chunks), rows staged as [32][Tp] fp16
-        drain();
+      SF_TICK(2);
+      {
+        // ---- E_q: per-head softmax of q + bq.  The quadrant's two warps take two heads each; a head's T/H columns are
+        // read as ceil(hd/32) chunks ALIGNED TO THE HEAD START (TMEM columns are addressable one by one), so only a
+        // per-chunk valid count masks elements.  Pass 1: online max / sum; pass 2: normalised fp16 into the row staging.
+        if (part == 0) drain();                                // the staging rows may still be read by this warp's last store
+        bar_sync(1 + quad, 64);
 #pragma unroll 1
-        for (int hh = 0; hh < H; ++hh) {
-          const int lo = hh * p.hd, hi = lo + p.hd;
-          const int c0 = lo >> 5, c1 = (hi - 1) >> 5;
-          float m = -INFINITY;
+        for (int hh = 2 * part; hh < 2 * part + 2; ++hh) {
+          const int lo = hh * p.hd;
+          const int nc = (p.hd + 31) >> 5;
+          float m = -INFINITY, ssum = 0.f;
 #pragma unroll 1
-          for (int c = c0; c <= c1; ++c) {
+          for (int c = 0; c < nc; ++c) {
             float v[32];
-            tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_32x32(trow + (uint32_t)(lo + c * 32), v);
+            const int nv = min(32, p.hd - c * 32);
+            const float bmine = lane < nv ? prm[2 * Tq + lo + c * 32 + lane] : 0.f;
             tmem_ld_wait();
+            add_bias32(bslot, lane, bmine, v);
+            float cm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = c * 32 + j;
-              if (col >= lo && col < hi) m = fmaxf(m, v[j] + prm[2 * Tq + col]);
-            }
+            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < nv ? v[j] : -INFINITY);
+            const float mn = fmaxf(m, cm);
+            const float mnl = mn * L2E;
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs += j < nv ? ex2_fast(fmaf(v[j], L2E, -mnl)) : 0.f;
+            ssum = ssum * ex2_fast((m - mn) * L2E) + cs;      // exp(-inf) = 0 on the first chunk
+            m = mn;
           }
           const float ml = m * L2E;
-          float ssum = 0.f;
-#pragma unroll 1
-          for (int c = c0; c <= c1; ++c) {
-            float v[32];
-            tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = c * 32 + j;
-              if (col >= lo && col < hi) ssum += ex2_fast(fmaf(v[j] + prm[2 * Tq + col], L2E, -ml));
-            }
-          }
           const float inv = 1.f / ssum;
 #pragma unroll 1
-          for (int c = c0; c <= c1; ++c) {
+          for (int c = 0; c < nc; ++c) {
             float v[32];
-            tmem_ld_32x32(trow + (uint32_t)(c * 32), v);
+            tmem_ld_32x32(trow + (uint32_t)(lo + c * 32), v);
+            const int nv = min(32, p.hd - c * 32);
+            const float bmine = lane < nv ? prm[2 * Tq + lo + c * 32 + lane] : 0.f;
             tmem_ld_wait();
+            add_bias32(bslot, lane, bmine, v);
+            uint16_t* dst = stg_q_gen + lane * p.Tp + lo + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = c * 32 + j;
-              if (col >= lo && col < hi)
-                stg_q_gen[lane * p.Tp + col] = f32_to_f16_bits(ex2_fast(fmaf(v[j] + prm[2 * Tq + col], L2E, -ml)) * inv);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) dst[j] = f32_to_f16_bits(ex2_fast(fmaf(v[j], L2E, -ml)) * inv);
           }
         }
-        for (int col = p.T; col < p.Tp; ++col) stg_q_gen[lane * p.Tp + col] = 0;   // operand pad columns
+        if (part == 1)
+          for (int col = p.T; col < p.Tp; ++col) stg_q_gen[lane * p.Tp + col] = 0;   // operand pad columns
         fence_async_smem();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_remote(smem_u32(&qd_bar), 0u);
-          tma_store_3d(&tm.qs, stg_q, 0, b * D + n0 + quad * 32, 0);
-          tma_commit();
+        bar_sync(1 + quad, 64);                               // both warps' halves of the 32 staged rows are written
+        if (lane == 0) mbar_arrive_remote(smem_u32(&qd_bar), 0u);
+        if (part == 0) {
+          if (lane == 0) {
+            tma_store_3d(&tm.qs, stg_q, 0, b * D + n0 + quad * 32, 0);
+            tma_commit();
+          }
+          pending = true;
         }
-        pending = true;
-        wait_tf(1);                                           // (k is handled by warps 4..7; keep the phase count in step)
-      } else {
-        // ---- E_k: k + bk, fp32, transposed 32 x 32 tiles into [B, T, 512]
+        SF_TICK(3);
+      }
+      {
+        // ---- E_k: k + bk, fp32, transposed 32 x 32 tiles into [B, T, 512]; chunks split between the quadrant's two warps
         wait_tf(1);
 #pragma unroll 1
-        for (int c = 0; c < p.nch; ++c) {
+        for (int c = (part == 0 ? 0 : c_split); c < (part == 0 ? c_split : p.nch); ++c) {
           float v[32];
           tmem_ld_32x32(trow + (uint32_t)(256 + c * 32), v);
           tmem_ld_wait();
@@ -1392,20 +1466,22 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float o = v[j] + prm[3 * Tq + c * 32 + j];
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg_k + (uint32_t)(j * 32 + lane) * 4u), "f"(o) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg_mine + (uint32_t)(j * 32 + lane) * 4u), "f"(o) : "memory");
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tm.k32, stg_k, n0 + quad * 32, c * 32, b);
+            tma_store_3d(&tm.k32, stg_mine, n0 + quad * 32, c * 32, b);
             tma_commit();
           }
           pending = true;
         }
         tc_fence_before();
+        SF_TICK(4);
       }
       // ---- E_v: v + bv, fp16, transposed 32 x 32 tiles into [B, T, 512]; chunks split between the quadrant's two warps
       wait_tf(0);
+      SF_TICK(5);
 #pragma unroll 1
       for (int c = (part == 0 ? 0 : c_split); c < (part == 0 ? c_split : p.nch); ++c) {
         float v[32];
@@ -1426,9 +1502,15 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
         pending = true;
       }
       tc_fence_before();
+      SF_TICK(6);
     }
     if (lane == 0) tma_wait_all0();
     __syncwarp();
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(p.prof + 8 * part + i, (unsigned long long)tph[i]);
+    }
+#undef SF_TICK
   }
 
   tc_fence_before();
@@ -1519,7 +1601,9 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
   p.f_b1 = a.f_b1; p.f_b2 = a.f_b2; p.f_pn_w = a.f_pn_w; p.f_pn_b = a.f_pn_b; p.f_scale = a.f_scale; p.f_shift = a.f_shift;
   p.f_bo = a.f_bo;
   p.dbg = reinterpret_cast<uint16_t*>(a.dbg);
-  p.prof = g_fb_prof;
+  static const int stagger = [] { const char* e = getenv("MCM_FB_STAGGER"); return e ? atoi(e) : 0; }();
+  p.stagger = stagger;
+  p.prof = getenv("MCM_SF_PROF") != nullptr ? nullptr : g_fb_prof;
 
   // algorithmic flops of the two sub-blocks (AdaLN emb GEMM is not in this kernel)
   const double flops = 2.0 * (double)a.rows * ((double)D * D * 2 + (double)D * HD + 2.0 * D * F + (double)D * D);
@@ -1633,6 +1717,7 @@ int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream) {
   std::memset(&p, 0, sizeof(p));
   p.h = a.h; p.T = T; p.Tp = Tp; p.Np = Np; p.nkb = (T + 63) / 64; p.nch = (T + 31) / 32; p.hd = T / H; p.batch = a.batch;
   p.n_tiles = a.batch * 2; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.bqkv = a.bqkv;
+  p.prof = (g_fb_prof != nullptr && getenv("MCM_SF_PROF") != nullptr) ? g_fb_prof : nullptr;
   const int n_pairs = std::min(p.n_tiles, max_pairs);
   const double flops = 2.0 * (double)a.batch * D * (double)T * 3.0 * T;
   {

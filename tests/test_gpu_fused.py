@@ -105,3 +105,43 @@ def test_fused_benchmark_shape_batch_vs_oracle_sample():
         want = C.block_stages(sd, h0[b:b + 1], emb[b:b + 1], xf_out[b:b + 1])["out"]
         assert C.rel_l2(fused[b:b + 1], want) < TOL, b
     eng.close()
+
+
+@pytest.mark.parametrize("T,B", [(196, 3), (256, 2), (64, 4), (40, 3), (300, 2)])
+def test_channel_attention_fusion_levels(T, B):
+    """sa_front_kernel / sa_tail_kernel against the kernel-per-op channel attention and float64, incl. the largest
+    supported T (256: four full K blocks), heads of 10 / 16 / 49 / 64 features, and T = 300 where the fused kernels do not
+    apply and the library must fall back to the unfused sequence by itself."""
+    sd, h0, emb, xf_out, eng = _setup(T, B)
+    want = C.block_stages(sd, h0, emb, xf_out)["out"]
+    outs = {}
+    for lvl in (0, 1, 2):
+        eng.set_option("fused_sa", lvl)
+        outs[lvl] = eng.block_forward(0, 0, h0, emb)
+        assert C.rel_l2(outs[lvl], want) < TOL, lvl
+        assert torch.equal(outs[lvl], eng.block_forward(0, 0, h0, emb)), "deterministic"
+    assert C.rel_l2(outs[1], outs[0]) < 5e-4 and C.rel_l2(outs[2], outs[0]) < 5e-4
+    eng.close()
+
+
+def test_control_branch_fused_vs_unfused_vs_oracle():
+    """ControlT2MHalf_MCM: the copied blocks run through the same fused kernels on the control stream (a different h
+    buffer and modulation slice per block); fused and kernel-per-op schedules against the fp32 oracle."""
+    from motioncraft_b200 import modules
+    T, B, n_ctrl, c_feats = 196, 3, 2, 35
+    sd = synth.synth_state_dict(modules.ctrl_state_shapes(T, n_ctrl, c_feats))
+    x, xf_out, xf_proj = C.inputs(B, T)
+    c = synth.synth_tensor("c", (B, T, c_feats), synth.SEED_C_EMB)
+    t = torch.full((B,), 640, dtype=torch.long)
+    with torch.no_grad():
+        want = O.control_forward(sd, x, t, xf_proj, xf_out, c)
+    eng = DenoiserEngine(modules.engine_state_from_ctrl(sd), seq_len=T, max_batch=B, num_ctrl_blocks=n_ctrl,
+                         ctrl_cond_feats=c_feats)
+    eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda(), c.cuda())
+    outs = []
+    for fused in (1, 0):
+        eng.set_option("fused", fused)
+        outs.append(eng.denoise(x.cuda(), 640))
+        assert C.rel_l2(outs[-1], want) < TOL, fused
+    assert C.rel_l2(outs[0], outs[1]) < 5e-4
+    eng.close()

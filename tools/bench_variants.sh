@@ -9,7 +9,7 @@ import json, sys
 d = json.loads(open('/tmp/bv.json').read().strip().splitlines()[-1])
 r = d["roofline"]
 print(sys.argv[1], "| frames/s", round(d["value"]), "| ms/run", round(d["ms_per_step"], 1), "| e2e", round(d["e2e"]["value"]),
-      "| gemm ms", round(r["gemm_ms_per_run"], 1), "row ms", round(r["row_kernel_ms_per_run"], 1), "| frac", round(r["frac"], 3),
+      "| tcgen05 ms", round(r["all_tcgen05_kernels_ms_per_run"], 1), "row ms", round(r["row_kernel_ms_per_run"], 1), "| frac", round(r["frac"], 3),
       "| clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 PY
 done

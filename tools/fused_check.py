@@ -71,6 +71,8 @@ def main():
         eng.set_option("fused_sa", lvl)
         o = eng.block_forward(0, 0, h0, emb)
         print(f"fused CA/FFN, channel-attention fusion level {lvl} vs fp64: {rel(o, h_out):.3e}", flush=True)
+    eng.set_option("fused_sa", 1)
+    out = eng.block_forward(0, 0, h0, emb)
     out2 = eng.block_forward(0, 0, h0, emb)
     print("fused deterministic:", torch.equal(out, out2), flush=True)
     eng.close()
