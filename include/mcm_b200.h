@@ -113,6 +113,29 @@ int mcm_sample(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* x_T, 
 int mcm_sample_host(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* x_T_host,
                     const float* step_noise_host, float* x0_out_host, void* stream);
 
+/* RePaint / outpainting description for mcm_sample_repaint (the long-form generation of tools/m2d_test.py:176-195 and
+ * tools/s2g_test.py with --repaint: the first frames of a window are pinned to the tail of the previous window). */
+typedef struct mcm_repaint {
+  int n_times;                      /* length of `times`, or 0 = plain loop over all steps (opt.no_repaint)                */
+  const int* times;                 /* host: get_schedule_jump_cjm_ddim (mogen/models/utils/scheduler.py:178-208), ends -1 */
+  const float* betas;               /* host [n_steps]: respaced betas, float32 cast (undo, gaussian_diffusion.py:426-435)  */
+  const float* gt;                  /* device [B,T,F]: y['gt']                                                              */
+  const unsigned char* keep_mask;   /* device [B,T,F]: y['outpainting_mask'], 1 = keep the (noised) ground truth            */
+  const float* noise_seq;           /* device [n_draws,B,T,F]: the reference's torch.randn_like draws IN ORDER -- two per
+                                     * denoise call (the eta noise of :847, unused at eta = 0, then the blend noise of
+                                     * :867), one per undo                                                                  */
+  long long n_draws;
+  int overlap_len;                  /* opt.overlap_len                                                                      */
+  int add_blend;                    /* opt.addBlend                                                                         */
+  const float* blend_w;             /* device [overlap_len]: torch.linspace(0, 1, overlap_len) (:873), or NULL              */
+} mcm_repaint;
+
+/* replaces: SpacedDiffusion.ddim_sample_loop with y['outpainting_mask'] set (gaussian_diffusion.py:925-997): the
+ * harmonising loop ddim_sample_loop_progressive_harmonize (:1050-1118) -- denoise / undo along `times` -- or the plain
+ * loop, with the mask blend of ddim_sample (:855-879) after every DDIM update.  eta = 0, same_overlap_noisy = False. */
+int mcm_sample_repaint(mcm_ctx* ctx, const mcm_sampler* s, const mcm_repaint* r, int batch, const float* x_T,
+                       float* x0_out, void* stream);
+
 /* Raw tensor-core GEMM, exposed for unit tests of the kernel itself:
  *   C[M,N] (fp32) = A[M,K] * W[N,K]^T + bias[N]   with A, W fp32 device tensors quantised to
  *   fmt 0 = fp16 (1 pass) or 1 = bf16 hi/lo (3 passes). */

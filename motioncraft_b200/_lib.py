@@ -34,6 +34,12 @@ class McmSampler(ctypes.Structure):
                 ("posterior_log_variance_clipped", _FP)]
 
 
+class McmRepaint(ctypes.Structure):
+    _fields_ = [("n_times", ctypes.c_int), ("times", _IP), ("betas", _FP), ("gt", ctypes.c_void_p),
+                ("keep_mask", ctypes.c_void_p), ("noise_seq", ctypes.c_void_p), ("n_draws", ctypes.c_longlong),
+                ("overlap_len", ctypes.c_int), ("add_blend", ctypes.c_int), ("blend_w", ctypes.c_void_p)]
+
+
 # name -> (restype, argtypes); exactly the symbols include/mcm_b200.h declares
 _VP, _I, _LL = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
 SIGNATURES = {
@@ -47,6 +53,7 @@ SIGNATURES = {
     "mcm_block_forward": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
     "mcm_sample": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
     "mcm_sample_host": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
+    "mcm_sample_repaint": (_I, [_VP, ctypes.POINTER(McmSampler), ctypes.POINTER(McmRepaint), _I, _VP, _VP, _VP]),
     "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
     "mcm_timing_enable": (None, [_I]),
     "mcm_timing_collect": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong),

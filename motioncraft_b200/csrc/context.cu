@@ -952,6 +952,56 @@ int mcm_sample(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T, const 
   return run_sampler(c, s, B, step_noise, x0_out, st);
 }
 
+int mcm_sample_repaint(mcm_ctx* c, const mcm_sampler* s, const mcm_repaint* r, int B, const float* x_T, float* x0_out,
+                       void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_TRY(check_sampler(s, nullptr));
+  MCM_CHECK(s->mode == 0 && s->eta == 0.f, "mcm_sample_repaint: DDIM with eta = 0 only (what MotionDiffusion passes)");
+  MCM_CHECK(r != nullptr && x_T && x0_out && r->gt && r->keep_mask && r->noise_seq, "mcm_sample_repaint: null argument");
+  MCM_CHECK(r->n_times == 0 || (r->times != nullptr && r->betas != nullptr), "mcm_sample_repaint: schedule without times / betas");
+  MCM_CHECK(r->overlap_len >= 0 && r->overlap_len <= c->T, "mcm_sample_repaint: overlap_len out of range");
+  MCM_CHECK(!(r->add_blend && r->overlap_len > 0) || r->blend_w != nullptr, "mcm_sample_repaint: addBlend needs blend_w");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t rows = (size_t)B * c->T, n = rows * c->IN;
+  if (x0_out != x_T) MCM_CUDA(cudaMemcpyAsync(x0_out, x_T, n * 4, cudaMemcpyDeviceToDevice, st));
+  MCM_TRY(pack_op_launch(x0_out, B * c->T, c->IN, c->IN, false, c->xop, c->fmt_prec(), st));
+  long long draw = 0;
+  const OpPtr none{nullptr, nullptr, 0};
+  auto denoise = [&](int i) -> int {
+    MCM_CHECK(i >= 0 && i < s->n_steps, "mcm_sample_repaint: time index outside the sampler tables");
+    MCM_CHECK(draw + 2 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
+    MCM_TRY(run_denoiser_step(c, B, s->timestep_map[i], st));
+    DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
+                s->alphas_cumprod_prev[i], 0.f, 0};
+    MCM_TRY(ddim_update_launch(x0_out, c->eps32, nullptr, x0_out, rows, c->IN, k, none, c->fmt_prec(), st));
+    const float abp = s->alphas_cumprod_prev[i];
+    const float noise_w = sqrtf(1.f - abp), gt_w = sqrtf(abp);
+    const bool blend = r->add_blend && r->overlap_len > 0 && noise_w < 0.2f;     // :872
+    MCM_TRY(repaint_blend_launch(x0_out, r->gt, r->keep_mask, r->noise_seq + (size_t)(draw + 1) * n, rows, c->IN, c->T, gt_w,
+                                 noise_w, blend ? r->blend_w : nullptr, r->overlap_len, c->xop, c->fmt_prec(), st));
+    draw += 2;
+    return 0;
+  };
+  if (r->n_times == 0) {
+    for (int i = s->n_steps - 1; i >= 0; --i) MCM_TRY(denoise(i));
+    return 0;
+  }
+  for (int k = 0; k + 1 < r->n_times; ++k) {
+    const int t_last = r->times[k], t_cur = r->times[k + 1];
+    if (t_cur < t_last) {
+      MCM_TRY(denoise(t_last));
+    } else {
+      MCM_CHECK(t_last >= 0 && t_last < s->n_steps, "mcm_sample_repaint: undo time outside the sampler tables");
+      MCM_CHECK(draw + 1 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
+      const float beta = r->betas[t_last];
+      MCM_TRY(undo_launch(x0_out, r->noise_seq + (size_t)draw * n, rows, c->IN, sqrtf(1.f - beta), sqrtf(beta), c->xop,
+                          c->fmt_prec(), st));
+      draw += 1;
+    }
+  }
+  return 0;
+}
+
 int mcm_sample_host(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T_host, const float* step_noise_host,
                     float* x0_out_host, void* stream) {
   MCM_TRY(check_batch(c, B));

@@ -353,6 +353,61 @@ ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_mo
   }
 }
 
+// RePaint / outpainting blend after a DDIM update (ddim_sample, gaussian_diffusion.py:855-879, same_overlap_noisy=False):
+//   weighed_gt = sqrt(abar_prev) gt + sqrt(1 - abar_prev) noise ; over the first `overlap` frames, once the noise weight is
+//   below 0.2 (and opt.addBlend), weighed_gt = weighed_gt (1 - lw[t]) + x lw[t] ; x <- keep_mask ? weighed_gt : x
+// in the reference's fp32 op order (no FMA contraction).  Also rewrites the operand copy of x.
+__global__ void __launch_bounds__(256)
+repaint_blend_kernel(float* __restrict__ x, const float* __restrict__ gt, const unsigned char* __restrict__ keep,
+                     const float* __restrict__ noise, size_t rows, int cols, int T, float gt_w, float noise_w,
+                     const float* __restrict__ blend_w, int overlap, OpPtr xop, int op_fmt) {
+  pdl_trigger();
+  pdl_wait();
+  const int ldo = xop.hi ? xop.ld : cols;
+  const size_t total = rows * (size_t)ldo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ldo;
+    const int c = (int)(i - r * ldo);
+    float xn = 0.f;
+    if (c < cols) {
+      const size_t j = r * cols + c;
+      xn = x[j];
+      if (keep[j]) {
+        float wg = __fadd_rn(__fmul_rn(gt_w, gt[j]), __fmul_rn(noise_w, noise[j]));
+        const int t = (int)(r % (size_t)T);
+        if (blend_w != nullptr && t < overlap) {
+          const float lw = blend_w[t];
+          wg = __fadd_rn(__fmul_rn(wg, __fsub_rn(1.f, lw)), __fmul_rn(xn, lw));
+        }
+        xn = wg;
+        x[j] = xn;
+      }
+    }
+    if (xop.hi) op_store1(xop, op_fmt, i, xn);
+  }
+}
+
+// RePaint "undo" (gaussian_diffusion.py:426-435): x <- sqrt(1 - beta) x + sqrt(beta) noise ; rewrites the operand copy
+__global__ void __launch_bounds__(256)
+undo_kernel(float* __restrict__ x, const float* __restrict__ noise, size_t rows, int cols, float a, float b, OpPtr xop,
+            int op_fmt) {
+  pdl_trigger();
+  pdl_wait();
+  const int ldo = xop.hi ? xop.ld : cols;
+  const size_t total = rows * (size_t)ldo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / ldo;
+    const int c = (int)(i - r * ldo);
+    float xn = 0.f;
+    if (c < cols) {
+      const size_t j = r * cols + c;
+      xn = __fadd_rn(__fmul_rn(a, x[j]), __fmul_rn(b, noise[j]));
+      x[j] = xn;
+    }
+    if (xop.hi) op_store1(xop, op_fmt, i, xn);
+  }
+}
+
 __global__ void fill_timesteps_kernel(long long* __restrict__ t_buf, long long t, int B) {
   pdl_trigger();
   pdl_wait();
@@ -490,6 +545,30 @@ int ddim_update_launch(const float* x, const float* eps, const float* noise, flo
   const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
   LaunchTimer lt(LK_ROW, stream);
   MCM_CUDA(launch_pdl(ddim_update_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, x, eps, noise, x_out, rows, cols, c, xop, op_fmt));
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int repaint_blend_launch(float* x, const float* gt, const unsigned char* keep, const float* noise, size_t rows, int cols,
+                         int T, float gt_w, float noise_w, const float* blend_w, int overlap, OpPtr xop, int op_fmt,
+                         cudaStream_t stream) {
+  MCM_CHECK(x && gt && keep && noise && T > 0, "repaint_blend: null argument");
+  const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
+  LaunchTimer lt(LK_ROW, stream);
+  MCM_CUDA(launch_pdl(repaint_blend_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, x, gt, keep, noise, rows, cols,
+                      T, gt_w, noise_w, blend_w, overlap, xop, op_fmt));
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int undo_launch(float* x, const float* noise, size_t rows, int cols, float a, float b, OpPtr xop, int op_fmt,
+                cudaStream_t stream) {
+  MCM_CHECK(x && noise, "undo: null argument");
+  const size_t total = rows * (size_t)(xop.hi ? xop.ld : cols);
+  LaunchTimer lt(LK_ROW, stream);
+  MCM_CUDA(launch_pdl(undo_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, x, noise, rows, cols, a, b, xop, op_fmt));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

@@ -41,6 +41,14 @@ int ddim_update_launch(const float* x, const float* eps, const float* noise, flo
 int ddpm_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
                        DdpmCoefs c, OpPtr xop, int op_fmt, cudaStream_t stream);
 
+// RePaint / outpainting (gaussian_diffusion.py:855-879, :426-435): mask blend after a DDIM update, and the re-noising
+// "undo" step of the harmonising loop.  Both update x in place and rewrite its operand copy.
+int repaint_blend_launch(float* x, const float* gt, const unsigned char* keep, const float* noise, size_t rows, int cols,
+                         int T, float gt_w, float noise_w, const float* blend_w, int overlap, OpPtr xop, int op_fmt,
+                         cudaStream_t stream);
+int undo_launch(float* x, const float* noise, size_t rows, int cols, float a, float b, OpPtr xop, int op_fmt,
+                cudaStream_t stream);
+
 // t_buf[0..B) = t  (the timestep of the current sampler step, read by the graph-captured timestep embedding)
 int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream);
 

@@ -4,8 +4,9 @@
 The float64 numpy tables are computed exactly as `GaussianDiffusion.__init__` (:354-387) and
 `SpacedDiffusion.__init__` (:1416-1431) do; the sampling LOOPS (`p_sample_loop`, `ddim_sample_loop`)
 do not call a Python model per step: they hand the whole loop to `mcm_sample` (one C call, no host
-synchronisation between steps).  Training-side methods (training_losses, VB terms) and the RePaint /
-outpainting branches are out of scope and raise.
+synchronisation between steps).  The RePaint / outpainting branch of `ddim_sample_loop` (y['outpainting_mask'],
+:855-884, :1050-1118) goes to `mcm_sample_repaint`.  Training-side methods (training_losses, VB terms) and
+`opt.same_overlap_noisy` are out of scope and raise.
 """
 import enum
 
@@ -14,6 +15,7 @@ import torch
 
 from ._lib import McmError
 from .engine import SamplerTables
+from .scheduler import count_draws, get_schedule_jump_cjm_ddim
 
 
 class ModelMeanType(enum.Enum):
@@ -121,10 +123,6 @@ class GaussianDiffusion:
             raise McmError("clip_denoised=True is never used by MotionDiffusion (diffusion_architecture.py:179,186)")
         if cond_fn is not None or denoised_fn is not None or pre_seq is not None or transl_req is not None:
             raise McmError("cond_fn / denoised_fn / pre_seq / transl_req are not part of the re-hosted hot path")
-        y = (model_kwargs or {}).get("y") or {}
-        if "outpainting_mask" in y:
-            raise McmError("RePaint / outpainting sampling (gaussian_diffusion.py:855-884) is a 'next' row "
-                           "(SURVEY.md section 8f-2), not implemented yet")
 
     def _run(self, model, shape, noise, model_kwargs, mode, eta, step_noise, device):
         B = shape[0]
@@ -150,12 +148,53 @@ class GaussianDiffusion:
         return self._run(model, shape, noise, model_kwargs, "ddpm", 0.0, step_noise, device)
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
-                         model_kwargs=None, device=None, progress=False, eta=0.0, pre_seq=None, step_noise=None):
+                         model_kwargs=None, device=None, progress=False, eta=0.0, pre_seq=None, step_noise=None,
+                         repaint_noise=None):
         """gaussian_diffusion.py:925-997."""
         self._check_unsupported(model_kwargs, cond_fn, denoised_fn, pre_seq, None, clip_denoised)
         if self.opt is not None and getattr(self.opt, "same_overlap_noisy", False):
             raise McmError("opt.same_overlap_noisy (long-form RePaint) is a 'next' row, not implemented yet")
+        y = (model_kwargs or {}).get("y") or {}
+        mask = y.get("outpainting_mask", None) if hasattr(y, "get") else None
+        if mask is not None and bool(torch.as_tensor(mask).any()):
+            return self._run_repaint(model, shape, noise, model_kwargs, float(eta), device, repaint_noise)
         return self._run(model, shape, noise, model_kwargs, "ddim", float(eta), step_noise, device)
+
+    def _run_repaint(self, model, shape, noise, model_kwargs, eta, device, repaint_noise):
+        """ddim_sample_loop with y['outpainting_mask'] set (gaussian_diffusion.py:962-989): the harmonising loop unless
+        opt.no_repaint, the mask blend of ddim_sample in every step.  `repaint_noise` [n_draws, *shape] (extension)
+        replaces the reference's randn_like draws in order (scheduler.count_draws)."""
+        opt = self.opt
+        if opt is None:
+            raise McmError("outpainting needs the `opt` namespace the reference's tools pass (overlap_len, addBlend, ...)")
+        if eta != 0.0:
+            raise McmError("outpainting is implemented for eta = 0 (what MotionDiffusion passes)")
+        y = model_kwargs["y"]
+        if "gt" not in y:
+            raise McmError("y['outpainting_mask'] without y['gt']")
+        times = None
+        if not getattr(opt, "no_repaint", False):
+            n = int(str(opt.timestep_respacing)[4:])                                      # 'ddim50' -> 50 (:1079-1084)
+            if getattr(opt, "no_resample", False):
+                times = get_schedule_jump_cjm_ddim(n)
+            else:
+                times = get_schedule_jump_cjm_ddim(n, jump_length=opt.jump_length, jump_n_sample=opt.jump_n_sample)
+            if max(times) >= self.num_timesteps:
+                raise McmError(f"harmonising schedule reaches step {max(times)} but the sampler has {self.num_timesteps}")
+        B = shape[0]
+        dev = device if device is not None else next(model.parameters()).device
+        if noise is None:
+            noise = torch.randn(*shape, device=dev)
+        n_draws = count_draws(times, self.num_timesteps)
+        if repaint_noise is None:
+            repaint_noise = torch.randn(n_draws, *shape, device=dev)
+        elif repaint_noise.shape[0] < n_draws:
+            raise McmError(f"repaint_noise holds {repaint_noise.shape[0]} draws, the schedule needs {n_draws}")
+        eng = model.bind_for_sampling(B, dict(model_kwargs), dev)
+        tables = SamplerTables(self._tables(), self.timestep_map, "ddim", 0.0)
+        return eng.sample_repaint(tables, noise.to(dev), torch.as_tensor(y["gt"]), torch.as_tensor(y["outpainting_mask"]),
+                                  repaint_noise, times=times, betas=self.betas, overlap_len=int(getattr(opt, "overlap_len", 0)),
+                                  add_blend=bool(getattr(opt, "addBlend", True)))
 
     def training_losses(self, *a, **k):
         raise McmError("training is out of scope for motioncraft_b200 (inference hot path only)")

@@ -151,6 +151,37 @@ class DenoiserEngine:
                                            _ptr(step_noise), _ptr(out), _stream(self.device)))
         return out
 
+    def sample_repaint(self, tables: SamplerTables, x_T, gt, keep_mask, noise_seq, *, times=None, betas=None,
+                       overlap_len=0, add_blend=True):
+        """RePaint / outpainting DDIM sampling (mcm_sample_repaint).  gt / keep_mask broadcast to x_T's shape; `times` is
+        the harmonising schedule (list ending with -1) or None for the plain loop; `noise_seq` [n_draws, B, T, F]."""
+        x_T = _f32c(x_T, self.device)
+        out = torch.empty_like(x_T)
+        gt = _f32c(gt, self.device).expand_as(x_T).contiguous()
+        keep = keep_mask.to(device=self.device, dtype=torch.bool).expand_as(x_T).contiguous().to(torch.uint8)
+        noise_seq = _f32c(noise_seq, self.device)
+        r = _lib.McmRepaint()
+        keepalive = []
+        if times is not None:
+            t_arr = np.ascontiguousarray(np.asarray(times, dtype=np.int32))
+            b_arr = np.ascontiguousarray(np.asarray(betas, dtype=np.float64).astype(np.float32))
+            keepalive += [t_arr, b_arr]
+            r.n_times = len(t_arr)
+            r.times = t_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+            r.betas = b_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        else:
+            r.n_times = 0
+        r.gt, r.keep_mask, r.noise_seq = gt.data_ptr(), keep.data_ptr(), noise_seq.data_ptr()
+        r.n_draws = noise_seq.shape[0]
+        r.overlap_len, r.add_blend = int(overlap_len), int(bool(add_blend))
+        blend_w = torch.linspace(0, 1, int(overlap_len)).to(self.device) if overlap_len > 0 else None   # gaussian_diffusion.py:873
+        r.blend_w = blend_w.data_ptr() if blend_w is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mcm_sample_repaint(self._ctx, ctypes.byref(tables.struct), ctypes.byref(r), x_T.shape[0],
+                                                   _ptr(x_T), _ptr(out), _stream(self.device)))
+            torch.cuda.current_stream(self.device).synchronize()     # host arrays / temporaries may go out of scope
+        return out
+
     def sample_host(self, tables: SamplerTables, x_T_host, out_host=None):
         """x_T in (pinned) host memory -> x_0 in host memory; H2D + loop + D2H inside the library."""
         assert x_T_host.device.type == "cpu" and x_T_host.dtype == torch.float32 and x_T_host.is_contiguous()

@@ -3,7 +3,7 @@
 Runs in the build container only (needs /root/reference, imported under oracle/ref_shim.py).  Inputs
 and weights are pure functions of seeds (motioncraft_b200/synth.py), so only OUTPUTS are stored.
 
-    python oracle/make_golden.py            # writes tests/golden/{t2m_T60,ctrl_T60,schedule}.npz
+    python oracle/make_golden.py            # writes tests/golden/{t2m_T60,ctrl_T60,schedule,repaint_T60}.npz
 """
 import contextlib
 import os
@@ -122,9 +122,48 @@ def schedule():
     print("schedule ok")
 
 
+def repaint(T=60, B=2, L=10):
+    """RePaint / outpainting long-form sampling: SpacedDiffusion.ddim_sample_loop with
+    y = {gt, outpainting_mask} as tools/m2d_test.py:176-195 builds it (first `overlap_len` frames kept), both through the
+    harmonising loop (jump_length 3, jump_n_sample 5: 138 denoise + 108 undo steps) and with opt.no_repaint (plain loop,
+    blend inside every ddim_sample).  torch.randn_like is scripted; the draw order is part of the contract."""
+    import copy
+    from oracle import mcm_oracle as O
+    ref = ref_shim.build_reference_mcm(T=T)
+    sd = synth.synth_state_dict({k: v.shape for k, v in ref.state_dict().items()})
+    ref.load_state_dict(sd)
+    x, xf_out, xf_proj = inputs(B, T)
+    kw = dict(motion_mask=torch.ones(B, T), motion_length=torch.full((B,), T), xf_proj=xf_proj, xf_out=xf_out)
+    gt = torch.zeros(T, 322)
+    mask = torch.zeros(T, 322, dtype=torch.bool)
+    gt[:L] = synth.synth_tensor("gt", (T, 322), synth.SEED_REPAINT_GT)[:L]
+    mask[:L] = True
+    out = {"overlap_len": np.array(L)}
+    for mode in ("harmonize", "plain"):
+        ddim = ref_shim.build_reference_diffusion("15,15,8,6,6")
+        ddim.opt = copy.copy(ddim.opt)
+        ddim.opt.overlap_len = L
+        ddim.opt.no_repaint = (mode == "plain")
+        times = None if mode == "plain" else O.schedule_jump_cjm_ddim(50, ddim.opt.jump_length, ddim.opt.jump_n_sample)
+        n_den = 50 if times is None else sum(1 for a, b in zip(times[:-1], times[1:]) if b < a)
+        n_undo = 0 if times is None else sum(1 for a, b in zip(times[:-1], times[1:]) if b >= a)
+        n_draw = 2 * n_den + n_undo
+        noise = synth.synth_tensor("repaint_noise", (n_draw, B, T, 322), synth.SEED_REPAINT_NOISE)
+        with torch.no_grad(), scripted_randn_like([noise[i] for i in range(n_draw)]):
+            out[f"{mode}_x0"] = ddim.ddim_sample_loop(ref, (B, T, 322), noise=x.clone(), clip_denoised=False,
+                                                      model_kwargs=dict(kw, y={"gt": gt.clone(), "outpainting_mask": mask}),
+                                                      eta=0).numpy()
+        out[f"{mode}_n_draw"] = np.array(n_draw)
+        if times is not None:
+            out["times"] = np.array(times)
+    np.savez_compressed(os.path.join(GOLD, f"repaint_T{T}.npz"), **out)
+    print("repaint", {k: (v.shape, float(np.abs(v).max())) for k, v in out.items() if v.dtype.kind == "f"})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     schedule()
     t2m()
     ctrl()
+    repaint()

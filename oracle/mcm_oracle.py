@@ -361,6 +361,83 @@ def p_sample_loop(model_fn, x_T, tables, tmap, step_noise, trace=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# RePaint / outpainting long-form sampling
+# ----------------------------------------------------------------------------------------------
+def schedule_jump_cjm_ddim(time_respacing=25, jump_length=1, jump_n_sample=1):
+    """get_schedule_jump_cjm_ddim, mogen/models/utils/scheduler.py:178-208: the sequence of (respaced) timesteps the
+    harmonising loop visits -- it starts at int(0.6 * time_respacing) - 1 (15 - 1 for 25), walks down to 0 and, at every
+    `jump_length`-th step below t_T - jump_length, jumps back up `jump_length` steps `jump_n_sample - 1` times; ends with -1."""
+    t_T = 15 if time_respacing == 25 else int(time_respacing * 0.6)
+    jumps = {j: jump_n_sample - 1 for j in range(0, t_T - jump_length, jump_length)}
+    t, ts = t_T, []
+    while t >= 1:
+        t -= 1
+        ts.append(t)
+        if jumps.get(t, 0) > 0:
+            jumps[t] -= 1
+            for _ in range(jump_length):
+                t += 1
+                ts.append(t)
+    ts.append(-1)
+    return ts
+
+
+def repaint_step(x_in, eps_model, tables, i, gt, keep_mask, blend_noise, overlap_len, add_blend):
+    """One ddim_sample call with eta = 0 and an outpainting mask, gaussian_diffusion.py:821-884 (same_overlap_noisy=False):
+    the DDIM update, then x <- mask ? (sqrt(abar_prev) gt + sqrt(1 - abar_prev) noise) : x, with the overlap frames of the
+    weighted ground truth linearly cross-faded into the sample once the noise weight drops below 0.2 (:872-876)."""
+    x = x_in
+    c1 = _coef(tables["sqrt_recip_alphas_cumprod"], i, x)
+    c2 = _coef(tables["sqrt_recipm1_alphas_cumprod"], i, x)
+    pred_xstart = c1 * x - c2 * eps_model
+    eps = (c1 * x - pred_xstart) / c2
+    alpha_bar_prev = _coef(tables["alphas_cumprod_prev"], i, x)
+    sample = pred_xstart * torch.sqrt(alpha_bar_prev) + torch.sqrt(1 - alpha_bar_prev) * eps      # sigma = 0
+    x = sample
+    if keep_mask is not None and bool(keep_mask.any()):
+        noise_weight = torch.sqrt(1 - alpha_bar_prev)
+        weighed_gt = torch.sqrt(alpha_bar_prev) * gt + noise_weight * blend_noise
+        weighed_gt = weighed_gt.expand_as(x).clone()
+        if bool(noise_weight < 0.2) and add_blend:
+            lw = torch.linspace(0, 1, overlap_len).view(1, -1, 1).expand(x.shape[0], -1, -1).to(x.dtype)
+            weighed_gt[:, :overlap_len, :] = weighed_gt[:, :overlap_len, :] * (1 - lw) + x[:, :overlap_len, :] * lw
+        x = (weighed_gt * keep_mask) + (x * ~keep_mask)
+    return x, pred_xstart
+
+
+def ddim_repaint_loop(model_fn, x_T, tables, tmap, betas, gt, keep_mask, noise_seq, times=None, overlap_len=0,
+                      add_blend=True):
+    """ddim_sample_loop with y['outpainting_mask'] (gaussian_diffusion.py:925-997): the harmonising loop
+    (:1050-1118) over `times` (denoise when the next time is lower, else `undo` :426-435 = re-noise with the respaced
+    beta), or, with times=None (opt.no_repaint), the plain progressive loop -- ddim_sample blends in both.
+    `noise_seq` replaces the reference's torch.randn_like draws IN ORDER: two per denoise call (the unused eta noise of
+    :847, then the blend noise of :867 when the mask is set), one per undo."""
+    x = x_T
+    B = x.shape[0]
+    it = iter(noise_seq)
+    has_mask = keep_mask is not None and bool(keep_mask.any())
+
+    def denoise(x, i):
+        t_model = torch.full((B,), tmap[i], dtype=torch.long)
+        eps_model = model_fn(x, t_model)
+        next(it)                                              # :847 randn_like(x), multiplied by sigma = 0
+        blend_noise = next(it) if has_mask else None          # :867
+        return repaint_step(x, eps_model, tables, i, gt, keep_mask, blend_noise, overlap_len, add_blend)[0]
+
+    if times is None:
+        for i in reversed(range(len(tmap))):
+            x = denoise(x, i)
+        return x
+    for t_last, t_cur in zip(times[:-1], times[1:]):
+        if t_cur < t_last:
+            x = denoise(x, t_last)
+        else:
+            beta = _coef(betas, t_last, x)
+            x = torch.sqrt(1 - beta) * x + torch.sqrt(beta) * next(it)
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
 # candidate operand roundings for precision emulation
 # ----------------------------------------------------------------------------------------------
 def round_fp16(x):

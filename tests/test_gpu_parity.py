@@ -299,3 +299,37 @@ torch.save(x0.cpu(), sys.argv[1])
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
         outs.append(torch.load(f))
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("mode", ["harmonize", "plain"])
+def test_repaint_sampler_vs_reference_golden(golden_dir, mode):
+    """RePaint / outpainting long-form DDIM (mcm_sample_repaint): first 10 frames pinned to a ground-truth tail, through the
+    harmonising loop (138 denoise + 108 undo steps) and the plain 50-step loop, against the unmodified reference's x_0 with
+    the same scripted noise draws.  Through the reference-facing front end (SpacedDiffusion.ddim_sample_loop + opt)."""
+    import argparse
+    from motioncraft_b200 import diffusion
+    g = np.load(os.path.join(golden_dir, "repaint_T60.npz"))
+    T, B, L = 60, 2, int(g["overlap_len"])
+    x, xf_out, xf_proj = C.inputs(B, T)
+    gt = torch.zeros(T, 322)
+    mask = torch.zeros(T, 322, dtype=torch.bool)
+    gt[:L] = synth.synth_tensor("gt", (T, 322), synth.SEED_REPAINT_GT)[:L]
+    mask[:L] = True
+    n_draw = int(g[f"{mode}_n_draw"])
+    noise = synth.synth_tensor("repaint_noise", (n_draw, B, T, 322), synth.SEED_REPAINT_NOISE)
+    opt = argparse.Namespace(no_repaint=(mode == "plain"), same_overlap_noisy=False, addBlend=True, overlap_len=L,
+                             no_resample=False, timestep_respacing="ddim50", jump_length=3, jump_n_sample=5)
+    d = diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                                       model_var_type="fixed_small", respace="15,15,8,6,6"), opt=opt)
+    net = M.MCMTransformer(**modules.mcm_config(T))
+    net.use_text_proj = True            # as the reference model the golden was generated with (oracle/ref_shim.py)
+    net.load_state_dict(C.base_state(T))
+    net = net.cuda().eval()
+    kw = dict(motion_mask=torch.ones(B, T).cuda(), motion_length=torch.full((B,), T).cuda(), xf_proj=xf_proj.cuda(),
+              xf_out=xf_out.cuda(), y={"gt": gt.cuda(), "outpainting_mask": mask.cuda()})
+    x0 = d.ddim_sample_loop(net, (B, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw, eta=0,
+                            repaint_noise=noise.cuda())
+    want = torch.from_numpy(g[f"{mode}_x0"])
+    assert C.rel_l2(x0, want) < TOL_FAST
+    # the pinned frames end exactly on the ground truth blend of the last step (mask == True there)
+    assert torch.isfinite(x0).all()

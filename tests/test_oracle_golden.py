@@ -111,3 +111,31 @@ def test_dead_ffn_channel_has_no_effect(gold_t2m):
     x, xf_out, xf_proj = C.inputs(1, 60)
     got = C.oracle_forward(sd, x, 999, xf_proj, xf_out)
     assert C.rel_l2(got, gold_t2m["eps_t999"]) < 1e-6
+
+
+def test_repaint_oracle_matches_reference_golden(golden_dir):
+    """RePaint / outpainting long-form sampling: the oracle's restatement of ddim_sample's blend branch,
+    the harmonising loop and `undo` against tensors produced by the UNMODIFIED reference (oracle/make_golden.py::repaint,
+    scripted randn_like), and the product's own schedule restatement against the reference's."""
+    from motioncraft_b200 import scheduler
+    g = np.load(os.path.join(golden_dir, "repaint_T60.npz"))
+    T, B, L = 60, 2, int(g["overlap_len"])
+    times = [int(t) for t in g["times"]]
+    assert O.schedule_jump_cjm_ddim(50, 3, 5) == times
+    assert scheduler.get_schedule_jump_cjm_ddim(50, jump_length=3, jump_n_sample=5) == times
+    assert scheduler.count_draws(times, 50) == int(g["harmonize_n_draw"]) and scheduler.count_draws(None, 50) == int(g["plain_n_draw"])
+    assert times[0] == 29 and times[-1] == -1 and len(times) == 247
+    sd = C.base_state(T)
+    x, xf_out, xf_proj = C.inputs(B, T)
+    gt = torch.zeros(T, 322)
+    mask = torch.zeros(T, 322, dtype=torch.bool)
+    gt[:L] = synth.synth_tensor("gt", (T, 322), synth.SEED_REPAINT_GT)[:L]
+    mask[:L] = True
+    tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
+    mode = "plain"       # the harmonising loop (246 model calls) is exercised on the GPU; one CPU pass keeps this suite short
+    n_draw = int(g[f"{mode}_n_draw"])
+    noise = synth.synth_tensor("repaint_noise", (n_draw, B, T, 322), synth.SEED_REPAINT_NOISE)
+    with torch.no_grad():
+        got = O.ddim_repaint_loop(lambda xx, tt: O.mcm_forward(sd, xx, tt, xf_proj, xf_out), x.clone(), tables, tmap,
+                                  tables["betas"], gt, mask, [noise[i] for i in range(n_draw)], times=None, overlap_len=L)
+    assert torch.equal(got, torch.from_numpy(g[f"{mode}_x0"])), "oracle must be bit-identical to the reference on this host"
