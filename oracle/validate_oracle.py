@@ -50,6 +50,34 @@ def main():
                                  tables, tmap)
     print("ddim50 max|diff| =", (want - got).abs().max().item(), "|x0|max =", want.abs().max().item())
     assert torch.equal(want, got), "oracle DDIM loop is not bit-identical to the reference"
+
+    # RePaint / outpainting (harmonising loop + plain loop), scripted randn_like
+    import copy
+    from oracle.make_golden import scripted_randn_like
+    from mogen.models.utils.scheduler import get_schedule_jump_cjm_ddim
+    for args in [(25, 1, 1), (50, 3, 5), (50, 1, 1), (50, 2, 3), (100, 4, 2)]:
+        assert get_schedule_jump_cjm_ddim(*args) == O.schedule_jump_cjm_ddim(*args), args
+    L = 10
+    gt = torch.zeros(T, 322)
+    mask = torch.zeros(T, 322, dtype=torch.bool)
+    gt[:L] = synth.synth_tensor("gt", (T, 322), synth.SEED_REPAINT_GT)[:L]
+    mask[:L] = True
+    for mode in ("harmonize", "plain"):
+        d = ref_shim.build_reference_diffusion("15,15,8,6,6")
+        d.opt = copy.copy(d.opt)
+        d.opt.overlap_len, d.opt.no_repaint = L, (mode == "plain")
+        times = None if mode == "plain" else O.schedule_jump_cjm_ddim(50, d.opt.jump_length, d.opt.jump_n_sample)
+        n_den = 50 if times is None else sum(1 for a_, b_ in zip(times[:-1], times[1:]) if b_ < a_)
+        n_draw = 2 * n_den + (0 if times is None else len(times) - 1 - n_den)
+        noise = synth.synth_tensor("repaint_noise", (n_draw, B, T, 322), synth.SEED_REPAINT_NOISE)
+        with torch.no_grad(), scripted_randn_like([noise[i] for i in range(n_draw)]):
+            want = d.ddim_sample_loop(ref, (B, T, 322), noise=x.clone(), clip_denoised=False,
+                                      model_kwargs=dict(kw, y={"gt": gt.clone(), "outpainting_mask": mask}), eta=0)
+        with torch.no_grad():
+            got = O.ddim_repaint_loop(lambda xx, tt: O.mcm_forward(sd, xx, tt, xf_proj, xf_out), x.clone(), tables, tmap,
+                                      tables["betas"], gt, mask, [noise[i] for i in range(n_draw)], times=times, overlap_len=L)
+        print(f"repaint {mode}: max|diff| =", (want - got).abs().max().item())
+        assert torch.equal(want, got), f"oracle RePaint loop ({mode}) is not bit-identical to the reference"
     print("OK")
 
 
