@@ -391,12 +391,16 @@ class ControlT2MHalf_MCM(nn.Module):
         enc_cfg = _cfg_get(cfg, "condition_encode_cfg")
         self._pre_encode = bool(_cfg_get(enc_cfg, "condition_pre_encode"))
         if self._pre_encode:
-            # the WavEncoder (mogen/models/utils/blocks.py:53-71) is step-invariant and stays outside this
-            # library ("next" row f-3): callers hand the PRE-ENCODED audio embedding as `c`.
+            # controlnet_mcm.py:138-146: raw audio -> WavEncoder -> control_cond_input.  The encoder is step-invariant:
+            # it runs ONCE per sampling run (cuDNN through torch, condition_encoder.py), not once per denoise step as in
+            # the reference.  Callers may also hand the already encoded embedding as `c`.
+            from .condition_encoder import ConditionEncoder
             in_feats = _cfg_get(enc_cfg, "condition_latent_dim")
+            self.condition_pre_encoder = ConditionEncoder(enc_cfg)
         else:
             in_feats = control_cond_feats
-        self.condition_pre_encoder = None
+            self.condition_pre_encoder = None
+        self._enc_cache = None
         self.control_cond_feats = in_feats
         self.control_cond_input = _zero_(nn.Linear(in_feats, base_model.latent_dim))
         self._engine = None
@@ -458,6 +462,13 @@ class ControlT2MHalf_MCM(nn.Module):
     def _condition(self, c):
         if c is None:
             return None
+        enc = self.condition_pre_encoder
+        if enc is not None and c.shape[-1] == enc.raw_feats and c.shape[-1] != self.control_cond_feats:
+            key = (c.data_ptr(), c._version, tuple(c.shape))
+            if self._enc_cache is None or self._enc_cache[0] != key:
+                dev = self.control_cond_input.weight.device
+                self._enc_cache = (key, enc(c.to(device=dev, dtype=torch.float32)))
+            c = self._enc_cache[1]
         if c.shape[-1] != self.control_cond_feats:
             raise McmError(f"control condition has {c.shape[-1]} features, control_cond_input expects "
                            f"{self.control_cond_feats} (raw audio must be pre-encoded; see INTEGRATION.md)")

@@ -33,6 +33,14 @@ def synth_param(name, shape, seed=SEED_WEIGHTS):
     is_norm = ".norm." in name or name.endswith("norm.weight") or name.endswith("norm.bias") or "text_norm" in name
     if name.endswith("sequence_embedding"):
         return torch.randn(shape, generator=g)
+    if leaf == "running_var":                      # BatchNorm statistics of the WavEncoder: positive
+        return 0.5 + torch.rand(shape, generator=g)
+    if leaf == "running_mean":
+        return 0.1 * torch.randn(shape, generator=g)
+    if leaf == "num_batches_tracked":
+        return torch.zeros(shape, dtype=torch.long)
+    if ".bn" in name or ".downsample.1." in name:  # BatchNorm affine
+        return (1.0 if leaf == "weight" else 0.0) + 0.1 * torch.randn(shape, generator=g)
     if is_norm:
         if leaf == "weight":
             return 1.0 + 0.1 * torch.randn(shape, generator=g)

@@ -3,7 +3,7 @@
 Runs in the build container only (needs /root/reference, imported under oracle/ref_shim.py).  Inputs
 and weights are pure functions of seeds (motioncraft_b200/synth.py), so only OUTPUTS are stored.
 
-    python oracle/make_golden.py            # writes tests/golden/{t2m_T60,ctrl_T60,schedule,repaint_T60}.npz
+    python oracle/make_golden.py            # writes tests/golden/{t2m_T60,ctrl_T60,schedule,repaint_T60,wav_encoder}.npz
 """
 import contextlib
 import os
@@ -122,6 +122,23 @@ def schedule():
     print("schedule ok")
 
 
+def wav_encoder(out_dim=64, audio_in=2, n_samples=16000, B=2):
+    """WavEncoder (mogen/models/utils/blocks.py:53-71) in eval mode on a seeded waveform; also the reference's parameter
+    names of ConditionEncoder / the full-size encoder's frame count for the s2g window (159 900 samples -> 297)."""
+    ref_shim.install()
+    from mogen.models.utils.blocks import WavEncoder
+    enc = WavEncoder(out_dim, audio_in=audio_in).eval()
+    sd = synth.synth_state_dict({k: v.shape for k, v in enc.state_dict().items()})
+    enc.load_state_dict(sd)
+    wav = synth.synth_tensor("wav", (B, n_samples, audio_in), synth.SEED_C_EMB)
+    with torch.no_grad():
+        out = enc(wav).numpy()
+        frames = WavEncoder(8, audio_in=audio_in).eval()(torch.zeros(1, 159900, audio_in)).shape[1]
+    np.savez_compressed(os.path.join(GOLD, "wav_encoder.npz"), out=out, keys=np.array(sorted(sd.keys())),
+                        frames_159900=np.array(frames), out_dim=np.array(out_dim), n_samples=np.array(n_samples))
+    print("wav_encoder", out.shape, float(np.abs(out).max()), "frames(159900) =", frames)
+
+
 def repaint(T=60, B=2, L=10):
     """RePaint / outpainting long-form sampling: SpacedDiffusion.ddim_sample_loop with
     y = {gt, outpainting_mask} as tools/m2d_test.py:176-195 builds it (first `overlap_len` frames kept), both through the
@@ -167,3 +184,4 @@ if __name__ == "__main__":
     t2m()
     ctrl()
     repaint()
+    wav_encoder()

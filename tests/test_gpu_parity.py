@@ -333,3 +333,38 @@ def test_repaint_sampler_vs_reference_golden(golden_dir, mode):
     assert C.rel_l2(x0, want) < TOL_FAST
     # the pinned frames end exactly on the ground truth blend of the last step (mask == True there)
     assert torch.isfinite(x0).all()
+
+
+def test_speech_control_with_raw_audio_condition():
+    """speech-to-gesture as the reference's tools call it: ControlT2MHalf_MCM with condition_pre_encode=True receives RAW
+    audio (B, samples, 2); the WavEncoder runs once (torch / cuDNN), its output enters control_cond_input inside the CUDA
+    library.  Checked against the oracle fed with the CPU evaluation of the same encoder, and against handing the
+    pre-encoded embedding directly."""
+    from motioncraft_b200.condition_encoder import WavEncoder
+    T, B, latent = 60, 2, 64
+    base = M.MCMTransformer(**modules.mcm_config(T))
+    base.use_text_proj = True
+    cfg = dict(model=dict(model=modules.mcm_config(T)),
+               condition_encode_cfg=dict(dataset_name="beats2", condition_pre_encode=True, condition_pre_encode_type="wav",
+                                         condition_latent_dim=latent, control_cond_feats=2, condition_cfg=True))
+    net = M.ControlT2MHalf_MCM(base, copy_blocks_num=2, control_cond_feats=2, cfg=cfg)
+    assert any(k.startswith("condition_pre_encoder.pre_encoder.feat_extractor.0.conv1") for k in net.state_dict())
+    sd = synth.synth_state_dict({k: v.shape for k, v in net.state_dict().items()})
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    x, xf_out, xf_proj = C.inputs(B, T)
+    wav = synth.synth_tensor("wav", (B, 16000, 2), synth.SEED_C_EMB)
+    t = torch.full((B,), 999, dtype=torch.long)
+    kw = dict(motion_mask=torch.ones(B, T).cuda(), xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    got = net(x.cuda(), t.cuda(), c=wav.cuda(), **kw)
+    enc = WavEncoder(latent, audio_in=2).eval()
+    enc.load_state_dict({k[len("condition_pre_encoder.pre_encoder."):]: v for k, v in sd.items()
+                         if k.startswith("condition_pre_encoder.pre_encoder.")})
+    with torch.no_grad():
+        c_emb = enc(wav)                                              # (B, 30, latent) on the CPU
+        osd = {k: v for k, v in sd.items() if not k.startswith("condition_pre_encoder.")}
+        want = O.control_forward(osd, x, t, xf_proj, xf_out, c_emb)
+    assert c_emb.shape == (B, 30, latent)
+    assert C.rel_l2(got, want) < TOL_FAST
+    got2 = net(x.cuda(), t.cuda(), c=c_emb.cuda(), **kw)              # pre-encoded embedding is accepted as well
+    assert C.rel_l2(got2, want) < TOL_FAST

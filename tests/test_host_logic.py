@@ -143,3 +143,29 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "ref_shim" not in src and "/root/reference" not in src, f
+
+
+def test_wav_encoder_matches_reference_golden(golden_dir):
+    """Condition pre-encoder of the speech-to-gesture ControlNet branch: same parameter names as the
+    reference's WavEncoder, bit-identical output on CPU for seeded weights / waveform (golden from the unmodified
+    reference, oracle/make_golden.py::wav_encoder), and the s2g window length 159 900 samples -> 297 frames.  The encoder
+    is torch / cuDNN library code evaluated once per sampling run, so it has a CPU evaluation to test against."""
+    import numpy as np
+    import os
+    from motioncraft_b200 import synth
+    from motioncraft_b200.condition_encoder import ConditionEncoder, WavEncoder
+    g = np.load(os.path.join(golden_dir, "wav_encoder.npz"))
+    enc = WavEncoder(int(g["out_dim"]), audio_in=2).eval()
+    assert sorted(enc.state_dict().keys()) == list(g["keys"])
+    enc.load_state_dict(synth.synth_state_dict({k: v.shape for k, v in enc.state_dict().items()}))
+    wav = synth.synth_tensor("wav", (2, int(g["n_samples"]), 2), synth.SEED_C_EMB)
+    with torch.no_grad():
+        out = enc(wav)
+    assert torch.equal(out, torch.from_numpy(g["out"]))
+    assert WavEncoder(8, audio_in=2).eval()(torch.zeros(1, 159900, 2)).shape[1] == int(g["frames_159900"]) == 297
+    ce = ConditionEncoder(dict(dataset_name="beats2", condition_pre_encode_type="wav", condition_latent_dim=32,
+                               control_cond_feats=2))
+    assert all(k.startswith("pre_encoder.feat_extractor.") for k in ce.state_dict())
+    with pytest.raises(McmError):
+        ConditionEncoder(dict(dataset_name="finedance", condition_pre_encode_type="wav", condition_latent_dim=32,
+                              control_cond_feats=2))
