@@ -69,7 +69,8 @@ void mcm_destroy(mcm_ctx* ctx);
  *   "chunk" n = pass the batch through the layer stack n samples at a time (default 0 = whole batch)
  *   "fused" 1 = cross-attention + FFN of a layer in one persistent kernel (default; same arithmetic, fp32 reduction
  *               order of the LayerNorm statistics differs), 0 = one kernel per GEMM / row op
- *   "fused_sa" channel attention: 0 = separate kernels, 1 = fused tail kernel, 2 = fused head and tail (default) */
+ *   "fused_sa" channel attention: 0 = separate kernels, 1 = fused tail kernel, 2 = fused head and tail (default),
+ *               3 = also the token softmax + context in one kernel (experimental, slower) */
 int mcm_set_option(mcm_ctx* ctx, const char* name, int value);
 
 /* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key

@@ -62,7 +62,9 @@ struct mcm_ctx {
   mcm_config cfg;
   int T, Tp, D, E, F, L, H, IN, INp, NTmax, NTp, nL, nC, Cin, Cinp, hdT, hdD, Bmax, mod_total;
   int fused = 1;          // MCM_FUSED=0: run cross-attention + FFN as separate GEMM / row kernels (the round-1 path)
-  int fused_sa = 2;       // MCM_FUSED_SA: 0 = channel attention as separate kernels, 1 = fused tail, 2 = fused head and tail
+  int fused_sa = 2;       // MCM_FUSED_SA: 0 = channel attention as separate kernels, 1 = fused tail, 2 = + fused head (default),
+                          // 3 = + fused token softmax / context (parity-green, but 135 us vs 74 us for the two kernels it
+                          //     replaces: its per-sample rounds serialise behind the row softmax; opt-in until reworked)
   int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
   void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
@@ -288,6 +290,13 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
   // q: softmax over each head's T/H features; k: softmax over the D channel-tokens (a row in [B,T',D])
   MCM_TRY(softmax_seg_launch(w.f32A, B * D, T, T, hdT, opC_t, ff, st));
   }   // unfused channel-attention head
+  if (sa_fused && c->fused_sa >= 3) {
+    // ---- token softmax of k + per-head context k^T v: one persistent kernel (fused_block.cu)
+    SaCtxArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.k32 = w.f32B; a.v16 = opB_d; a.ctxT = view(w.ctxT_sa, Tp); a.T = T; a.batch = B; a.heads = H;
+    MCM_TRY(sa_ctx_launch(a, st));
+  } else {
   MCM_TRY(softmax_seg_launch(w.f32B, B * T, D, D, D, opD_d, ff, st));
   {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, stored transposed: ctxT[b][l][dk]
     GemmProblem g;
@@ -303,6 +312,7 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     g.algo_flops = 2.0 * T * hdT * D * B;      // only the per-head diagonal blocks are algorithmic work
     MCM_TRY(gemm_tc_launch(g, st));
   }
+  }   // unfused token softmax + context
   if (sa_fused) {
     // ---- y = softmax(q) ctx -> AdaLN_T -> SiLU -> Linear(T,T) -> h^T += : one persistent kernel (fused_block.cu)
     SaTailArgs a;

@@ -1523,6 +1523,227 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
 }
 
 
+// =================================================================================================================
+// sa_ctx_kernel -- the per-head context of the channel attention (efficient_attention.py:36-39 on x^T): for a tile of
+// 256 rows of k [B*T, 512] (fp32; row = (sample, feature d), columns = the 512 channel-tokens):
+//   P   OPA = softmax over the 512 tokens of each row (warp per row)          [key softmax, dim=1 of (B, N, H, d)]
+//   per sample s of the tile:
+//   G   c = OPA v[s]^T        (B operand: the sample's value rows [T, 512], K-major)      ctx[d, l] = sum_n ks[n, d] v[n, l]
+//   E   rows of s: keep the block-diagonal (head(d) == head(l)), fp16, transposed 32 x 32 tiles -> ctxT[s][l][d]
+// Rounds alternate between the two TMEM halves, so the epilogue of one sample overlaps the MMAs of the next.
+// =================================================================================================================
+struct ScMaps {
+  CUtensorMap v;
+};
+struct ScParams {
+  const float* k32;
+  uint16_t* ctxT;
+  int rows, T, Tp, Np, hd, nch, batch, n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+sa_ctx_kernel(const __grid_constant__ ScMaps tm, const __grid_constant__ ScParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NSLOT];
+  __shared__ __align__(8) uint64_t empty_bar[NSLOT];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t opa = smem_base, ring = smem_base + OPA_BYTES, stg = ring + RING_BYTES;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+  const uint32_t slab_b = (uint32_t)(p.Np / 2) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSLOT; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&tfull_bar[s]), 1);
+        mbar_init(smem_u32(&tempty_bar[s]), 2u * NCW);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(smem_u32(&tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: value slabs of every sample of the tile
+    int slot = 0;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+      const int g0 = tile * 2 * ROWS;
+      const int s_first = g0 / p.T, s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
+#pragma unroll 1
+      for (int s = s_first; s <= s_last; ++s)
+#pragma unroll 1
+        for (int kb = 0; kb < D / 64; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[slot]), ph ^ 1u);
+          const uint32_t bar = smem_u32(&full_bar[slot]);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(bar, 2u * slab_b);
+            tma_load_3d_2sm(&tm.v, bar, ring + (uint32_t)slot * SLAB, kb * 64, rank * (p.Np / 2), s);
+          }
+          __syncwarp();
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader)
+    if (rank == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      uint32_t te_par[2] = {0u, 0u};
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Np >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+#pragma unroll 1
+      for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+        const int g0 = tile * 2 * ROWS;
+        const int s_first = g0 / p.T, s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
+#pragma unroll 1
+        for (int s = s_first; s <= s_last; ++s) {
+          const int hh = (s - s_first) & 1;
+          mbar_wait(smem_u32(&tempty_bar[hh]), te_par[hh]);
+          te_par[hh] ^= 1u;
+          tc_fence_after();
+#pragma unroll 1
+          for (int kb = 0; kb < D / 64; ++kb) {
+            mbar_wait(smem_u32(&full_bar[slot]), ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_addr = opa + (uint32_t)kb * SLAB, b_addr = ring + (uint32_t)slot * SLAB;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_2sm(tmem_base + (uint32_t)(hh * 256), make_smem_desc_sw128(a_addr + k * 32),
+                             make_smem_desc_sw128(b_addr + k * 32), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+              umma_commit_2sm(smem_u32(&empty_bar[slot]), (uint16_t)3);
+            }
+            __syncwarp();
+            if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+          }
+          if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[hh]), (uint16_t)3);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int part = ew >> 2;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int c_split = (p.nch + 1) / 2;
+    const int c_lo = part == 0 ? 0 : c_split, c_hi = part == 0 ? c_split : p.nch;
+    uint32_t tf_par[2] = {0u, 0u};
+    auto arrive = [&](int hh) {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(smem_u32(&tempty_bar[hh]), 0u);
+    };
+#pragma unroll 1
+    for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
+      const int g0 = tile * 2 * ROWS, gc = g0 + rank * ROWS;
+      const int s_first = g0 / p.T, s_last = (min(g0 + 2 * ROWS, p.rows) - 1) / p.T;
+      const int nsamp = s_last - s_first + 1;
+      // ---- P: softmax over the 512 tokens of every row -> fp16 operand tile (the arithmetic of softmax_seg_kernel)
+#pragma unroll 1
+      for (int i = 0; i < ROWS / NCW; i += 2) {
+        float4 x[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const long long g = (long long)gc + ew + NCW * (i + u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            x[u][j] = g < p.rows ? __ldcg(reinterpret_cast<const float4*>(p.k32 + g * D) + j * 32 + lane)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = ew + NCW * (i + u);
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m = fmaxf(m, fmaxf(fmaxf(x[u][j].x, x[u][j].y), fmaxf(x[u][j].z, x[u][j].w)));
+          m = warp_max(m);
+          float ssum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            x[u][j].x = ex2_fast((x[u][j].x - m) * L2E); x[u][j].y = ex2_fast((x[u][j].y - m) * L2E);
+            x[u][j].z = ex2_fast((x[u][j].z - m) * L2E); x[u][j].w = ex2_fast((x[u][j].w - m) * L2E);
+            ssum += (x[u][j].x + x[u][j].y) + (x[u][j].z + x[u][j].w);
+          }
+          const float inv = 1.f / warp_sum(ssum);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = j * 128 + lane * 4;
+            st_shared_v2u(opa_addr(opa, r, col) + (uint32_t)(lane & 1) * 8u, pack_f16x2_sat(x[u][j].x * inv, x[u][j].y * inv),
+                          pack_f16x2_sat(x[u][j].z * inv, x[u][j].w * inv));
+          }
+        }
+      }
+      arrive(0);
+      if (nsamp >= 2) arrive(1);
+      // ---- rounds
+#pragma unroll 1
+      for (int s = s_first; s <= s_last; ++s) {
+        const int hh = (s - s_first) & 1;
+        mbar_wait(smem_u32(&tfull_bar[hh]), tf_par[hh]);
+        tf_par[hh] ^= 1u;
+        tc_fence_after();
+        const int d = gc + quad * 32 + lane - s * p.T;          // this thread's feature index within sample s
+        const bool mine = d >= 0 && d < p.T;
+        if (__any_sync(0xffffffffu, mine)) {
+          // ctxT[s][l][d]: for a fixed l the 32 lanes (consecutive d) write 64 contiguous bytes.  (A transposed TMA tile
+          // store cannot be used: its start coordinate d0 = row - s T is not 16-byte aligned in general.)
+          const int dh = mine ? d / p.hd : -1;
+          uint16_t* const dst = p.ctxT + ((size_t)s * p.T) * p.Tp + (mine ? d : 0);
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; ++c) {
+            float v[32];
+            tmem_ld_32x32(trow + (uint32_t)(hh * 256 + c * 32), v);
+            tmem_ld_wait();
+            if (mine) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int l = c * 32 + j;
+                if (l < p.T) dst[(size_t)l * p.Tp] = (l / p.hd == dh) ? f32_to_f16_bits(v[j]) : (uint16_t)0;
+              }
+            }
+          }
+        }
+        if (s + 2 <= s_last) arrive(hh);                         // a later round reuses this TMEM half
+        else tc_fence_before();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+
 std::atomic<unsigned long long> g_fb_launches{0};
 int g_fb_max_pairs = -1;
 unsigned long long* g_fb_prof = nullptr;
@@ -1734,6 +1955,58 @@ int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_front_kernel, tm, p));
+  }
+  MCM_CUDA(cudaGetLastError());
+  g_fb_launches.fetch_add(1);
+  return 0;
+}
+
+int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream) {
+  MCM_TRY(fb_init());
+  MCM_CHECK(a.k32 && a.v16.hi && a.ctxT.hi && a.batch > 0 && sa_tail_supported(a.T, D) && a.heads > 0 && a.T % a.heads == 0,
+            "sa ctx: bad arguments");
+  static int max_pairs = -1;
+  if (max_pairs < 0) {
+    MCM_CUDA(cudaFuncSetAttribute(sa_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    cudaLaunchConfig_t oc = {};
+    oc.gridDim = dim3(tc_num_sms() / 2 * 2);
+    oc.blockDim = dim3(THREADS);
+    oc.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute oa[1];
+    oa[0].id = cudaLaunchAttributeClusterDimension;
+    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+    oc.attrs = oa; oc.numAttrs = 1;
+    int n = 0;
+    MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, sa_ctx_kernel, &oc));
+    MCM_CHECK(n > 0, "sa_ctx_kernel does not fit on this device");
+    max_pairs = n;
+  }
+  const int T = a.T, Tp = a.ctxT.ld;
+  const int Np = (T + 15) / 16 * 16;
+  MCM_CHECK(a.v16.ld == D && Tp % 8 == 0 && Tp >= T, "sa ctx: operand layout");
+  ScMaps tm;
+  std::memset(&tm, 0, sizeof(tm));
+  MCM_TRY(tc_make_operand_map(&tm.v, a.v16.hi, OP_F16, D, T, a.batch, D, Np / 2));
+  ScParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.k32 = a.k32; p.ctxT = reinterpret_cast<uint16_t*>(a.ctxT.hi); p.Tp = Tp; p.rows = a.batch * T; p.T = T; p.Np = Np; p.hd = T / a.heads; p.nch = (T + 31) / 32; p.batch = a.batch;
+  p.n_tiles = (p.rows + 2 * ROWS - 1) / (2 * ROWS);
+  const int n_pairs = std::min(p.n_tiles, max_pairs);
+  const double flops = 2.0 * (double)a.batch * T * (T / a.heads) * D;      // only the per-head diagonal blocks are algorithmic
+  {
+    LaunchTimer lt(LK_GEMM, stream, flops);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_ctx_kernel, tm, p));
   }
   MCM_CUDA(cudaGetLastError());
   g_fb_launches.fetch_add(1);

@@ -64,6 +64,16 @@ struct SaFrontArgs {
 };
 int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream);
 
+// The middle of the channel attention: softmax of k over the 512 channel-tokens and the per-head context k^T v, written
+// block-diagonal and transposed (the B operand of the tail's q ctx GEMM); see sa_ctx_kernel in fused_block.cu.
+struct SaCtxArgs {
+  const float* k32;     // [B, T, 512] fp32 key (row = (sample, feature), 512 tokens contiguous)
+  OpPtr v16;            // [B, T, 512] fp16 value operand
+  OpPtr ctxT;           // out: [B, T, Tp] fp16, ctxT[b][l][d]; pad columns stay zero
+  int T, batch, heads;
+};
+int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream);
+
 // true if the fused kernel covers this architecture (latent 512, ffn 1024, 4 heads, T >= 52)
 bool fused_block_supported(int T, int D, int F, int H);
 size_t fused_block_hid_bytes();

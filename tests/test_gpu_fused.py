@@ -68,7 +68,7 @@ def test_fused_matches_unfused_on_ragged_tiles(T, B):
     unfused = eng.block_forward(0, 0, h0, emb)
     eng.set_option("fused", 1)
     assert C.rel_l2(unfused, want) < TOL
-    for sa_level in (0, 1, 2):      # channel attention: separate kernels / fused tail / fused head and tail
+    for sa_level in (0, 1, 2, 3):   # channel attention: separate kernels / fused tail / + fused head / + fused context
         eng.set_option("fused_sa", sa_level)
         fused = eng.block_forward(0, 0, h0, emb)
         assert C.rel_l2(fused, want) < TOL, sa_level
@@ -115,12 +115,12 @@ def test_channel_attention_fusion_levels(T, B):
     sd, h0, emb, xf_out, eng = _setup(T, B)
     want = C.block_stages(sd, h0, emb, xf_out)["out"]
     outs = {}
-    for lvl in (0, 1, 2):
+    for lvl in (0, 1, 2, 3):
         eng.set_option("fused_sa", lvl)
         outs[lvl] = eng.block_forward(0, 0, h0, emb)
         assert C.rel_l2(outs[lvl], want) < TOL, lvl
         assert torch.equal(outs[lvl], eng.block_forward(0, 0, h0, emb)), "deterministic"
-    assert C.rel_l2(outs[1], outs[0]) < 5e-4 and C.rel_l2(outs[2], outs[0]) < 5e-4
+    assert all(C.rel_l2(outs[lvl], outs[0]) < 5e-4 for lvl in (1, 2, 3))
     eng.close()
 
 

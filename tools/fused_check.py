@@ -67,7 +67,7 @@ def main():
     eng.set_option("fused_stop", 0)
     out = eng.block_forward(0, 0, h0, emb)
     print(f"fused block vs fp64: {rel(out, h_out):.3e}   vs unfused: {rel(out, ref_block):.3e}", flush=True)
-    for lvl in (0, 1, 2):
+    for lvl in (0, 1, 2, 3):
         eng.set_option("fused_sa", lvl)
         o = eng.block_forward(0, 0, h0, emb)
         print(f"fused CA/FFN, channel-attention fusion level {lvl} vs fp64: {rel(o, h_out):.3e}", flush=True)
