@@ -338,7 +338,6 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
 
 // ---- E3 / E6: h[rows, 256 columns of this warp] += acc + bias, 32 x 32 fp32 tiles through the warp's staging slot
 // (two 4 KB halves... the slot is 4 KB, so a tile waits for the previous reduction to have READ the slot)
-__device__ __forceinline__ void tma_wait_read3() { asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); }
 // `stg4`: 16 KB of the (idle) operand tile private to this warp = 4 rotating 4 KB slots, so a tile only waits for the
 // reduction issued 4 tiles earlier to have read its slot.
 __device__ __forceinline__ void epi_reduce_h(uint32_t trow, int part, uint32_t stg4, const CUtensorMap* map, int grow0,
@@ -1554,7 +1553,7 @@ sa_ctx_kernel(const __grid_constant__ ScMaps tm, const __grid_constant__ ScParam
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t opa = smem_base, ring = smem_base + OPA_BYTES, stg = ring + RING_BYTES;
+  const uint32_t opa = smem_base, ring = smem_base + OPA_BYTES;
   const int rank = (int)cluster_ctarank();
   const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
   const uint32_t slab_b = (uint32_t)(p.Np / 2) * 128u;
