@@ -70,7 +70,9 @@ void mcm_destroy(mcm_ctx* ctx);
  *   "fused" 1 = cross-attention + FFN of a layer in one persistent kernel (default; same arithmetic, fp32 reduction
  *               order of the LayerNorm statistics differs), 0 = one kernel per GEMM / row op
  *   "fused_sa" channel attention: 0 = separate kernels, 1 = fused tail kernel, 2 = fused head and tail (default),
- *               3 = also the token softmax + context in one kernel (experimental, slower) */
+ *               3 = also the token softmax + context in one kernel (experimental, slower)
+ *   "fused_min_rows" n = use the persistent fused kernels only for launches of at least n rows (B*T, per
+ *               stream: half the batch with "dual"); default 2048.  Results of the two schedules agree to ~2e-4, not bit for bit */
 int mcm_set_option(mcm_ctx* ctx, const char* name, int value);
 
 /* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key

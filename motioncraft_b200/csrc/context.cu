@@ -65,6 +65,8 @@ struct mcm_ctx {
   int fused_sa = 2;       // MCM_FUSED_SA: 0 = channel attention as separate kernels, 1 = fused tail, 2 = + fused head (default),
                           // 3 = + fused token softmax / context (parity-green, but 135 us vs 74 us for the two kernels it
                           //     replaces: its per-sample rounds serialise behind the row softmax; opt-in until reworked)
+  int fused_min_rows = 2048;   // the persistent tile kernels need enough 256-row tiles to fill the 74 CTA pairs: below this
+                               // many rows (B*T) per launch the kernel-per-op path is faster (B=1: 66 vs 75 ms per 50-step run)
   int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
   void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
@@ -259,7 +261,8 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
   const OpPtr hop = view(w.hop, D);
 
   // ---- channel attention (EfficientSelfAttention on x^T, efficient_attention.py:25-46) ----
-  const bool sa_fused = c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D) && H == 4 && 32 * Tp * 2 <= 16384;
+  const bool big = (long long)B * T >= c->fused_min_rows || c->fused_stop != 0;
+  const bool sa_fused = big && c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D) && H == 4 && 32 * Tp * 2 <= 16384;
   if (sa_fused && c->fused_sa >= 2) {
     // ---- LN_T(h^T) -> q | k | v -> softmax(q): one persistent kernel (fused_block.cu); k (fp32) and v go back to [B, T', D]
     SaFrontArgs a;
@@ -354,7 +357,7 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
   }
   }   // unfused channel-attention tail
 
-  if (c->fused && ff == OP_F16 && w.hid != nullptr && fused_block_supported(T, D, F, H)) {
+  if (big && c->fused && ff == OP_F16 && w.hid != nullptr && fused_block_supported(T, D, F, H)) {
     // ---- cross attention + FFN in ONE persistent kernel (fused_block.cu) ----
     FusedBlockArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -559,7 +562,7 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
   MCM_TRY(fill_timesteps_launch(c->t_buf, (long long)t, B, gs));
   cudaGraphExec_t exec = nullptr;
   for (auto& g : c->graphs)
-    if (g.B == B && g.have_c == c->have_c && g.fused == c->fused + 2 * c->fused_sa) {
+    if (g.B == B && g.have_c == c->have_c && g.fused == c->fused + 2 * c->fused_sa + 16 * c->fused_min_rows) {
       exec = g.exec;
       gemm_tc_count_replayed(g.n_gemm);          // keep the library's launch counters truthful under graph replay
       elementwise_count_replayed(g.n_row);
@@ -580,7 +583,7 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     MCM_CUDA(ie);
-    c->graphs.push_back({B, c->have_c, c->fused + 2 * c->fused_sa, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
+    c->graphs.push_back({B, c->have_c, c->fused + 2 * c->fused_sa + 16 * c->fused_min_rows, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
                          fused_block_launch_count() - f0});
   }
   MCM_CUDA(cudaGraphLaunch(exec, gs));
@@ -719,6 +722,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   }
   if (const char* e = getenv("MCM_FUSED")) c->fused = atoi(e);
   if (const char* e = getenv("MCM_FUSED_SA")) c->fused_sa = atoi(e);
+  if (const char* e = getenv("MCM_FUSED_MIN_ROWS")) c->fused_min_rows = atoi(e);
   c->ws[0].hid = nullptr;
   if (!lo && fused_block_supported(c->T, c->D, c->F, c->H)) {
     if (dev_alloc(c, &c->ws[0].hid, fused_block_hid_bytes())) return fail(0);
@@ -781,6 +785,8 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     c->fused = value;
   } else if (n == "fused_sa") {
     c->fused_sa = value;
+  } else if (n == "fused_min_rows") {
+    c->fused_min_rows = value;
   } else if (n == "fused_stop") {
     MCM_CHECK(value >= 0 && value <= 7, "fused_stop must be 0..7");
     c->fused_stop = value;

@@ -28,6 +28,7 @@ def _setup(T, B, layers=1):
     xf_out = torch.randn(B, 77, 256, generator=g)
     xf_proj = torch.randn(B, 2048, generator=g)
     eng = DenoiserEngine(sd, seq_len=T, num_layers=layers, max_batch=B)
+    eng.set_option("fused_min_rows", 0)      # by default launches below 2048 rows take the kernel-per-op path
     eng.prepare_conditions(xf_out, xf_proj)
     return sd, h0, emb, xf_out, eng
 
@@ -84,6 +85,7 @@ def test_sampler_fused_and_unfused_vs_reference_golden(golden_dir, fused):
     g = np.load(os.path.join(golden_dir, "t2m_T60.npz"))
     x, xf_out, xf_proj = C.inputs(1, 60)
     eng = DenoiserEngine(C.hot(C.base_state(60)), seq_len=60, max_batch=1)
+    eng.set_option("fused_min_rows", 0)
     eng.set_option("fused", fused)
     eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda())
     tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
@@ -137,6 +139,7 @@ def test_control_branch_fused_vs_unfused_vs_oracle():
         want = O.control_forward(sd, x, t, xf_proj, xf_out, c)
     eng = DenoiserEngine(modules.engine_state_from_ctrl(sd), seq_len=T, max_batch=B, num_ctrl_blocks=n_ctrl,
                          ctrl_cond_feats=c_feats)
+    eng.set_option("fused_min_rows", 0)
     eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda(), c.cuda())
     outs = []
     for fused in (1, 0):
@@ -144,4 +147,20 @@ def test_control_branch_fused_vs_unfused_vs_oracle():
         outs.append(eng.denoise(x.cuda(), 640))
         assert C.rel_l2(outs[-1], want) < TOL, fused
     assert C.rel_l2(outs[0], outs[1]) < 5e-4
+    eng.close()
+
+
+def test_small_launches_take_the_kernel_per_op_path():
+    """Below `fused_min_rows` rows per launch the persistent tile kernels cannot fill the 74 CTA pairs and the library
+    schedules the kernel-per-op sequence instead (B=1: 66 vs 75 ms per 50-step run); the switch must not change results
+    beyond the fused / unfused difference and must follow the option."""
+    T, B = 196, 2
+    sd, h0, emb, xf_out, eng = _setup(T, B)
+    fused = eng.block_forward(0, 0, h0, emb)                      # _setup set fused_min_rows = 0
+    eng.set_option("fused_min_rows", 2048)
+    small = eng.block_forward(0, 0, h0, emb)
+    eng.set_option("fused", 0)
+    unfused = eng.block_forward(0, 0, h0, emb)
+    assert torch.equal(small, unfused), "392 rows < 2048: the default policy must pick the kernel-per-op path"
+    assert not torch.equal(fused, unfused) and C.rel_l2(fused, unfused) < 5e-4
     eng.close()

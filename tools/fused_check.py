@@ -35,6 +35,7 @@ def main():
     xf_proj = torch.randn(B, 2048, generator=g)
     eng = DenoiserEngine(sd, seq_len=T, num_layers=1, max_batch=B)
     eng.prepare_conditions(xf_out, xf_proj)
+    eng.set_option("fused_min_rows", 0)
     eng.set_option("dual", 0)
     eng.set_option("graph", 0)
 

@@ -8,7 +8,7 @@ from motioncraft_b200.engine import DenoiserEngine
 B, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 256), 196
 sd = {k: v for k, v in synth.synth_state_dict(modules.state_shapes(seq_len=T, num_layers=1)).items() if ".ffn_channel." not in k}
 eng = DenoiserEngine(sd, seq_len=T, max_batch=B, num_layers=1)
-eng.set_option("dual", 0); eng.set_option("graph", 0); eng.set_option("fused_sa", 2)
+eng.set_option("dual", 0); eng.set_option("graph", 0); eng.set_option("fused_sa", 2); eng.set_option("fused_min_rows", 0)
 g = torch.Generator().manual_seed(0)
 h = torch.randn(B, T, 512, generator=g).cuda(); emb = torch.randn(B, 2048, generator=g).cuda()
 eng.prepare_conditions(torch.randn(B, 77, 256, generator=g).cuda(), torch.randn(B, 2048, generator=g).cuda())
