@@ -1111,9 +1111,12 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
         }
         // transposed tile: [t][n], lanes (= channels n) contiguous; the output bias bo[t] is a broadcast read
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float o = v[j] + prm[2 * Tq + c * 32 + j];
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sl + (uint32_t)(j * 32 + lane) * 4u), "f"(o) : "memory");
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(prm + 2 * Tq + c * 32 + 4 * q4);
+          const float o[4] = {v[4 * q4] + b4.x, v[4 * q4 + 1] + b4.y, v[4 * q4 + 2] + b4.z, v[4 * q4 + 3] + b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sl + (uint32_t)((4 * q4 + e) * 32 + lane) * 4u), "f"(o[e]) : "memory");
         }
         fence_async_smem();
         __syncwarp();
@@ -1320,7 +1323,9 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
 #define SF_TICK(i) do { if (prof) { const long long _n = clock64(); tph[i] += _n - tlast; tlast = _n; } } while (0)
     const int T2 = ((p.T + 1) / 2 + 7) / 8 * 8;               // frames [0, T2) to warps 0..3, [T2, T) to warps 4..7
     const int t_lo = part * T2, t_hi = part == 0 ? T2 : p.T;
-    const int t_end = part == 0 ? T2 : p.nkb * 64;            // warps 4..7 also write the zero K padding
+    const int Tr8 = (p.T + 7) / 8 * 8;
+    const int t_end = part == 0 ? T2 : Tr8;                   // the zero K padding [Tr8, nkb * 64) is written by warps 0..3,
+                                                              // which have the shorter half of the frames
 #pragma unroll 1
     for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
       const int b = tile >> 1;
@@ -1355,6 +1360,8 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
         const float mean = mean_w + delta * (n_o / (float)p.T);
         const float m2 = (m2_w + m2_o) + delta * delta * (n_mine * n_o / (float)p.T);
         const float rstd = rsqrtf(m2 / (float)p.T + 1e-5f);
+        if (part == 0)
+          for (int t8 = Tr8; t8 < p.nkb * 64; t8 += 8) st_shared_v4u(opa_addr(opa, row, t8), 0u, 0u, 0u, 0u);
 #pragma unroll 1
         for (int t0 = t_lo; t0 < t_end; t0 += 32) {
           float x[32];
@@ -1364,14 +1371,16 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
           for (int g8 = 0; g8 < 4; ++g8) {
             const int t8 = t0 + 8 * g8;
             if (t8 < t_end) {
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int t = t8 + e;
-                y[e] = (t < p.T) ? fmaf((x[8 * g8 + e] - mean) * rstd, prm[t], prm[Tq + t]) : 0.f;
-              }
-              st_shared_v4u(opa_addr(opa, row, t8), pack_f16x2_sat(y[0], y[1]), pack_f16x2_sat(y[2], y[3]),
-                            pack_f16x2_sat(y[4], y[5]), pack_f16x2_sat(y[6], y[7]));
+              // gamma / beta are zero beyond T (staged that way) and x is 0 there: (0 - mean) rstd * 0 + 0 = 0 exactly
+              const float4 ga = *reinterpret_cast<const float4*>(prm + t8), gb = *reinterpret_cast<const float4*>(prm + t8 + 4);
+              const float4 ba = *reinterpret_cast<const float4*>(prm + Tq + t8), bb = *reinterpret_cast<const float4*>(prm + Tq + t8 + 4);
+              const float* xx = x + 8 * g8;
+              const float y0 = fmaf((xx[0] - mean) * rstd, ga.x, ba.x), y1 = fmaf((xx[1] - mean) * rstd, ga.y, ba.y);
+              const float y2 = fmaf((xx[2] - mean) * rstd, ga.z, ba.z), y3 = fmaf((xx[3] - mean) * rstd, ga.w, ba.w);
+              const float y4 = fmaf((xx[4] - mean) * rstd, gb.x, bb.x), y5 = fmaf((xx[5] - mean) * rstd, gb.y, bb.y);
+              const float y6 = fmaf((xx[6] - mean) * rstd, gb.z, bb.z), y7 = fmaf((xx[7] - mean) * rstd, gb.w, bb.w);
+              st_shared_v4u(opa_addr(opa, row, t8), pack_f16x2_sat(y0, y1), pack_f16x2_sat(y2, y3), pack_f16x2_sat(y4, y5),
+                            pack_f16x2_sat(y6, y7));
             }
           }
         }
@@ -1463,9 +1472,12 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
           tmem_ld_wait();
           drain();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float o = v[j] + prm[3 * Tq + c * 32 + j];
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg_mine + (uint32_t)(j * 32 + lane) * 4u), "f"(o) : "memory");
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(prm + 3 * Tq + c * 32 + 4 * q4);
+            const float o[4] = {v[4 * q4] + b4.x, v[4 * q4 + 1] + b4.y, v[4 * q4 + 2] + b4.z, v[4 * q4 + 3] + b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg_mine + (uint32_t)((4 * q4 + e) * 32 + lane) * 4u), "f"(o[e]) : "memory");
           }
           fence_async_smem();
           __syncwarp();
@@ -1488,9 +1500,14 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
         tmem_ld_wait();
         drain();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint16_t o = f32_to_f16_bits(v[j] + prm[4 * Tq + c * 32 + j]);
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg_mine + (uint32_t)(j * 32 + lane) * 2u), "h"(o) : "memory");
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(prm + 4 * Tq + c * 32 + 4 * q4);
+          const float o[4] = {v[4 * q4] + b4.x, v[4 * q4 + 1] + b4.y, v[4 * q4 + 2] + b4.z, v[4 * q4 + 3] + b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint16_t h16 = f32_to_f16_bits(o[e]);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg_mine + (uint32_t)((4 * q4 + e) * 32 + lane) * 2u), "h"(h16) : "memory");
+          }
         }
         fence_async_smem();
         __syncwarp();
