@@ -1764,10 +1764,12 @@ std::atomic<unsigned long long> g_fb_launches{0};
 int g_fb_max_pairs = -1;
 unsigned long long* g_fb_prof = nullptr;
 
-int fb_init() {
-  if (g_fb_max_pairs >= 0) return 0;
-  MCM_TRY(gemm_tc_init());
-  MCM_CUDA(cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+// All four kernels of this file are persistent CTA-pair kernels with the same launch shape: cluster of 2, THREADS
+// threads, SMEM_BYTES of dynamic shared memory, one pair per SM pair, programmatic dependent launch.
+template <typename K>
+int pair_capacity(K kernel, int* cached, const char* name) {
+  if (*cached > 0) return 0;
+  MCM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tc_num_sms() / 2 * 2);
   cfg.blockDim = dim3(THREADS);
@@ -1777,8 +1779,42 @@ int fb_init() {
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, fused_block_kernel, &cfg));
-  MCM_CHECK(n > 0, "fused_block_kernel does not fit on this device");
+  MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+  if (n <= 0) {
+    set_error(std::string(name) + " does not fit on this device");
+    return 1;
+  }
+  *cached = n;
+  return 0;
+}
+
+template <typename K, typename M, typename P>
+int launch_pairs(K kernel, int n_pairs, int kind, double flops, const M& maps, const P& params, cudaStream_t stream) {
+  {
+    LaunchTimer lt(kind, stream, flops);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    MCM_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, params));
+  }
+  MCM_CUDA(cudaGetLastError());
+  g_fb_launches.fetch_add(1);
+  return 0;
+}
+
+int fb_init() {
+  if (g_fb_max_pairs >= 0) return 0;
+  MCM_TRY(gemm_tc_init());
+  int n = 0;
+  MCM_TRY(pair_capacity(fused_block_kernel, &n, "fused_block_kernel"));
   g_fb_max_pairs = n;
   if (const char* e = getenv("MCM_FUSED_PROF")) {
     if (e[0] == '1') {
@@ -1844,24 +1880,7 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
 
   // algorithmic flops of the two sub-blocks (AdaLN emb GEMM is not in this kernel)
   const double flops = 2.0 * (double)a.rows * ((double)D * D * 2 + (double)D * HD + 2.0 * D * F + (double)D * D);
-  {
-    LaunchTimer lt(LK_FUSED, stream, flops);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    MCM_CUDA(cudaLaunchKernelEx(&cfg, fused_block_kernel, tm, p));
-  }
-  MCM_CUDA(cudaGetLastError());
-  g_fb_launches.fetch_add(1);
-  return 0;
+  return launch_pairs(fused_block_kernel, n_pairs, LK_FUSED, flops, tm, p, stream);
 }
 
 bool sa_tail_supported(int T, int Dm) { return NCW == 8 && Dm == D && T >= 40 && T <= 256 && T % 4 == 0; }
@@ -1870,21 +1889,7 @@ int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
   MCM_TRY(fb_init());
   MCM_CHECK(a.h && a.qs.hi && a.ctxT.hi && a.wo.hi && a.batch > 0 && sa_tail_supported(a.T, D), "sa tail: bad arguments");
   static int max_pairs = -1;
-  if (max_pairs < 0) {
-    MCM_CUDA(cudaFuncSetAttribute(sa_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    cudaLaunchConfig_t oc = {};
-    oc.gridDim = dim3(tc_num_sms() / 2 * 2);
-    oc.blockDim = dim3(THREADS);
-    oc.dynamicSmemBytes = SMEM_BYTES;
-    cudaLaunchAttribute oa[1];
-    oa[0].id = cudaLaunchAttributeClusterDimension;
-    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
-    oc.attrs = oa; oc.numAttrs = 1;
-    int n = 0;
-    MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, sa_tail_kernel, &oc));
-    MCM_CHECK(n > 0, "sa_tail_kernel does not fit on this device");
-    max_pairs = n;
-  }
+  MCM_TRY(pair_capacity(sa_tail_kernel, &max_pairs, "sa_tail_kernel"));
   const int T = a.T, Tp = a.qs.ld;
   const int Np = (T + 15) / 16 * 16;
   MCM_CHECK(a.ctxT.ld == Tp && a.wo.ld == Tp && Tp % 8 == 0 && Tp >= T, "sa tail: operand pitch");
@@ -1900,24 +1905,7 @@ int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
   p.mod_ld = a.mod_ld; p.pn_w = a.pn_w; p.pn_b = a.pn_b; p.scale = a.scale; p.shift = a.shift; p.bo = a.bo;
   const int n_pairs = std::min(p.n_tiles, max_pairs);
   const double flops = 2.0 * (double)a.batch * D * ((double)T * (T / 4) + (double)T * T);   // q ctx (per head) + out
-  {
-    LaunchTimer lt(LK_GEMM, stream, flops);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * n_pairs);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_tail_kernel, tm, p));
-  }
-  MCM_CUDA(cudaGetLastError());
-  g_fb_launches.fetch_add(1);
-  return 0;
+  return launch_pairs(sa_tail_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
 }
 
 // generic [d0 contiguous, d1, d2] tensor map with an explicit box (the E_q row store: box {Tp, 32, 1}, no swizzle)
@@ -1925,21 +1913,7 @@ int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream) {
   MCM_TRY(fb_init());
   MCM_CHECK(a.h && a.w.hi && a.qs.hi && a.k32 && a.v16.hi && a.batch > 0 && sa_tail_supported(a.T, D), "sa front: bad arguments");
   static int max_pairs = -1;
-  if (max_pairs < 0) {
-    MCM_CUDA(cudaFuncSetAttribute(sa_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    cudaLaunchConfig_t oc = {};
-    oc.gridDim = dim3(tc_num_sms() / 2 * 2);
-    oc.blockDim = dim3(THREADS);
-    oc.dynamicSmemBytes = SMEM_BYTES;
-    cudaLaunchAttribute oa[1];
-    oa[0].id = cudaLaunchAttributeClusterDimension;
-    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
-    oc.attrs = oa; oc.numAttrs = 1;
-    int n = 0;
-    MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, sa_front_kernel, &oc));
-    MCM_CHECK(n > 0, "sa_front_kernel does not fit on this device");
-    max_pairs = n;
-  }
+  MCM_TRY(pair_capacity(sa_front_kernel, &max_pairs, "sa_front_kernel"));
   const int T = a.T, Tp = a.w.ld;
   const int Np = (T + 15) / 16 * 16;
   MCM_CHECK(a.qs.ld == Tp && Tp % 8 == 0 && Tp >= T && a.v16.ld == D && a.heads == H && T % H == 0 && 32 * Tp * 2 <= SLAB,
@@ -1957,24 +1931,7 @@ int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream) {
   p.prof = (g_fb_prof != nullptr && getenv("MCM_SF_PROF") != nullptr) ? g_fb_prof : nullptr;
   const int n_pairs = std::min(p.n_tiles, max_pairs);
   const double flops = 2.0 * (double)a.batch * D * (double)T * 3.0 * T;
-  {
-    LaunchTimer lt(LK_GEMM, stream, flops);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * n_pairs);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_front_kernel, tm, p));
-  }
-  MCM_CUDA(cudaGetLastError());
-  g_fb_launches.fetch_add(1);
-  return 0;
+  return launch_pairs(sa_front_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
 }
 
 int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream) {
@@ -1982,21 +1939,7 @@ int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream) {
   MCM_CHECK(a.k32 && a.v16.hi && a.ctxT.hi && a.batch > 0 && sa_tail_supported(a.T, D) && a.heads > 0 && a.T % a.heads == 0,
             "sa ctx: bad arguments");
   static int max_pairs = -1;
-  if (max_pairs < 0) {
-    MCM_CUDA(cudaFuncSetAttribute(sa_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    cudaLaunchConfig_t oc = {};
-    oc.gridDim = dim3(tc_num_sms() / 2 * 2);
-    oc.blockDim = dim3(THREADS);
-    oc.dynamicSmemBytes = SMEM_BYTES;
-    cudaLaunchAttribute oa[1];
-    oa[0].id = cudaLaunchAttributeClusterDimension;
-    oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
-    oc.attrs = oa; oc.numAttrs = 1;
-    int n = 0;
-    MCM_CUDA(cudaOccupancyMaxActiveClusters(&n, sa_ctx_kernel, &oc));
-    MCM_CHECK(n > 0, "sa_ctx_kernel does not fit on this device");
-    max_pairs = n;
-  }
+  MCM_TRY(pair_capacity(sa_ctx_kernel, &max_pairs, "sa_ctx_kernel"));
   const int T = a.T, Tp = a.ctxT.ld;
   const int Np = (T + 15) / 16 * 16;
   MCM_CHECK(a.v16.ld == D && Tp % 8 == 0 && Tp >= T, "sa ctx: operand layout");
@@ -2009,24 +1952,7 @@ int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream) {
   p.n_tiles = (p.rows + 2 * ROWS - 1) / (2 * ROWS);
   const int n_pairs = std::min(p.n_tiles, max_pairs);
   const double flops = 2.0 * (double)a.batch * T * (T / a.heads) * D;      // only the per-head diagonal blocks are algorithmic
-  {
-    LaunchTimer lt(LK_GEMM, stream, flops);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * n_pairs);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    MCM_CUDA(cudaLaunchKernelEx(&cfg, sa_ctx_kernel, tm, p));
-  }
-  MCM_CUDA(cudaGetLastError());
-  g_fb_launches.fetch_add(1);
-  return 0;
+  return launch_pairs(sa_ctx_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
 }
 
 }  // namespace mcm
