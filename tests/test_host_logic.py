@@ -169,3 +169,41 @@ def test_wav_encoder_matches_reference_golden(golden_dir):
     with pytest.raises(McmError):
         ConditionEncoder(dict(dataset_name="finedance", condition_pre_encode_type="wav", condition_latent_dim=32,
                               control_cond_feats=2))
+
+
+def test_repaint_front_end_argument_checks():
+    """Host logic of the outpainting branch of SpacedDiffusion.ddim_sample_loop: everything it needs from the tools' `opt`
+    namespace, and every unsupported combination, is reported as McmError before any device work."""
+    import argparse
+    from motioncraft_b200 import scheduler
+    cfg = dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon", model_var_type="fixed_small",
+               respace="15,15,8,6,6")
+    y = {"gt": torch.zeros(60, 322), "outpainting_mask": torch.ones(60, 322, dtype=torch.bool)}
+    opt = argparse.Namespace(no_repaint=False, same_overlap_noisy=False, addBlend=True, overlap_len=10, no_resample=False,
+                             timestep_respacing="ddim50", jump_length=3, jump_n_sample=5)
+    with pytest.raises(McmError, match="opt"):                         # the reference dereferences self.opt (:962)
+        diffusion.build_diffusion(cfg).ddim_sample_loop(None, (1, 60, 322), clip_denoised=False, model_kwargs={"y": y})
+    d = diffusion.build_diffusion(cfg, opt=opt)
+    with pytest.raises(McmError, match="eta"):
+        d.ddim_sample_loop(None, (1, 60, 322), clip_denoised=False, model_kwargs={"y": y}, eta=0.5)
+    with pytest.raises(McmError, match="gt"):
+        d.ddim_sample_loop(None, (1, 60, 322), clip_denoised=False,
+                           model_kwargs={"y": {"outpainting_mask": y["outpainting_mask"]}})
+    opt1000 = argparse.Namespace(**{**vars(opt), "timestep_respacing": "ddim1000"})   # the tools' default: 600 > 50 steps
+    with pytest.raises(McmError, match="schedule"):
+        diffusion.build_diffusion(cfg, opt=opt1000).ddim_sample_loop(None, (1, 60, 322), clip_denoised=False,
+                                                                     model_kwargs={"y": y})
+    noisy = argparse.Namespace(**{**vars(opt), "same_overlap_noisy": True})
+    with pytest.raises(McmError, match="same_overlap_noisy"):
+        diffusion.build_diffusion(cfg, opt=noisy).ddim_sample_loop(None, (1, 60, 322), clip_denoised=False,
+                                                                   model_kwargs={"y": y})
+    # an all-False mask is the plain sampler (gaussian_diffusion.py:962: `True in outpainting_mask`): reaches the model bind
+    with pytest.raises(AttributeError):
+        d.ddim_sample_loop(None, (1, 60, 322), clip_denoised=False,
+                           model_kwargs={"y": {"gt": y["gt"], "outpainting_mask": torch.zeros(60, 322, dtype=torch.bool)}})
+    # schedule bookkeeping
+    times = scheduler.get_schedule_jump_cjm_ddim(50, jump_length=3, jump_n_sample=5)
+    n_den = sum(1 for a, b in zip(times[:-1], times[1:]) if b < a)
+    assert (n_den, len(times) - 1 - n_den) == (138, 108) and scheduler.count_draws(times, 50) == 2 * 138 + 108
+    assert scheduler.get_schedule_jump_cjm_ddim(25)[0] == 14 and scheduler.get_schedule_jump_cjm_ddim(50)[0] == 29
+    assert scheduler.get_schedule_jump_cjm_ddim(50) == list(range(29, -2, -1))      # no resampling: straight walk down
