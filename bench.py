@@ -178,11 +178,174 @@ def run_reference_arm(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, wl, world):
-    return {"workload": f"{args.workload}: synthetic (B={wl['B']}/GPU x T={wl['T']} x 322), 50-step DDIM eta=0 respace "
+def workload_config(args, wl, world, name=None):
+    return {"workload": f"{name or args.workload}: synthetic (B={wl['B']}/GPU x T={wl['T']} x 322), 50-step DDIM eta=0 respace "
                         f"'{RESPACE}', MCMTransformer 8 layers" + (f" + {wl['n_ctrl']} control blocks" if wl["n_ctrl"] else ""),
             "global_batch": wl["B"] * world, "seq_len": wl["T"], "parallelism": f"dp{world} (batch shards, one all-gather)",
             "l2": "per-step working set (>1 GB activations + 124 MB weights) exceeds the 126 MB L2; no explicit flush"}
+
+
+def build_engine_and_inputs(wl, rank, world, dev, precise=False):
+    import torch
+    from motioncraft_b200 import dist as mdist, modules, synth
+    from motioncraft_b200.engine import DenoiserEngine
+    B, T = wl["B"], wl["T"]
+    n_total = B * world
+    lo, hi = mdist.shard_range(n_total, rank, world)
+    # synthetic weights (replicated) and this rank's rows of the globally seeded inputs
+    if wl["n_ctrl"]:
+        sd = modules.engine_state_from_ctrl(synth.synth_state_dict(modules.ctrl_state_shapes(T, wl["n_ctrl"], wl["c_feats"])))
+    else:
+        sd = {k: v for k, v in synth.synth_state_dict(modules.state_shapes(seq_len=T)).items() if ".ffn_channel." not in k}
+    x_T = synth.synth_rows("x_T", (T, 322), synth.SEED_XT, lo, hi)
+    xf_out = synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, lo, hi)
+    xf_proj = synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, lo, hi)
+    c = synth.synth_rows("c", (wl["c_len"], wl["c_feats"]), synth.SEED_C_EMB, lo, hi) if wl["n_ctrl"] else None
+    eng = DenoiserEngine(sd, seq_len=T, max_batch=B, num_ctrl_blocks=wl["n_ctrl"], ctrl_cond_feats=wl["c_feats"],
+                         precise_all=precise, device=dev)
+    del sd
+    return eng, x_T, xf_out, xf_proj, c, n_total
+
+
+def measure_workload(args, name, wl, rank, local_rank, world, dev, steps, warmup, with_clocks):
+    """Times `steps` complete sampling runs of one workload; returns the numbers of its JSON block (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    from motioncraft_b200 import _lib
+    from motioncraft_b200 import dist as mdist
+    from motioncraft_b200.diffusion import build_diffusion
+    from motioncraft_b200.engine import SamplerTables
+
+    B, T = wl["B"], wl["T"]
+    eng, x_T, xf_out, xf_proj, c, n_total = build_engine_and_inputs(wl, rank, world, dev, args.precise)
+    d = build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                             model_var_type="fixed_small", respace=RESPACE))
+    tables = SamplerTables(d._tables(), d.timestep_map, "ddim", 0.0)
+    x_dev = x_T.to(dev)
+    # host side of the end-to-end leg: EVERYTHING a caller hands over lives in pinned host memory
+    x_pin = x_T.pin_memory()
+    out_pin = torch.empty_like(x_pin).pin_memory()
+    cond_pin = [t.pin_memory() if t is not None else None for t in (xf_out, xf_proj, c)]
+    cond = tuple(t.to(dev) if t is not None else None for t in (xf_out, xf_proj, c))
+    full_pin = torch.empty((n_total, T, 322), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_run_device():
+        # the step-invariant condition work is part of every sampling run (counted in the algorithmic FLOPs)
+        eng.prepare_conditions(*cond)
+        x0 = eng.sample(tables, x_dev)
+        return mdist.gather_rows(x0, n_total) if world > 1 else x0
+
+    def one_run_host():
+        # H2D of the conditions, then the host-buffer C-ABI call (H2D x_T + loop + D2H x_0)
+        cd = [t.to(dev, non_blocking=True) if t is not None else None for t in cond_pin]
+        eng.prepare_conditions(*cd)
+        if world == 1:
+            return eng.sample_host(tables, x_pin, out_pin)
+        # N > 1: the result every caller receives is the GATHERED batch: H2D, loop, one NCCL all-gather, D2H on rank 0
+        x0 = eng.sample(tables, x_pin.to(dev, non_blocking=True))
+        full = mdist.gather_rows(x0, n_total)
+        if rank == 0:
+            full_pin.copy_(full, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return full_pin
+
+    for _ in range(warmup):
+        one_run_device()
+    barrier()
+    clocks = ClockSampler(local_rank) if with_clocks else None
+    if clocks is not None and rank == 0:
+        clocks.start()
+    launches0 = _lib.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        one_run_device()
+    ev1.record()
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    launches = _lib.kernel_launches() - launches0
+    clk = clocks.stop() if (clocks is not None and rank == 0) else None
+
+    # ---- end-to-end through the host-buffer C-ABI call (H2D + loop + D2H inside the timed region)
+    one_run_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_run_host()
+    torch.cuda.synchronize(dev)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+
+    # ---- roofline leg: separate instrumented run (events around every launch), not part of the numbers above
+    # (single stream, eager launches: with the two-stream schedule of the timed region kernels of different streams
+    # share the SMs, so per-kernel event times would no longer be times of a kernel running alone)
+    dual_default = os.environ.get("MCM_DUAL", "1") != "0"
+    eng.set_option("dual", 0)
+    _lib.timing_enable(True)
+    one_run_device()
+    tm = _lib.timing_collect()
+    _lib.timing_enable(False)
+    eng.set_option("dual", 1 if dual_default else 0)
+    eng.close()
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+
+    frames = n_total * T * steps
+    value = frames / (ms_dev * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    per_step, once = algorithmic_flops(T, wl["n_ctrl"], c_feats=wl["c_feats"], c_len=wl["c_len"])
+    flops_run = B * (N_STEPS * per_step + once)            # per GPU per sampling run
+    peaks = measured_peaks()
+    gemm_ms = tm["gemm"]["ms"] + tm["fused"]["ms"]          # every tcgen05 kernel of the run
+    all_tc = flops_run / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    whole = flops_run / (ms_dev / steps * 1e-3) / 1e12
+    fz = tm["fused"]
+    if fz["launches"] > 0:
+        # dominant kernel: the fused cross-attention + FFN token kernel (one launch per decoder layer and step).
+        # achieved = its ALGORITHMIC flops (SURVEY.md 8a rows a9 + a10 without the AdaLN emb GEMM:
+        # 2 * rows * (2*512*512 + 512*128 + 2*512*1024 + 512*512) per launch) / its CUDA-event device time
+        kernel = ("fused_block_kernel (cross-attention + FFN of one decoder layer, tcgen05 cta_group::2; all launches of "
+                  "one sampling run, timed single-stream with CUDA events around every launch)")
+        achieved = fz["flops"] / (fz["ms"] * 1e-3) / 1e12
+        dom_ms, dom_n = fz["ms"], fz["launches"]
+        # dram__bytes_read + dram__bytes_write per launch, ncu --set full (profiles/); algorithmic minimum is one read +
+        # one write of h = 2 * B*T*512*4 bytes
+        traffic = FUSED_DRAM_BYTES_PER_LAUNCH if (name == "t2m" and B == 256) else None
+        algo_bytes = 2.0 * B * T * 512 * 4
+    else:
+        kernel = "gemm_tc_kernel (tcgen05, all launches of one sampling run; timed single-stream, eager)"
+        achieved, dom_ms, dom_n, traffic, algo_bytes = all_tc, tm["gemm"]["ms"], tm["gemm"]["launches"], None, None
+    h2d = sum(int(t.numel() * 4) for t in [x_pin] + [t for t in cond_pin if t is not None])
+    d2h = int((full_pin if full_pin is not None else out_pin).numel() * 4)
+    return {
+        "value": value, "ms_per_step": ms_dev / steps, "steps": steps, "warmup": warmup,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": ("mcm_prepare_conditions + mcm_sample_host: pinned host x_T / xf_out / xf_proj / c -> x_0 in pinned host memory"
+                        if world == 1 else
+                        "pinned host inputs -> H2D -> mcm_sample -> ONE NCCL all-gather -> D2H of the gathered batch on rank 0")},
+        "gpu_launches": int(launches), "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": kernel,
+                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": (achieved / peaks["tflops"]) if achieved else None,
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "algorithmic_bytes_per_launch": algo_bytes,
+                     "peak_source": peaks["source"], "algorithmic_gflop_per_frame": flops_run / (B * T) / 1e9,
+                     "kernel_ms_per_run": dom_ms, "kernel_launches_per_run": dom_n,
+                     "kernel_share_of_device_time": dom_ms / (gemm_ms + tm["row"]["ms"]) if gemm_ms > 0 else None,
+                     "all_tcgen05_kernels_ms_per_run": gemm_ms, "all_tcgen05_kernels_achieved": all_tc,
+                     "other_tcgen05_launches_per_run": tm["gemm"]["launches"],
+                     "row_kernel_ms_per_run": tm["row"]["ms"], "row_kernel_launches_per_run": tm["row"]["launches"],
+                     "whole_step_achieved": whole, "whole_step_frac": whole / peaks["tflops"]},
+    }
 
 
 def main():
@@ -195,6 +358,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the s2g / m2d extra_workloads block (N = 1 only)")
     ap.add_argument("--precise", action="store_true", help="debug: every GEMM in bf16x2-split mode")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -209,10 +373,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from motioncraft_b200 import _lib, modules, synth
-    from motioncraft_b200 import dist as mdist
-    from motioncraft_b200.diffusion import build_diffusion
-    from motioncraft_b200.engine import DenoiserEngine, SamplerTables
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: motioncraft_b200 has no CPU fallback (use --impl reference for the CPU arm)")
@@ -221,139 +381,34 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B, T = wl["B"], wl["T"]
-    n_total = B * world
-    lo, hi = mdist.shard_range(n_total, rank, world)
 
-    # ---- synthetic weights (replicated) and this rank's rows of the globally seeded inputs
-    if wl["n_ctrl"]:
-        sd = modules.engine_state_from_ctrl(synth.synth_state_dict(modules.ctrl_state_shapes(T, wl["n_ctrl"], wl["c_feats"])))
-    else:
-        sd = {k: v for k, v in synth.synth_state_dict(modules.state_shapes(seq_len=T)).items() if ".ffn_channel." not in k}
-    x_T = synth.synth_rows("x_T", (T, 322), synth.SEED_XT, lo, hi)
-    xf_out = synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, lo, hi)
-    xf_proj = synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, lo, hi)
-    c = synth.synth_rows("c", (wl["c_len"], wl["c_feats"]), synth.SEED_C_EMB, lo, hi) if wl["n_ctrl"] else None
-
-    eng = DenoiserEngine(sd, seq_len=T, max_batch=B, num_ctrl_blocks=wl["n_ctrl"], ctrl_cond_feats=wl["c_feats"],
-                         precise_all=args.precise, device=dev)
-    del sd
-    d = build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
-                             model_var_type="fixed_small", respace=RESPACE))
-    tables = SamplerTables(d._tables(), d.timestep_map, "ddim", 0.0)
-    x_dev = x_T.to(dev)
-    x_pin = x_T.pin_memory()
-    out_pin = torch.empty_like(x_pin).pin_memory()
-    cond = (xf_out.to(dev), xf_proj.to(dev), c.to(dev) if c is not None else None)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def one_run_device():
-        # the step-invariant condition work is part of every sampling run (counted in the algorithmic FLOPs)
-        eng.prepare_conditions(*cond)
-        x0 = eng.sample(tables, x_dev)
-        return mdist.gather_rows(x0, n_total) if world > 1 else x0
-
-    def one_run_host():
-        eng.prepare_conditions(*cond)
-        out = eng.sample_host(tables, x_pin, out_pin)
-        return out
-
-    for _ in range(args.warmup):
-        one_run_device()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    launches0 = _lib.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        one_run_device()
-    ev1.record()
-    barrier()
-    ms_dev = ev0.elapsed_time(ev1)
-    launches = _lib.kernel_launches() - launches0
-    clk = clocks.stop() if rank == 0 else None
-
-    # ---- end-to-end through the host-buffer C-ABI call (H2D + loop + D2H inside the timed region)
-    one_run_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_run_host()
-        if world > 1:
-            pass  # results stay per-rank on the host; the reference's collect_results is outside this path
-    torch.cuda.synchronize(dev)
-    ms_e2e = (time.perf_counter() - t0) * 1e3
-
-    # ---- roofline leg: separate instrumented run (events around every launch), not part of the numbers above
-    # (single stream, eager launches: with the two-stream schedule of the timed region kernels of different streams
-    # share the SMs, so per-kernel event times would no longer be times of a kernel running alone)
-    dual_default = os.environ.get("MCM_DUAL", "1") != "0"
-    eng.set_option("dual", 0)
-    _lib.timing_enable(True)
-    one_run_device()
-    tm = _lib.timing_collect()
-    _lib.timing_enable(False)
-    eng.set_option("dual", 1 if dual_default else 0)
-
-    if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    main_res = measure_workload(args, args.workload, wl, rank, local_rank, world, dev, args.steps, args.warmup, True)
+    extra = {}
+    if world == 1 and not args.no_extra and args.workload == "t2m" and not args.batch:
+        # BASELINE.json configs 2 and 3 on the same box, 2 timed runs each after 3 warm-up runs, so that the driver's
+        # record carries their throughput and roofline fractions too (they are parity-test cases, not the headline)
+        for name in ("s2g", "m2d"):
+            r = measure_workload(args, name, dict(WORKLOADS[name]), rank, local_rank, world, dev, 2, 3, False)
+            extra[name] = {"value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"], "steps": 2, "warmup": 3,
+                           "config": workload_config(args, dict(WORKLOADS[name]), world, name),
+                           "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
+                           "roofline": {k: r["roofline"][k] for k in ("kernel", "achieved", "peak", "unit", "frac",
+                                                                      "kernel_share_of_device_time",
+                                                                      "all_tcgen05_kernels_achieved", "whole_step_achieved",
+                                                                      "whole_step_frac", "algorithmic_gflop_per_frame")}}
 
     if rank == 0:
-        frames = n_total * T * args.steps
-        value = frames / (ms_dev * 1e-3)
-        e2e = frames / (ms_e2e * 1e-3)
-        per_step, once = algorithmic_flops(T, wl["n_ctrl"], c_feats=wl["c_feats"], c_len=wl["c_len"])
-        flops_run = B * (N_STEPS * per_step + once)            # per GPU per sampling run
-        peaks = measured_peaks()
-        gemm_ms = tm["gemm"]["ms"] + tm["fused"]["ms"]          # every tcgen05 kernel of the run
-        all_tc = flops_run / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        whole = flops_run / (ms_dev / args.steps * 1e-3) / 1e12
-        fz = tm["fused"]
-        if fz["launches"] > 0:
-            # dominant kernel: the fused cross-attention + FFN token kernel (one launch per decoder layer and step).
-            # achieved = its ALGORITHMIC flops (SURVEY.md 8a rows a9 + a10 without the AdaLN emb GEMM:
-            # 2 * rows * (2*512*512 + 512*128 + 2*512*1024 + 512*512) per launch) / its CUDA-event device time
-            kernel = ("fused_block_kernel (cross-attention + FFN of one decoder layer, tcgen05 cta_group::2; all launches of "
-                      "one sampling run, timed single-stream with CUDA events around every launch)")
-            achieved = fz["flops"] / (fz["ms"] * 1e-3) / 1e12
-            dom_ms, dom_n = fz["ms"], fz["launches"]
-            # dram__bytes_read + dram__bytes_write per launch, ncu --set full (profiles/r01_fused_block_kernel_metrics.csv);
-            # algorithmic minimum is one read + one write of h = 2 * B*T*512*4 bytes
-            traffic = FUSED_DRAM_BYTES_PER_LAUNCH if (args.workload == "t2m" and B == 256) else None
-            algo_bytes = 2.0 * B * T * 512 * 4
-        else:
-            kernel = "gemm_tc_kernel (tcgen05, all launches of one sampling run; timed single-stream, eager)"
-            achieved, dom_ms, dom_n, traffic, algo_bytes = all_tc, tm["gemm"]["ms"], tm["gemm"]["launches"], None, None
+        B, T = wl["B"], wl["T"]
         line = {
-            "metric": "sampled motion frames/sec (50-step DDIM)", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "metric": "sampled motion frames/sec (50-step DDIM)", "value": main_res["value"], "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands (bf16x2-split for embed/out/AdaLN), f32 accumulate/residual",
             "data": "synthetic", "config": workload_config(args, wl, world),
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x_pin.numel() * 4),
-                    "d2h_bytes_per_step": int(out_pin.numel() * 4), "api": "mcm_sample_host (pinned host x_T -> x_0)"},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": kernel,
-                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tflops"]) if achieved else None,
-                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "algorithmic_bytes_per_launch": algo_bytes,
-                         "peak_source": peaks["source"], "algorithmic_gflop_per_frame": flops_run / (B * T) / 1e9,
-                         "kernel_ms_per_run": dom_ms, "kernel_launches_per_run": dom_n,
-                         "kernel_share_of_device_time": dom_ms / (gemm_ms + tm["row"]["ms"]) if gemm_ms > 0 else None,
-                         "all_tcgen05_kernels_ms_per_run": gemm_ms, "all_tcgen05_kernels_achieved": all_tc,
-                         "other_tcgen05_launches_per_run": tm["gemm"]["launches"],
-                         "row_kernel_ms_per_run": tm["row"]["ms"], "row_kernel_launches_per_run": tm["row"]["launches"],
-                         "whole_step_achieved": whole, "whole_step_frac": whole / peaks["tflops"]},
+            "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"],
+            "roofline": main_res["roofline"],
         }
+        if extra:
+            line["extra_workloads"] = extra
         if not args.no_cpu_baseline:
             B_cpu = args.cpu_batch or 64
             torch.set_num_threads(os.cpu_count() or 1)
@@ -362,7 +417,6 @@ def main():
                                     "sample": f"oracle (bit-identical restatement of mogen's CPU path): B={B_cpu} x 25 of 50 "
                                               f"DDIM steps, fp32, {dt:.1f} s of CPU work, extrapolated B*T/(50*t_step)"}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -11,7 +11,8 @@
  *     the calling thread's last failure.  Nothing throws, nothing calls exit().
  *   - one context per (device, stream); a context is NOT re-entrant.  The caller keeps OWNERSHIP of all
  *     parameter and activation memory; the context borrows parameter pointers only during
- *     mcm_finalize_params() (it keeps its own packed 16-bit copies; call it again after load_state_dict).
+ *     mcm_finalize_params() (it keeps its own packed 16-bit copies; after load_state_dict set every parameter again and
+ *     call it again: the copies are re-packed in place, then call mcm_prepare_conditions again).
  *   - requires an sm_100a device.  There is no CPU or non-tcgen05 fallback: creation fails loudly.
  */
 #ifndef MCM_B200_H_
@@ -56,6 +57,8 @@ typedef struct mcm_sampler {
   const float* posterior_mean_coef1;
   const float* posterior_mean_coef2;
   const float* posterior_log_variance_clipped;
+  unsigned long long seed;                    /* stochastic samplers without explicit noise: Philox key; step i uses
+                                               * stream i, so a run is reproducible from (seed, x_T) alone            */
 } mcm_sampler;
 
 /* replaces: MCMTransformer.__init__ / DiffusionTransformer.__init__
@@ -105,14 +108,25 @@ int mcm_denoise(mcm_ctx* ctx, int batch, const float* x, const long long* timest
 int mcm_block_forward(mcm_ctx* ctx, int kind, int index, int batch, float* x_inout, const float* emb,
                       void* stream);
 
+/* replaces: MCMTransformer.forward_test(h, src_mask, emb, xf_out) (mcm.py:93-102) and, when control blocks and a
+ * condition are prepared, ControlT2MHalf_MCM.forward_test (controlnet_mcm.py:306-361): the decoder layers and `out` on an
+ * ALREADY EMBEDDED residual stream.  h [B, T, latent_dim] (read only), emb [B, time_embed_dim] (time embedding + text
+ * projection, diffusion_transformer.py:206-213), out [B, T, input_feats].  src_mask is replaced by ones inside the MCM
+ * decoder layer (mcm.py:28) and therefore is not an argument; xf_out enters through mcm_prepare_conditions. */
+int mcm_layers_forward(mcm_ctx* ctx, int batch, const float* h, const float* emb, float* out, void* stream);
+
 /* replaces: GaussianDiffusion.ddim_sample_loop / p_sample_loop (gaussian_diffusion.py:698-797, 925-1049)
  * with clip_denoised=False, epsilon prediction, fixed_small variance.
- *   x_T [B,T,F] device; step_noise: device [n_steps, B, T, F] (index i = retained step i) or NULL
- *   (required for DDPM and for DDIM with eta != 0); x0_out [B,T,F] device. */
+ *   x_T [B,T,F] device; x0_out [B,T,F] device.  step_noise: device [n_steps, B, T, F] (index i = retained step i): the
+ *   reference's randn_like draws, for reproducing a reference run bit for bit -- or NULL: a stochastic sampler (DDPM, DDIM
+ *   with eta != 0) then generates each step's noise on the device (Philox4x32-10 keyed by (s->seed, i) + Box-Muller) into
+ *   ONE step-sized buffer, as the reference draws one randn_like per step (:685, :847) instead of n_steps up front. */
 int mcm_sample(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* x_T, const float* step_noise,
                float* x0_out, void* stream);
 /* Same through HOST buffers (pinned or pageable): host->device copy of x_T, the loop, device->host copy
- * of x_0, all on `stream`, synchronised before returning.  This is the end-to-end call bench.py times. */
+ * of x_0, all on `stream`, synchronised before returning.  This is the end-to-end call bench.py times.
+ * step_noise_host: host [n_steps, B, T, F] or NULL (generated on the device, as above); a host tensor is copied one
+ * step at a time, so device memory stays at one step's worth. */
 int mcm_sample_host(mcm_ctx* ctx, const mcm_sampler* s, int batch, const float* x_T_host,
                     const float* step_noise_host, float* x0_out_host, void* stream);
 
@@ -126,7 +140,8 @@ typedef struct mcm_repaint {
   const unsigned char* keep_mask;   /* device [B,T,F]: y['outpainting_mask'], 1 = keep the (noised) ground truth            */
   const float* noise_seq;           /* device [n_draws,B,T,F]: the reference's torch.randn_like draws IN ORDER -- two per
                                      * denoise call (the eta noise of :847, unused at eta = 0, then the blend noise of
-                                     * :867), one per undo                                                                  */
+                                     * :867), one per undo.  NULL: the draws that are actually read are generated on the
+                                     * device (Philox keyed by (sampler seed, draw index)), one buffer, nothing up front   */
   long long n_draws;
   int overlap_len;                  /* opt.overlap_len                                                                      */
   int add_blend;                    /* opt.addBlend                                                                         */
@@ -144,6 +159,10 @@ int mcm_sample_repaint(mcm_ctx* ctx, const mcm_sampler* s, const mcm_repaint* r,
  *   fmt 0 = fp16 (1 pass) or 1 = bf16 hi/lo (3 passes). */
 int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
                     int fmt, void* stream);
+
+/* The on-device noise generator of the stochastic samplers, exposed for unit tests: out[0..n) ~ N(0,1), Philox4x32-10
+ * keyed by `seed`, counter (element quad, sub), Box-Muller. */
+int mcm_test_randn(float* out_dev, long long n, unsigned long long seed, unsigned long long sub, void* stream);
 
 /* Measurement aid for bench.py's roofline leg: when enabled, every kernel launch of the library is
  * bracketed by CUDA events on its stream; collect() synchronises the device and returns, for class 0

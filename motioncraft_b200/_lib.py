@@ -31,7 +31,7 @@ class McmSampler(ctypes.Structure):
                 ("timestep_map", _IP), ("alphas_cumprod", _FP), ("alphas_cumprod_prev", _FP),
                 ("sqrt_recip_alphas_cumprod", _FP), ("sqrt_recipm1_alphas_cumprod", _FP),
                 ("posterior_mean_coef1", _FP), ("posterior_mean_coef2", _FP),
-                ("posterior_log_variance_clipped", _FP)]
+                ("posterior_log_variance_clipped", _FP), ("seed", ctypes.c_ulonglong)]
 
 
 class McmRepaint(ctypes.Structure):
@@ -51,9 +51,11 @@ SIGNATURES = {
     "mcm_prepare_conditions": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
     "mcm_denoise": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP]),
     "mcm_block_forward": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
+    "mcm_layers_forward": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "mcm_sample": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
     "mcm_sample_host": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
     "mcm_sample_repaint": (_I, [_VP, ctypes.POINTER(McmSampler), ctypes.POINTER(McmRepaint), _I, _VP, _VP, _VP]),
+    "mcm_test_randn": (_I, [_VP, _LL, ctypes.c_ulonglong, ctypes.c_ulonglong, _VP]),
     "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
     "mcm_timing_enable": (None, [_I]),
     "mcm_timing_collect": (_I, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong),

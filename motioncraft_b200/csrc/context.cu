@@ -96,15 +96,27 @@ struct mcm_ctx {
   // the step's timestep is read from `t_buf`, so the graph is identical for all steps.
   int use_graph = 1;                     // MCM_GRAPH=0: eager launches
   long long* t_buf = nullptr;
-  struct StepGraph { int B; bool have_c; int fused; cudaGraphExec_t exec; unsigned long long n_gemm, n_row, n_fused; };
-  std::vector<StepGraph> graphs;
+  struct StepGraph { int B; bool have_c; long long key; cudaGraphExec_t exec; unsigned long long n_gemm, n_row, n_fused, last_use; };
+  std::vector<StepGraph> graphs;         // at most MAX_GRAPHS entries, least recently used evicted
+  static constexpr size_t MAX_GRAPHS = 8;
+  unsigned long long graph_clock = 0;
+  float* noise_buf = nullptr;            // [Bmax*T*IN] per-step sampler noise staged / generated on the device (lazy)
+  // every scheduling option that changes the captured launch sequence is part of the graph key
+  long long graph_key() const {
+    return (long long)fused + 2ll * fused_sa + 16ll * (dual ? 1 : 0) + 32ll * fused_stop + 512ll * (long long)chunk +
+           (1ll << 24) * (long long)fused_min_rows;
+  }
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
 
   int fmt_fast() const { return cfg.precise_all ? OP_BF16X2 : OP_F16; }
   int fmt_prec() const { return OP_BF16X2; }
 
   ~mcm_ctx() {
     for (void* p : allocs) cudaFree(p);
-    for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+    drop_graphs();
     if (s1) cudaStreamDestroy(s1);
     if (s0) cudaStreamDestroy(s0);
     if (ev_in) cudaEventDestroy(ev_in);
@@ -156,7 +168,7 @@ int get_param(mcm_ctx* c, const std::string& name, long long numel, const float*
 int own_f32(mcm_ctx* c, const std::vector<std::pair<std::string, long long>>& pieces, float** out, cudaStream_t st) {
   long long total = 0;
   for (auto& p : pieces) total += p.second;
-  MCM_TRY(alloc_f32(c, out, (size_t)total));
+  if (*out == nullptr) MCM_TRY(alloc_f32(c, out, (size_t)total));      // a second mcm_finalize_params re-packs in place
   long long off = 0;
   for (auto& p : pieces) {
     const float* src;
@@ -173,7 +185,7 @@ int pack_weight(mcm_ctx* c, const std::vector<std::pair<std::string, int>>& piec
   int rows = 0;
   for (auto& p : pieces) rows += p.second;
   const int in_p = rup(in, 8);
-  MCM_TRY(alloc_op(c, out, (size_t)rows * in_p, in_p, fmt == OP_BF16X2));
+  if (out->hi == nullptr) MCM_TRY(alloc_op(c, out, (size_t)rows * in_p, in_p, fmt == OP_BF16X2));
   int r0 = 0;
   for (auto& p : pieces) {
     const float* src;
@@ -232,7 +244,8 @@ int build_block(mcm_ctx* c, const std::string& pfx, Block* b, int mod_off, cudaS
   MCM_TRY(own_f32(c, {{ca + "proj_out.norm.bias", D}}, &b->ca_pn_b, st));
   MCM_TRY(pack_weight(c, {{ca + "proj_out.out_layers.2.weight", D}}, D, ff, &b->ca_wo, st));
   MCM_TRY(own_f32(c, {{ca + "proj_out.out_layers.2.bias", D}}, &b->ca_bo, st));
-  MCM_TRY(alloc_op(c, &b->ca_ctxT, (size_t)c->Bmax * c->H * c->hdD * c->hdD, c->hdD, ff == OP_BF16X2));
+  if (b->ca_ctxT.hi == nullptr)
+    MCM_TRY(alloc_op(c, &b->ca_ctxT, (size_t)c->Bmax * c->H * c->hdD * c->hdD, c->hdD, ff == OP_BF16X2));
 
   MCM_TRY(pack_weight(c, {{fn + "linear1.weight", F}}, D, ff, &b->f_w1, st));
   MCM_TRY(own_f32(c, {{fn + "linear1.bias", F}}, &b->f_b1, st));
@@ -452,6 +465,8 @@ int check_batch(mcm_ctx* c, int B) {
   return 0;
 }
 
+int run_stack(mcm_ctx* c, Scratch& w, int b0, int B, float* eps_out, cudaStream_t st);
+
 // joint_embed -> decoder layers (+ control branch) -> out, for samples [b0, b0 + B) of the current step
 int run_layers(mcm_ctx* c, Scratch& w, int b0, int B, float* eps_out, cudaStream_t st) {
   const int T = c->T, D = c->D, IN = c->IN;
@@ -470,6 +485,15 @@ int run_layers(mcm_ctx* c, Scratch& w, int b0, int B, float* eps_out, cudaStream
     g.seg[0].out32 = w.h32; g.seg[0].ld32 = D;
     MCM_TRY(gemm_tc_launch(g, st));
   }
+  return run_stack(c, w, b0, B, eps_out, st);
+}
+
+// decoder layers (+ control branch) -> out on the residual stream already in w.h32: MCMTransformer.forward_test
+// (mcm.py:93-102) / ControlT2MHalf_MCM.forward_test (controlnet_mcm.py:306-361)
+int run_stack(mcm_ctx* c, Scratch& w, int b0, int B, float* eps_out, cudaStream_t st) {
+  const int T = c->T, D = c->D, IN = c->IN;
+  const int fp = c->fmt_prec();
+  const size_t r0 = (size_t)b0 * T;
   const OpPtr none{nullptr, nullptr, 0};
   const OpPtr hop_out = view(w.hop, D);
   const int nL = c->nL, nC = (c->have_c ? c->nC : 0);
@@ -509,7 +533,7 @@ int run_layers(mcm_ctx* c, Scratch& w, int b0, int B, float* eps_out, cudaStream
 
 // the whole denoiser on x32/xop already in place: writes eps32
 int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float* eps_out, cudaStream_t st) {
-  const int T = c->T, D = c->D, E = c->E, IN = c->IN;
+  const int D = c->D, E = c->E;
   const int fp = c->fmt_prec();
   MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first (for at least this batch)");
   // emb = time_embed(sinusoid(t)) + xf_proj                      (diffusion_transformer.py:206-213)
@@ -561,9 +585,11 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
   }
   MCM_TRY(fill_timesteps_launch(c->t_buf, (long long)t, B, gs));
   cudaGraphExec_t exec = nullptr;
+  const long long key = c->graph_key();
   for (auto& g : c->graphs)
-    if (g.B == B && g.have_c == c->have_c && g.fused == c->fused + 2 * c->fused_sa + 16 * c->fused_min_rows) {
+    if (g.B == B && g.have_c == c->have_c && g.key == key) {
       exec = g.exec;
+      g.last_use = ++c->graph_clock;
       gemm_tc_count_replayed(g.n_gemm);          // keep the library's launch counters truthful under graph replay
       elementwise_count_replayed(g.n_row);
       fused_block_count_replayed(g.n_fused);
@@ -583,8 +609,15 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     MCM_CUDA(ie);
-    c->graphs.push_back({B, c->have_c, c->fused + 2 * c->fused_sa + 16 * c->fused_min_rows, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
-                         fused_block_launch_count() - f0});
+    if (c->graphs.size() >= mcm_ctx::MAX_GRAPHS) {          // evict the least recently used instantiation
+      size_t victim = 0;
+      for (size_t i = 1; i < c->graphs.size(); ++i)
+        if (c->graphs[i].last_use < c->graphs[victim].last_use) victim = i;
+      cudaGraphExecDestroy(c->graphs[victim].exec);
+      c->graphs.erase(c->graphs.begin() + (long)victim);
+    }
+    c->graphs.push_back({B, c->have_c, key, exec, gemm_tc_launch_count() - g0, elementwise_launch_count() - r0,
+                         fused_block_launch_count() - f0, ++c->graph_clock});
   }
   MCM_CUDA(cudaGraphLaunch(exec, gs));
   if (hop_stream) {
@@ -594,13 +627,46 @@ int run_denoiser_step(mcm_ctx* c, int B, int t, cudaStream_t st) {
   return 0;
 }
 
-int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const float* step_noise, float* x_io, cudaStream_t st) {
+// Where the per-step noise of a stochastic sampler comes from: an explicit device tensor [n_steps, B, T, F] (oracle /
+// parity tests), an explicit host tensor of the same shape (copied one step at a time into the noise buffer), or -- the
+// default of the front end -- generated on the device per step, Philox keyed by (sampler seed, step index).  The last two
+// need ONE step's worth of device memory instead of n_steps (DDPM-1000 at B=256, T=196 would be 64.6 GB).
+struct NoiseSource {
+  const float* dev = nullptr;
+  const float* host = nullptr;
+  bool generate = false;
+  unsigned long long seed = 0;
+};
+
+int ensure_noise_buf(mcm_ctx* c) {
+  if (c->noise_buf == nullptr) MCM_TRY(alloc_f32(c, &c->noise_buf, (size_t)c->Bmax * c->T * c->IN));
+  return 0;
+}
+
+int step_noise_ptr(mcm_ctx* c, const NoiseSource& ns, long long index, size_t n, cudaStream_t st, const float** out) {
+  *out = nullptr;
+  if (ns.dev) {
+    *out = ns.dev + (size_t)index * n;
+  } else if (ns.host) {
+    MCM_CUDA(cudaMemcpyAsync(c->noise_buf, ns.host + (size_t)index * n, n * 4, cudaMemcpyHostToDevice, st));
+    *out = c->noise_buf;
+  } else if (ns.generate) {
+    MCM_TRY(randn_fill_launch(c->noise_buf, n, ns.seed, (unsigned long long)index, st));
+    *out = c->noise_buf;
+  }
+  return 0;
+}
+
+int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const NoiseSource& ns, float* x_io, cudaStream_t st) {
   const size_t rows = (size_t)B * c->T;
   const size_t n = rows * c->IN;
+  const bool stochastic = s->mode == 1 || s->eta != 0.f;
+  if (stochastic && !ns.dev) MCM_TRY(ensure_noise_buf(c));
   // x_io holds x_T on entry and x_0 on exit; xop must already hold the operand copy of x_T
   for (int i = s->n_steps - 1; i >= 0; --i) {
     MCM_TRY(run_denoiser_step(c, B, s->timestep_map[i], st));
-    const float* noise = step_noise ? step_noise + (size_t)i * n : nullptr;
+    const float* noise = nullptr;
+    if (stochastic && i != 0) MCM_TRY(step_noise_ptr(c, ns, i, n, st, &noise));
     if (s->mode == 0) {
       DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
                   s->alphas_cumprod_prev[i], s->eta, (s->eta != 0.f && i != 0) ? 1 : 0};
@@ -614,16 +680,14 @@ int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const float* step_noise
   return 0;
 }
 
-int check_sampler(const mcm_sampler* s, const float* step_noise) {
+int check_sampler(const mcm_sampler* s) {
   MCM_CHECK(s != nullptr && s->n_steps > 0 && s->timestep_map != nullptr, "bad sampler description");
   MCM_CHECK(s->mode == 0 || s->mode == 1, "sampler mode must be 0 (DDIM) or 1 (DDPM)");
   MCM_CHECK(s->sqrt_recip_alphas_cumprod && s->sqrt_recipm1_alphas_cumprod, "missing sampler tables");
   if (s->mode == 0) {
     MCM_CHECK(s->alphas_cumprod && s->alphas_cumprod_prev, "DDIM needs alphas_cumprod(_prev)");
-    MCM_CHECK(s->eta == 0.f || step_noise != nullptr, "DDIM with eta != 0 needs step noise");
   } else {
     MCM_CHECK(s->posterior_mean_coef1 && s->posterior_mean_coef2 && s->posterior_log_variance_clipped, "DDPM needs posterior tables");
-    MCM_CHECK(step_noise != nullptr || s->n_steps == 1, "DDPM needs step noise");
   }
   return 0;
 }
@@ -670,6 +734,16 @@ int mcm_timing_collect(double* ms, unsigned long long* launches, double* flops) 
 int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   MCM_CHECK(cfg != nullptr && out != nullptr, "null argument");
   *out = nullptr;
+  {
+    // Kernel attributes (opt-in shared memory size, cluster occupancy) are per DEVICE and are set up once per process for
+    // the device that is current at the first mcm_create: the deployment model is one process per GPU (torchrun /
+    // bench.py --gpus N).  A context on another device of the same process is refused instead of failing at launch.
+    static int g_device = -1;
+    int dev = -1;
+    MCM_CUDA(cudaGetDevice(&dev));
+    if (g_device < 0) g_device = dev;
+    MCM_CHECK(dev == g_device, "this process already runs motioncraft_b200 contexts on another CUDA device: use one process per GPU");
+  }
   MCM_TRY(gemm_tc_init());
   MCM_TRY(elementwise_init());
   MCM_CHECK(cfg->seq_len % cfg->num_heads == 0 && cfg->latent_dim % cfg->num_heads == 0, "heads must divide seq_len and latent_dim");
@@ -796,6 +870,7 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     set_error("unknown option: " + n);
     return 1;
   }
+  c->drop_graphs();      // captured step graphs embed the old schedule; the next sampler step re-captures
   return 0;
 }
 
@@ -807,8 +882,14 @@ int mcm_set_param(mcm_ctx* ctx, const char* name, const float* dev_ptr, long lon
 
 int mcm_finalize_params(mcm_ctx* c, void* stream) {
   MCM_CHECK(c != nullptr, "null context");
-  MCM_CHECK(!c->finalized, "parameters were already finalized (create a new context to reload weights)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // A repeated call (after load_state_dict: every parameter set again with mcm_set_param) re-packs into the SAME operand
+  // buffers, so captured CUDA graphs and the workspace stay valid; only the step-invariant condition work, which depends
+  // on the weights, must be redone by the caller (mcm_prepare_conditions).
+  if (c->finalized) {
+    c->finalized = false;
+    c->cond_ready = false;
+  }
   const int T = c->T, D = c->D, E = c->E, IN = c->IN;
   const int fp = c->fmt_prec();
   MCM_TRY(pack_weight(c, {{"joint_embed.weight", D}}, IN, fp, &c->w_joint, st));
@@ -956,24 +1037,41 @@ int mcm_block_forward(mcm_ctx* c, int kind, int index, int B, float* x_inout, co
   return run_block(c, c->ws[0], c->blocks[bi], B, x_inout, c->mod32, c->mod_total, none, 0, st);
 }
 
+int mcm_layers_forward(mcm_ctx* c, int B, const float* h, const float* emb, float* out, void* stream) {
+  MCM_TRY(check_batch(c, B));
+  MCM_CHECK(h && emb && out, "null tensor");
+  MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MCM_CUDA(cudaMemcpyAsync(c->ws[0].h32, h, (size_t)B * c->T * c->D * 4, cudaMemcpyDeviceToDevice, st));
+  MCM_TRY(run_mod(c, B, emb, 0, (int)c->blocks.size(), st));
+  return run_stack(c, c->ws[0], 0, B, out, st);
+}
+
 int mcm_sample(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T, const float* step_noise, float* x0_out,
                void* stream) {
   MCM_TRY(check_batch(c, B));
-  MCM_TRY(check_sampler(s, step_noise));
+  MCM_TRY(check_sampler(s));
   MCM_CHECK(x_T && x0_out, "null tensor");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t n = (size_t)B * c->T * c->IN;
   if (x0_out != x_T) MCM_CUDA(cudaMemcpyAsync(x0_out, x_T, n * 4, cudaMemcpyDeviceToDevice, st));
   MCM_TRY(pack_op_launch(x0_out, B * c->T, c->IN, c->IN, false, c->xop, c->fmt_prec(), st));
-  return run_sampler(c, s, B, step_noise, x0_out, st);
+  NoiseSource ns;
+  ns.dev = step_noise; ns.generate = step_noise == nullptr; ns.seed = s->seed;
+  return run_sampler(c, s, B, ns, x0_out, st);
 }
 
 int mcm_sample_repaint(mcm_ctx* c, const mcm_sampler* s, const mcm_repaint* r, int B, const float* x_T, float* x0_out,
                        void* stream) {
   MCM_TRY(check_batch(c, B));
-  MCM_TRY(check_sampler(s, nullptr));
+  MCM_TRY(check_sampler(s));
   MCM_CHECK(s->mode == 0 && s->eta == 0.f, "mcm_sample_repaint: DDIM with eta = 0 only (what MotionDiffusion passes)");
-  MCM_CHECK(r != nullptr && x_T && x0_out && r->gt && r->keep_mask && r->noise_seq, "mcm_sample_repaint: null argument");
+  MCM_CHECK(r != nullptr && x_T && x0_out && r->gt && r->keep_mask, "mcm_sample_repaint: null argument");
+  // noise_seq == NULL: every draw the loop actually READS (the blend noise of a denoise call, the undo noise) is generated
+  // on the device, Philox keyed by (sampler seed, draw index); the unread eta draw of each denoise call costs nothing.
+  NoiseSource ns;
+  ns.dev = r->noise_seq; ns.generate = r->noise_seq == nullptr; ns.seed = s->seed;
+  if (ns.generate) MCM_TRY(ensure_noise_buf(c));
   MCM_CHECK(r->n_times == 0 || (r->times != nullptr && r->betas != nullptr), "mcm_sample_repaint: schedule without times / betas");
   MCM_CHECK(r->overlap_len >= 0 && r->overlap_len <= c->T, "mcm_sample_repaint: overlap_len out of range");
   MCM_CHECK(!(r->add_blend && r->overlap_len > 0) || r->blend_w != nullptr, "mcm_sample_repaint: addBlend needs blend_w");
@@ -985,7 +1083,7 @@ int mcm_sample_repaint(mcm_ctx* c, const mcm_sampler* s, const mcm_repaint* r, i
   const OpPtr none{nullptr, nullptr, 0};
   auto denoise = [&](int i) -> int {
     MCM_CHECK(i >= 0 && i < s->n_steps, "mcm_sample_repaint: time index outside the sampler tables");
-    MCM_CHECK(draw + 2 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
+    MCM_CHECK(ns.generate || draw + 2 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
     MCM_TRY(run_denoiser_step(c, B, s->timestep_map[i], st));
     DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
                 s->alphas_cumprod_prev[i], 0.f, 0};
@@ -993,7 +1091,9 @@ int mcm_sample_repaint(mcm_ctx* c, const mcm_sampler* s, const mcm_repaint* r, i
     const float abp = s->alphas_cumprod_prev[i];
     const float noise_w = sqrtf(1.f - abp), gt_w = sqrtf(abp);
     const bool blend = r->add_blend && r->overlap_len > 0 && noise_w < 0.2f;     // :872
-    MCM_TRY(repaint_blend_launch(x0_out, r->gt, r->keep_mask, r->noise_seq + (size_t)(draw + 1) * n, rows, c->IN, c->T, gt_w,
+    const float* bn = nullptr;
+    MCM_TRY(step_noise_ptr(c, ns, draw + 1, n, st, &bn));
+    MCM_TRY(repaint_blend_launch(x0_out, r->gt, r->keep_mask, bn, rows, c->IN, c->T, gt_w,
                                  noise_w, blend ? r->blend_w : nullptr, r->overlap_len, c->xop, c->fmt_prec(), st));
     draw += 2;
     return 0;
@@ -1008,9 +1108,11 @@ int mcm_sample_repaint(mcm_ctx* c, const mcm_sampler* s, const mcm_repaint* r, i
       MCM_TRY(denoise(t_last));
     } else {
       MCM_CHECK(t_last >= 0 && t_last < s->n_steps, "mcm_sample_repaint: undo time outside the sampler tables");
-      MCM_CHECK(draw + 1 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
+      MCM_CHECK(ns.generate || draw + 1 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
       const float beta = r->betas[t_last];
-      MCM_TRY(undo_launch(x0_out, r->noise_seq + (size_t)draw * n, rows, c->IN, sqrtf(1.f - beta), sqrtf(beta), c->xop,
+      const float* un = nullptr;
+      MCM_TRY(step_noise_ptr(c, ns, draw, n, st, &un));
+      MCM_TRY(undo_launch(x0_out, un, rows, c->IN, sqrtf(1.f - beta), sqrtf(beta), c->xop,
                           c->fmt_prec(), st));
       draw += 1;
     }
@@ -1022,16 +1124,22 @@ int mcm_sample_host(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T_ho
                     float* x0_out_host, void* stream) {
   MCM_TRY(check_batch(c, B));
   MCM_CHECK(x_T_host && x0_out_host, "null tensor");
-  MCM_CHECK(step_noise_host == nullptr, "mcm_sample_host: per-step noise must be staged on the device (use mcm_sample)");
-  MCM_TRY(check_sampler(s, nullptr));
+  MCM_TRY(check_sampler(s));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t n = (size_t)B * c->T * c->IN;
   MCM_CUDA(cudaMemcpyAsync(c->x32, x_T_host, n * 4, cudaMemcpyHostToDevice, st));
   MCM_TRY(pack_op_launch(c->x32, B * c->T, c->IN, c->IN, false, c->xop, c->fmt_prec(), st));
-  MCM_TRY(run_sampler(c, s, B, nullptr, c->x32, st));
+  NoiseSource ns;
+  ns.host = step_noise_host; ns.generate = step_noise_host == nullptr; ns.seed = s->seed;
+  MCM_TRY(run_sampler(c, s, B, ns, c->x32, st));
   MCM_CUDA(cudaMemcpyAsync(x0_out_host, c->x32, n * 4, cudaMemcpyDeviceToHost, st));
   MCM_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+int mcm_test_randn(float* out_dev, long long n, unsigned long long seed, unsigned long long sub, void* stream) {
+  MCM_CHECK(out_dev != nullptr && n > 0, "bad argument");
+  return randn_fill_launch(out_dev, (size_t)n, seed, sub, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const float* bias, float* C, int fmt,

@@ -408,6 +408,47 @@ undo_kernel(float* __restrict__ x, const float* __restrict__ noise, size_t rows,
   }
 }
 
+// Standard-normal noise generated on the device: Philox4x32-10 (Salmon et al., SC'11) keyed by `seed`, counter =
+// (element quad index, stream id `sub`), Box-Muller on the four outputs.  Replaces the per-step torch.randn_like draws
+// of the reference samplers (gaussian_diffusion.py:685, :847, :867, :432) when the caller supplies no explicit noise:
+// one buffer of B*T*F floats is refilled per step instead of n_steps of them being allocated up front.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
+}
+__global__ void __launch_bounds__(256)
+randn_fill_kernel(float* __restrict__ out, size_t n, unsigned long long seed, unsigned long long sub) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t nq = (n + 3) / 4;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = ((float)(c[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);       // (0, 1]
+      const float u2 = (float)(c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);            // [0, 1)
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+    }
+    const size_t i = q * 4;
+    if (i + 3 < n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      *reinterpret_cast<float4*>(out + i) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+      for (int e = 0; e < 4; ++e) if (i + e < n) out[i + e] = z[e];
+    }
+  }
+}
+
 __global__ void fill_timesteps_kernel(long long* __restrict__ t_buf, long long t, int B) {
   pdl_trigger();
   pdl_wait();
@@ -424,6 +465,14 @@ inline int grid_for(size_t total, int block) {
 int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream) {
   LaunchTimer lt(LK_ROW, stream);
   MCM_CUDA(launch_pdl(fill_timesteps_kernel, dim3((B + 255) / 256), dim3(256), (size_t)(0), stream, t_buf, t, B));
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int randn_fill_launch(float* out, size_t n, unsigned long long seed, unsigned long long sub, cudaStream_t stream) {
+  LaunchTimer lt(LK_ROW, stream);
+  MCM_CUDA(launch_pdl(randn_fill_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), stream, out, n, seed, sub));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

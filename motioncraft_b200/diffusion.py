@@ -124,18 +124,30 @@ class GaussianDiffusion:
         if cond_fn is not None or denoised_fn is not None or pre_seq is not None or transl_req is not None:
             raise McmError("cond_fn / denoised_fn / pre_seq / transl_req are not part of the re-hosted hot path")
 
+    @staticmethod
+    def _draw_seed(dev):
+        """One draw from torch's generator of the sampling device: `torch.manual_seed` keeps controlling the run, as it
+        controls the reference's randn_like draws (the streams themselves differ: Philox per step inside the library)."""
+        return int(torch.randint(0, 2 ** 62, (1,), device=dev).item())
+
     def _run(self, model, shape, noise, model_kwargs, mode, eta, step_noise, device):
         B = shape[0]
         model_kwargs = dict(model_kwargs or {})
         dev = device if device is not None else next(model.parameters()).device
         if noise is None:
             noise = torch.randn(*shape, device=dev)
-        n = self.num_timesteps
-        if step_noise is None and ((mode == "ddpm" and n > 1) or (mode == "ddim" and eta != 0.0)):
-            # the reference draws randn_like(x) per step from torch's global generator (:685, :847)
-            step_noise = torch.randn(n, *shape, device=dev)
+        # The reference draws randn_like(x) once per step (:685, :847).  Here the library generates step i's noise on the
+        # device into ONE step-sized buffer (Philox keyed by (seed, i)); nothing of size n_steps x shape is allocated.
+        # An explicit `step_noise` [n_steps, *shape] (device or host tensor) reproduces scripted reference draws.
+        stochastic = (mode == "ddpm" and self.num_timesteps > 1) or (mode == "ddim" and eta != 0.0)
+        seed = self._draw_seed(dev) if (stochastic and step_noise is None) else 0
         eng = model.bind_for_sampling(B, model_kwargs, dev)
-        tables = SamplerTables(self._tables(), self.timestep_map, mode, eta)
+        tables = SamplerTables(self._tables(), self.timestep_map, mode, eta, seed=seed)
+        if step_noise is not None and step_noise.device.type == "cpu" and step_noise.numel() * 4 > (1 << 30):
+            # large scripted noise stays on the host and is streamed one step at a time
+            x0 = eng.sample_host(tables, noise.detach().float().cpu().contiguous(), None,
+                                 step_noise.detach().float().contiguous())
+            return x0.to(dev)
         return eng.sample(tables, noise.to(dev), step_noise)
 
     # ------------------------------------------------------------------ reference-facing API
@@ -186,12 +198,13 @@ class GaussianDiffusion:
         if noise is None:
             noise = torch.randn(*shape, device=dev)
         n_draws = count_draws(times, self.num_timesteps)
+        seed = 0
         if repaint_noise is None:
-            repaint_noise = torch.randn(n_draws, *shape, device=dev)
+            seed = self._draw_seed(dev)        # draws are generated inside the library, one buffer (mcm_repaint.noise_seq = NULL)
         elif repaint_noise.shape[0] < n_draws:
             raise McmError(f"repaint_noise holds {repaint_noise.shape[0]} draws, the schedule needs {n_draws}")
         eng = model.bind_for_sampling(B, dict(model_kwargs), dev)
-        tables = SamplerTables(self._tables(), self.timestep_map, "ddim", 0.0)
+        tables = SamplerTables(self._tables(), self.timestep_map, "ddim", 0.0, seed=seed)
         return eng.sample_repaint(tables, noise.to(dev), torch.as_tensor(y["gt"]), torch.as_tensor(y["outpainting_mask"]),
                                   repaint_noise, times=times, betas=self.betas, overlap_len=int(getattr(opt, "overlap_len", 0)),
                                   add_blend=bool(getattr(opt, "addBlend", True)))

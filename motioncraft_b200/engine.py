@@ -30,7 +30,7 @@ class SamplerTables:
     FIELDS = ("alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
               "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped")
 
-    def __init__(self, tables, timestep_map, mode, eta=0.0):
+    def __init__(self, tables, timestep_map, mode, eta=0.0, seed=0):
         self.n_steps = len(timestep_map)
         self._tmap = np.ascontiguousarray(np.asarray(timestep_map, dtype=np.int32))
         # the float64 -> float32 cast _extract_into_tensor applies (gaussian_diffusion.py:1340)
@@ -40,6 +40,7 @@ class SamplerTables:
         s.mode = {"ddim": 0, "ddpm": 1}[mode]
         s.n_steps = self.n_steps
         s.eta = float(eta)
+        s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF      # key of the on-device noise of stochastic samplers (no explicit noise given)
         s.timestep_map = self._tmap.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
         for k in self.FIELDS:
             setattr(s, k, self._arrs[k].ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
@@ -62,6 +63,15 @@ class DenoiserEngine:
         self._ctx = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mcm_create(ctypes.byref(cfg), ctypes.byref(self._ctx)))
+        self._cond_key = None
+        self._cond_refs = None
+        self.load_params(state_dict)
+
+    def load_params(self, state_dict):
+        """(Re)load weights: hands every parameter to the library and packs them (mcm_finalize_params).  On an engine
+        that already holds weights the packed copies are rewritten IN PLACE -- workspace, streams and captured graphs
+        survive a load_state_dict; only the step-invariant condition work must be prepared again."""
+        with torch.cuda.device(self.device):
             keep = []
             for name, t in state_dict.items():
                 if not torch.is_floating_point(t):
@@ -73,6 +83,7 @@ class DenoiserEngine:
             torch.cuda.synchronize(self.device)
         del keep
         self._cond_key = None
+        self._cond_refs = None
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -111,10 +122,19 @@ class DenoiserEngine:
         self._keep_cond = (xf_out, xf_proj, c)
 
     def prepare_conditions_cached(self, xf_out, xf_proj, c=None):
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in (xf_out, xf_proj, c))
+        """prepare_conditions unless the SAME tensor objects (identity, version counter, shape) were prepared last.
+        The cache entry holds strong references to the caller's tensors: their storage cannot be freed and handed to a
+        new batch at the same address (a fresh tensor has _version 0) while the entry is alive."""
+        key = tuple((id(t), t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
+                    for t in (xf_out, xf_proj, c))
         if key != self._cond_key:
             self.prepare_conditions(xf_out, xf_proj, c)
             self._cond_key = key
+            self._cond_refs = (xf_out, xf_proj, c)
+
+    def invalidate_conditions(self):
+        self._cond_key = None
+        self._cond_refs = None
 
     # ------------------------------------------------------------------ per-step / per-block
     def denoise(self, x, timesteps):
@@ -139,9 +159,20 @@ class DenoiserEngine:
                                                   _stream(self.device)))
         return x
 
+    def layers_forward(self, h, emb):
+        """MCMTransformer.forward_test (mcm.py:93-102): decoder layers + `out` on an already embedded h."""
+        h = _f32c(h, self.device)
+        emb = _f32c(emb, self.device)
+        out = torch.empty(h.shape[0], h.shape[1], self.input_feats, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mcm_layers_forward(self._ctx, h.shape[0], _ptr(h), _ptr(emb), _ptr(out),
+                                                   _stream(self.device)))
+        return out
+
     # ------------------------------------------------------------------ sampler
     def sample(self, tables: SamplerTables, x_T, step_noise=None):
-        """x_T on the device -> x_0 on the device (new tensor)."""
+        """x_T on the device -> x_0 on the device (new tensor).  step_noise=None with a stochastic sampler: the
+        library generates each step's noise on the device from tables.struct.seed."""
         x_T = _f32c(x_T, self.device)
         out = torch.empty_like(x_T)
         if step_noise is not None:
@@ -159,7 +190,8 @@ class DenoiserEngine:
         out = torch.empty_like(x_T)
         gt = _f32c(gt, self.device).expand_as(x_T).contiguous()
         keep = keep_mask.to(device=self.device, dtype=torch.bool).expand_as(x_T).contiguous().to(torch.uint8)
-        noise_seq = _f32c(noise_seq, self.device)
+        if noise_seq is not None:
+            noise_seq = _f32c(noise_seq, self.device)
         r = _lib.McmRepaint()
         keepalive = []
         if times is not None:
@@ -171,8 +203,9 @@ class DenoiserEngine:
             r.betas = b_arr.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
         else:
             r.n_times = 0
-        r.gt, r.keep_mask, r.noise_seq = gt.data_ptr(), keep.data_ptr(), noise_seq.data_ptr()
-        r.n_draws = noise_seq.shape[0]
+        r.gt, r.keep_mask = gt.data_ptr(), keep.data_ptr()
+        r.noise_seq = noise_seq.data_ptr() if noise_seq is not None else None    # None: generated on the device
+        r.n_draws = noise_seq.shape[0] if noise_seq is not None else 0
         r.overlap_len, r.add_blend = int(overlap_len), int(bool(add_blend))
         blend_w = torch.linspace(0, 1, int(overlap_len)).to(self.device) if overlap_len > 0 else None   # gaussian_diffusion.py:873
         r.blend_w = blend_w.data_ptr() if blend_w is not None else None
@@ -182,14 +215,19 @@ class DenoiserEngine:
             torch.cuda.current_stream(self.device).synchronize()     # host arrays / temporaries may go out of scope
         return out
 
-    def sample_host(self, tables: SamplerTables, x_T_host, out_host=None):
-        """x_T in (pinned) host memory -> x_0 in host memory; H2D + loop + D2H inside the library."""
+    def sample_host(self, tables: SamplerTables, x_T_host, out_host=None, step_noise_host=None):
+        """x_T in (pinned) host memory -> x_0 in host memory; H2D + loop + D2H inside the library.  Optional
+        step_noise_host [n_steps, B, T, F] in host memory is copied one step at a time."""
         assert x_T_host.device.type == "cpu" and x_T_host.dtype == torch.float32 and x_T_host.is_contiguous()
+        if step_noise_host is not None:
+            assert (step_noise_host.device.type == "cpu" and step_noise_host.dtype == torch.float32
+                    and step_noise_host.is_contiguous() and step_noise_host.shape[0] == tables.n_steps)
         if out_host is None:
             out_host = torch.empty_like(x_T_host, pin_memory=x_T_host.is_pinned())
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mcm_sample_host(self._ctx, ctypes.byref(tables.struct), x_T_host.shape[0],
-                                                _ptr(x_T_host), None, _ptr(out_host), _stream(self.device)))
+                                                _ptr(x_T_host), _ptr(step_noise_host), _ptr(out_host),
+                                                _stream(self.device)))
         return out_host
 
     def test_linear(self, A, W, bias, fmt):

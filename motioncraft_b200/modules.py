@@ -175,9 +175,11 @@ class MCMTransformer(nn.Module):
         self._precise_all = precise_all
         self._engine = None
         self._engine_key = None
+        self._param_epoch = 0          # bumped whenever the weights may have changed (load_state_dict, .to(), ...)
+        self._packed_epoch = -1        # epoch the engine's packed copies were made from
         for i, blk in enumerate(self.temporal_decoder_blocks):
             blk._bind(self, 0, i)
-        self._register_load_state_dict_pre_hook(self._drop_engine_hook)
+        self._register_load_state_dict_pre_hook(self._params_changed_hook)
 
     # ------------------------------------------------------------------ text encoder (outside the hot path)
     def _build_text_encoder(self, text_encoder):
@@ -243,8 +245,10 @@ class MCMTransformer(nn.Module):
         return motion
 
     # ------------------------------------------------------------------ engine plumbing
-    def _drop_engine_hook(self, *args, **kwargs):
-        self._drop_engine()
+    def _params_changed_hook(self, *args, **kwargs):
+        # the engine keeps packed 16-bit copies: they are re-packed IN PLACE (mcm_finalize_params again) at the next
+        # use, the workspace / streams / graphs of the engine survive a load_state_dict
+        self._param_epoch += 1
 
     def _drop_engine(self):
         if self._engine is not None:
@@ -273,15 +277,24 @@ class MCMTransformer(nn.Module):
             self._engine = DenoiserEngine(sd, max_batch=want, precise_all=self._precise_all, device=dev,
                                           **_shape_cfg(self), **extra_cfg)
             self._engine_key = (dev,)
+            self._packed_epoch = self._param_epoch
+        elif self._packed_epoch != self._param_epoch:
+            extra_sd, _ = self._engine_extra()
+            sd = self._hot_state_dict()
+            sd.update(extra_sd)
+            self._engine.load_params(sd)
+            self._packed_epoch = self._param_epoch
         return self._engine
 
     def _apply(self, fn, *a, **k):
-        self._drop_engine()
+        self._param_epoch += 1           # .to() / .cuda() / .float(): same device -> re-pack in place, new device -> new engine
         return super()._apply(fn, *a, **k)
 
     def _block_forward(self, kind, index, x, xf, emb):
         eng = self.engine(x.shape[0])
-        eng.prepare_conditions_cached(xf, torch.zeros(x.shape[0], self.time_embed_dim, device=x.device))
+        if getattr(self, "_ft_zero", None) is None or self._ft_zero.shape[0] != x.shape[0] or self._ft_zero.device != x.device:
+            self._ft_zero = torch.zeros(x.shape[0], self.time_embed_dim, device=x.device)
+        eng.prepare_conditions_cached(xf, self._ft_zero)
         return eng.block_forward(kind, index, x, emb)
 
     # ------------------------------------------------------------------ forward
@@ -315,9 +328,17 @@ class MCMTransformer(nn.Module):
         return eng
 
     def forward_test(self, h=None, src_mask=None, emb=None, xf_out=None, **kwargs):
-        """mcm.py:93-102, from an already embedded h: runs the per-block entry for every layer, then `out`."""
-        raise McmError("forward_test(h=..., emb=...) on pre-embedded activations is not exposed; call the module "
-                       "(forward) or the DecoderLayer blocks")
+        """mcm.py:93-102: the decoder layers and `out` on an ALREADY EMBEDDED residual stream h (B, T, latent) with the
+        time(+text) embedding emb (B, time_embed_dim).  src_mask is accepted for signature parity: DecoderLayer replaces
+        it by ones (mcm.py:28), and the all-ones mask is an identity in every block.  One C call (mcm_layers_forward)."""
+        if h is None or emb is None or xf_out is None:
+            raise McmError("forward_test needs h, emb and xf_out (mcm.py:93-102)")
+        eng = self.engine(h.shape[0])
+        # xf_proj only enters through emb, which the caller already formed (diffusion_transformer.py:206-213)
+        if getattr(self, "_ft_zero", None) is None or self._ft_zero.shape[0] != h.shape[0] or self._ft_zero.device != h.device:
+            self._ft_zero = torch.zeros(h.shape[0], self.time_embed_dim, device=h.device)
+        eng.prepare_conditions_cached(xf_out, self._ft_zero, self._control_condition(kwargs))
+        return eng.layers_forward(h, emb)
 
 
 def state_shapes(seq_len=196, input_feats=322, latent_dim=512, time_embed_dim=2048, ffn_dim=1024,
@@ -404,7 +425,9 @@ class ControlT2MHalf_MCM(nn.Module):
         self.control_cond_feats = in_feats
         self.control_cond_input = _zero_(nn.Linear(in_feats, base_model.latent_dim))
         self._engine = None
-        self._register_load_state_dict_pre_hook(lambda *a, **k: self._drop_engine())
+        self._param_epoch = 0
+        self._packed_epoch = (-1, -1)
+        self._register_load_state_dict_pre_hook(self._params_changed_hook)
         self.eval()
 
     # expose what the architecture wrapper touches
@@ -431,7 +454,12 @@ class ControlT2MHalf_MCM(nn.Module):
         if all(k.startswith(("base_model", "controlnet", "control_cond_input", "condition_pre_encoder"))
                for k in state_dict.keys()):
             return super().load_state_dict(state_dict, strict)
+        # the base model's own pre-hook bumps ITS epoch, which this module's engine also watches (engine())
         return self.base_model.load_state_dict(state_dict, strict)
+
+    def _params_changed_hook(self, *args, **kwargs):
+        self._param_epoch += 1
+        self._enc_cache = None
 
     def _drop_engine(self):
         if self._engine is not None:
@@ -439,24 +467,33 @@ class ControlT2MHalf_MCM(nn.Module):
         self._engine = None
 
     def _apply(self, fn, *a, **k):
-        self._drop_engine()
+        self._param_epoch += 1
+        self._enc_cache = None
         return super()._apply(fn, *a, **k)
+
+    def _engine_state(self):
+        sd = self.base_model._hot_state_dict()
+        for k, v in self.state_dict().items():
+            if k.startswith(("controlnet.", "control_cond_input.")) and ".ffn_channel." not in k:
+                sd[k] = v
+        return sd
 
     def engine(self, batch):
         base = self.base_model
         dev = base.sequence_embedding.device
         if dev.type != "cuda":
             raise McmError("motioncraft_b200 modules compute on an sm_100a CUDA device only (no CPU fallback)")
+        epoch = (self._param_epoch, base._param_epoch)      # own weights + the base model's (shared by this engine)
         if self._engine is None or self._engine.device != dev or self._engine.max_batch < batch:
             self._drop_engine()
-            sd = base._hot_state_dict()
-            for k, v in self.state_dict().items():
-                if k.startswith(("controlnet.", "control_cond_input.")) and ".ffn_channel." not in k:
-                    sd[k] = v
-            self._engine = DenoiserEngine(sd, max_batch=max(batch, base._max_batch_hint or 0),
+            self._engine = DenoiserEngine(self._engine_state(), max_batch=max(batch, base._max_batch_hint or 0),
                                           precise_all=base._precise_all, device=dev,
                                           num_ctrl_blocks=self.copy_blocks_num,
                                           ctrl_cond_feats=self.control_cond_feats, **_shape_cfg(base))
+            self._packed_epoch = epoch
+        elif self._packed_epoch != epoch:
+            self._engine.load_params(self._engine_state())
+            self._packed_epoch = epoch
         return self._engine
 
     def _condition(self, c):
@@ -464,10 +501,12 @@ class ControlT2MHalf_MCM(nn.Module):
             return None
         enc = self.condition_pre_encoder
         if enc is not None and c.shape[-1] == enc.raw_feats and c.shape[-1] != self.control_cond_feats:
-            key = (c.data_ptr(), c._version, tuple(c.shape))
+            # identity cache: holds a strong reference to the raw audio tensor, so its address cannot be recycled for a
+            # different batch while the entry is alive
+            key = (id(c), c.data_ptr(), c._version, tuple(c.shape))
             if self._enc_cache is None or self._enc_cache[0] != key:
                 dev = self.control_cond_input.weight.device
-                self._enc_cache = (key, enc(c.to(device=dev, dtype=torch.float32)))
+                self._enc_cache = (key, enc(c.to(device=dev, dtype=torch.float32)), c)
             c = self._enc_cache[1]
         if c.shape[-1] != self.control_cond_feats:
             raise McmError(f"control condition has {c.shape[-1]} features, control_cond_input expects "
@@ -481,6 +520,18 @@ class ControlT2MHalf_MCM(nn.Module):
         eng = self.engine(batch)
         eng.prepare_conditions_cached(cond["xf_out"], xf_proj, self._condition(model_kwargs.get("c")))
         return eng
+
+    def forward_test(self, h=None, src_mask=None, emb=None, xf_out=None, c=None, **kwargs):
+        """controlnet_mcm.py:306-361: base / control blocks and `out` on an already embedded h; `c` is the control
+        condition (raw or pre-encoded), None = the plain base model."""
+        if h is None or emb is None or xf_out is None:
+            raise McmError("forward_test needs h, emb and xf_out (controlnet_mcm.py:306-361)")
+        eng = self.engine(h.shape[0])
+        z = getattr(self, "_ft_zero", None)
+        if z is None or z.shape[0] != h.shape[0] or z.device != h.device:
+            self._ft_zero = z = torch.zeros(h.shape[0], self.base_model.time_embed_dim, device=h.device)
+        eng.prepare_conditions_cached(xf_out, z, self._condition(c))
+        return eng.layers_forward(h, emb)
 
     def forward(self, motion, timesteps, motion_mask=None, motion_length=None, num_intervals=1, c=None, **kwargs):
         """controlnet_mcm.py:168-233 + forward_test :306-361 (eval)."""

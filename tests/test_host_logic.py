@@ -117,7 +117,7 @@ def test_struct_layouts_match_header():
     fields = re.findall(r"^\s*int\s+([a-z_]+);", cfg_body, re.M)
     assert fields == [f[0] for f in _lib.McmConfig._fields_]
     smp_body = re.search(r"typedef struct mcm_sampler \{(.*?)\} mcm_sampler;", header, re.S).group(1)
-    fields = re.findall(r"^\s*(?:const\s+)?(?:int|float)\*?\s+([a-z_0-9]+);", smp_body, re.M)
+    fields = re.findall(r"^\s*(?:const\s+)?(?:int|float|unsigned long long)\*?\s+([a-z_0-9]+);", smp_body, re.M)
     assert fields == [f[0] for f in _lib.McmSampler._fields_]
 
 
