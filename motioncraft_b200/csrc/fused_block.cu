@@ -119,6 +119,16 @@ __device__ __forceinline__ void add_bias32(float* slot, int lane, float mine, fl
   __syncwarp();
 }
 
+// Column ownership of the compute warps in the thread-per-row E phases.  The accumulator is produced in two 256-column TMEM
+// halves (the two N passes of a 512-wide GEMM), and the MMA warp publishes each half as soon as it is complete, so that
+// the E phase of half 0 runs under the MMAs of half 1.  For that every warp owns columns in BOTH halves: with two warps
+// per lane quadrant (NCW == 8), warp `part` owns [part * 128, +128) of half 0 and of half 1 -- i.e. heads {part, 2 + part};
+// chunk c of a warp (32 columns) lives in half c >> 2.  With four warps per quadrant each warp owns 128 contiguous columns.
+__device__ __forceinline__ int ccol(int part, int c) {
+  if (NCW == 8) return ((c >> 2) << 8) + part * 128 + ((c & 3) << 5);
+  return part * CPW + c * 32;
+}
+
 // ---- P phase: 128 rows of h -> (LayerNorm) -> fp16 -> OPA.  Warp per row, the reduction order of ln_rows_kernel.
 // Two rows per iteration; the next iteration's rows are requested before the current ones are reduced (there is
 // next to no L1 beside 225 KB of shared memory, so every row is an L2 / HBM round trip).
@@ -193,11 +203,13 @@ __device__ __forceinline__ void rows_to_opa(const float* __restrict__ h, int row
 // OPA receives the UN-normalised exp(q - max) (in (0, 1], the same relative fp16 rounding as the normalised value);
 // the 1 / sum of each head is returned in inv0 / inv1 and applied to the fp32 accumulator of q * ctx by the same thread
 // in E2 (y = softmax(q) ctx is linear in the scale of q per head).  Two streaming passes over TMEM, 32 live values.
+template <typename WaitHalf>
 __device__ __forceinline__ void epi_softmax(uint32_t trow, int part, int row, uint32_t opa, float* bslot, int lane,
-                                            const float* __restrict__ bias, float& inv0, float& inv1) {
+                                            const float* __restrict__ bias, float& inv0, float& inv1, WaitHalf&& wait_half) {
 #pragma unroll 1
   for (int i = 0; i < CPW / HD; ++i) {
-    const int col0 = part * CPW + i * 128;
+    const int col0 = ccol(part, 4 * i);      // this warp's head in TMEM half i (NCW == 8) / its only head (NCW == 16)
+    wait_half(col0 >> 8);
     float m = -INFINITY;
     float bcur = __ldg(bias + col0 + lane);
 #pragma unroll 1
@@ -217,6 +229,9 @@ __device__ __forceinline__ void epi_softmax(uint32_t trow, int part, int row, ui
     }
     const float ml = m * L2E;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    // the numerators overwrite the operand tile, which the MMAs of BOTH halves read (K = all 512 columns): only the max
+    // pass above may run under the second half's MMAs
+    wait_half(0); wait_half(1);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {       // bcur holds chunk 0's bias again (the prefetch index wraps)
       float v[32];
@@ -247,22 +262,23 @@ __device__ __forceinline__ void epi_softmax(uint32_t trow, int part, int row, ui
 // gamma' = w (1 + scale), beta' = b (1 + scale) + shift were staged per sample in shared memory (prm: [gamma' 512 | beta' 512]).
 // The two warps of a lane quadrant each own 256 columns and exchange (mean, M2) partial statistics; the statistics
 // are accumulated about the row's first element so that one pass suffices without cancellation.
-template <bool BIAS, bool SCALE>
+template <bool BIAS, bool SCALE, typename WaitHalf>
 __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool act, const float* prm, float* xch, int ew,
                                           int quad, uint32_t opa, float* bslot, int lane, const float* __restrict__ bias,
-                                          float inv0, float inv1) {
+                                          float inv0, float inv1, WaitHalf&& wait_half) {
   float K = 0.f, sd = 0.f, sq = 0.f;
-  float bcur = BIAS ? __ldg(bias + part * CPW + lane) : 0.f;
-  float bcur2 = BIAS ? __ldg(bias + part * CPW + 32 + lane) : 0.f;
+  float bcur = BIAS ? __ldg(bias + ccol(part, 0) + lane) : 0.f;
+  float bcur2 = BIAS ? __ldg(bias + ccol(part, 1) + lane) : 0.f;
   float sd2 = 0.f, sq2 = 0.f;                 // second accumulator chain (tile pairs: two TMEM loads in flight)
 #pragma unroll 1
   for (int c = 0; c < NCH; c += 2) {
     float v[32], w[32];
-    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
-    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32 + 32), w);
+    wait_half(ccol(part, c) >> 8);            // the statistics pass of TMEM half 0 runs under the MMAs of half 1
+    tmem_ld_32x32(trow + (uint32_t)ccol(part, c), v);
+    tmem_ld_32x32(trow + (uint32_t)ccol(part, c + 1), w);
     const int cn = (c + 2) & (NCH - 1);
-    const float bnxt = BIAS ? __ldg(bias + part * CPW + cn * 32 + lane) : 0.f;
-    const float bnxt2 = BIAS ? __ldg(bias + part * CPW + cn * 32 + 32 + lane) : 0.f;
+    const float bnxt = BIAS ? __ldg(bias + ccol(part, cn) + lane) : 0.f;
+    const float bnxt2 = BIAS ? __ldg(bias + ccol(part, cn + 1) + lane) : 0.f;
     tmem_ld_wait();
     if (BIAS) {
       add_bias32(bslot, lane, bcur, v);
@@ -283,7 +299,7 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
   }
   sd += sd2;
   sq += sq2;
-  bcur = BIAS ? __ldg(bias + part * CPW + lane) : 0.f;
+  bcur = BIAS ? __ldg(bias + ccol(part, 0) + lane) : 0.f;
   const float mean_w = fmaf(sd, 1.f / (float)CPW, K);
   const float m2_w = fmaf(-sd * (1.f / (float)CPW), sd, sq);
   xch[(ew * 32 + lane) * 2] = mean_w;
@@ -305,15 +321,15 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {        // bcur holds chunk 0's bias again
     float v[32];
-    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
-    const float bnxt = BIAS ? __ldg(bias + part * CPW + ((c + 1) & (NCH - 1)) * 32 + lane) : 0.f;
+    tmem_ld_32x32(trow + (uint32_t)ccol(part, c), v);
+    const float bnxt = BIAS ? __ldg(bias + ccol(part, (c + 1) & (NCH - 1)) + lane) : 0.f;
     tmem_ld_wait();
     if (BIAS) add_bias32(bslot, lane, bcur, v);
     bcur = bnxt;
     // (x sc - mean) rstd = x A + B
     const float A = SCALE ? ((c >> 2) ? inv1 : inv0) * rstd : rstd;
     const float Bc = -mean * rstd;
-    const int col = part * CPW + c * 32;
+    const int col = ccol(part, c);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 ga = *reinterpret_cast<const float4*>(prm + col + 8 * q);
@@ -336,31 +352,59 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
   }
 }
 
-// ---- E3 / E6: h[rows, 256 columns of this warp] += acc + bias, 32 x 32 fp32 tiles through the warp's staging slot
-// (two 4 KB halves... the slot is 4 KB, so a tile waits for the previous reduction to have READ the slot)
-// `stg4`: 16 KB of the (idle) operand tile private to this warp = 4 rotating 4 KB slots, so a tile only waits for the
-// reduction issued 4 tiles earlier to have read its slot.
-__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int part, uint32_t stg4, const CUtensorMap* map, int grow0,
-                                             float* bslot, int lane, const float* __restrict__ bias, bool& pending) {
-  // two 32-column tiles per iteration: both TMEM loads are in flight together and one bulk group carries both reductions
-  static_assert(NCH % 2 == 0 && RED_SLOTS % 2 == 0, "tile pairs");
-  float b0 = __ldg(bias + part * CPW + lane), b1 = __ldg(bias + part * CPW + 32 + lane);
+// ---- E3 / E6: h[rows, 256 columns of this warp] += acc + bias, 32 x 32 fp32 tiles, TMA reduce-add.
+// Half 0 (chunks 0..3 of the warp) is reduced while the MMAs of half 1 still READ the operand tile, so its staging tile
+// must live elsewhere: `stg1`, one 4 KB slot per warp in the parameter staging region, which is idle in E3 / E6 (the
+// caller has synchronised the compute warps).  One tile at a time, each waiting for the previous reduction to have read
+// the slot.  Half 1 follows once both halves are complete, two tiles per bulk group through `stg4` = 16 KB of the now idle
+// operand tile private to this warp (4 rotating 4 KB slots).
+template <typename WaitHalf>
+__device__ __forceinline__ void epi_reduce_h(uint32_t trow, int part, uint32_t stg1, uint32_t stg4, const CUtensorMap* map,
+                                             int grow0, float* bslot, int lane, const float* __restrict__ bias, bool& pending,
+                                             WaitHalf&& wait_half) {
+  static_assert(NCW == 8 && NCH == 8 && RED_SLOTS == 4, "the split reduction assumes two warps per lane quadrant");
+  wait_half(0);
+  {
+    float b0 = __ldg(bias + ccol(part, 0) + lane);
 #pragma unroll 1
-  for (int c = 0; c < NCH; c += 2) {
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+      tmem_ld_32x32(trow + (uint32_t)ccol(part, c), v);
+      const float n0 = __ldg(bias + ccol(part, (c + 1) & 3) + lane);
+      tmem_ld_wait();
+      add_bias32(bslot, lane, b0, v);
+      b0 = n0;
+      if (pending) {                          // the previous reduction (or an older bulk store) has read the slot
+        if (lane == 0) tma_wait_read0();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        st_shared_v4(stg1 + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(map, stg1, ccol(part, c), grow0, 0);
+        tma_commit();
+      }
+      pending = true;
+    }
+  }
+  wait_half(1);
+  // two 32-column tiles per iteration: both TMEM loads are in flight together and one bulk group carries both reductions
+  float b0 = __ldg(bias + ccol(part, 4) + lane), b1 = __ldg(bias + ccol(part, 5) + lane);
+#pragma unroll 1
+  for (int c = 4; c < NCH; c += 2) {
     float v[32], w[32];
-    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32), v);
-    tmem_ld_32x32(trow + (uint32_t)(part * CPW + c * 32 + 32), w);
-    const int cn = (c + 2) & (NCH - 1);
-    const float n0 = __ldg(bias + part * CPW + cn * 32 + lane), n1 = __ldg(bias + part * CPW + cn * 32 + 32 + lane);
+    tmem_ld_32x32(trow + (uint32_t)ccol(part, c), v);
+    tmem_ld_32x32(trow + (uint32_t)ccol(part, c + 1), w);
+    const int cn = 4 + ((c + 2) & 3);
+    const float n0 = __ldg(bias + ccol(part, cn) + lane), n1 = __ldg(bias + ccol(part, cn + 1) + lane);
     tmem_ld_wait();
     add_bias32(bslot, lane, b0, v);
     add_bias32(bslot, lane, b1, w);
     b0 = n0; b1 = n1;
     const uint32_t sa = stg4 + (uint32_t)(c & (RED_SLOTS - 1)) * 4096u, sb = sa + 4096u;
-    if (c >= RED_SLOTS) {
-      if (lane == 0) { if (RED_SLOTS == 4) tma_wait_read1(); else tma_wait_read0(); }
-      __syncwarp();
-    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       st_shared_v4(sa + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -369,8 +413,8 @@ __device__ __forceinline__ void epi_reduce_h(uint32_t trow, int part, uint32_t s
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_reduce_add_3d(map, sa, part * CPW + c * 32, grow0, 0);
-      tma_reduce_add_3d(map, sb, part * CPW + c * 32 + 32, grow0, 0);
+      tma_reduce_add_3d(map, sa, ccol(part, c), grow0, 0);
+      tma_reduce_add_3d(map, sb, ccol(part, c + 1), grow0, 0);
       tma_commit();
     }
     pending = true;
@@ -561,11 +605,14 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
       };
       // a full-width GEMM out of the resident operand tile: D[128(x2) x 512] = OPA[.. x 512] W[512 x 512]^T
+      // (each 256-column half is published as soon as its MMAs are issued: the E phase of half 0 overlaps half 1)
       auto gemm_opa_512 = [&]() {
 #pragma unroll 1
-        for (int n = 0; n < 2; ++n)
+        for (int n = 0; n < 2; ++n) {
 #pragma unroll 1
           for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)(n * 256), idesc256, kb == 0);
+          commit_tf(n);
+        }
       };
 #pragma unroll 1
       for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
@@ -575,24 +622,23 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         if (last >= 2) {                                     // G1
           wait_te(0); wait_te(1);
           gemm_opa_512();
-          commit_tf(0); commit_tf(1);
         }
         if (last >= 3) {                                     // G2, one round per sample
 #pragma unroll 1
           for (int s = s_first; s <= s_last; ++s) {
             wait_te(0); wait_te(1);
 #pragma unroll 1
-            for (int hd = 0; hd < H; ++hd)
+            for (int hd = 0; hd < H; ++hd) {
 #pragma unroll 1
               for (int kb = 0; kb < HD / 64; ++kb)
                 step(opa + (uint32_t)(hd * 2 + kb) * SLAB, (uint32_t)(hd * HD), idesc128, kb == 0);
-            commit_tf(0); commit_tf(1);
+              if (hd & 1) commit_tf(hd >> 1);                 // heads 0, 1 = TMEM half 0; heads 2, 3 = half 1
+            }
           }
         }
         if (last >= 4) {                                     // G3
           wait_te(0); wait_te(1);
           gemm_opa_512();
-          commit_tf(0); commit_tf(1);
         }
         if (last >= 5) {                                     // G4: four 256-column quarters, alternating TMEM halves
 #pragma unroll 1
@@ -621,7 +667,6 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         if (last >= 7) {                                     // G6
           wait_te(0); wait_te(1);
           gemm_opa_512();
-          commit_tf(0); commit_tf(1);
         }
       }
       if (prof && lane == 0) {
@@ -648,6 +693,19 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       mbar_wait(smem_u32(&tfull_bar[hh]), tf_par[hh]);
       tf_par[hh] ^= 1u;
       tc_fence_after();
+    };
+    // a phase consumes each TMEM half exactly once, whichever chunk touches it first; `finish` closes the phase (a warp
+    // that skipped its epilogue still has to follow the barrier phases)
+    bool got_half[2] = {false, false};
+    auto wait_half = [&](int hh) {
+      if (!got_half[hh]) {
+        wait_tf(hh);
+        got_half[hh] = true;
+      }
+    };
+    auto finish_halves = [&]() {
+      wait_half(0); wait_half(1);
+      got_half[0] = got_half[1] = false;
     };
     // operand tile written / accumulator drained: tell the leader's MMA warp
     auto arrive_te = [&](bool h0, bool h1) {
@@ -705,9 +763,9 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       if (it == 0) FB_TICK(15 + 4); else FB_TICK(0);
       if (done < last) {
         // ---- E1
-        wait_tf(0); wait_tf(1);
         FB_TICK(1);
-        epi_softmax(trow, part, row, opa, bslot, lane, p.ca_bq, qinv0, qinv1);
+        epi_softmax(trow, part, row, opa, bslot, lane, p.ca_bq, qinv0, qinv1, wait_half);
+        finish_halves();
         if (++done < last) arrive_te(true, true);
         FB_TICK(2);
       }
@@ -717,20 +775,22 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         bar_sync(5, NCW * 32);
         ++done;
         for (int s = s_first; s <= s_last; ++s) {
-          wait_tf(0); wait_tf(1);
           FB_TICK(3);
           const bool act = (s_row == s) && (grow < p.rows);
           if (__any_sync(0xffffffffu, act))
-            epi_lnmod<false, true>(trow, part, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, nullptr, qinv0, qinv1);
+            epi_lnmod<false, true>(trow, part, row, act, prm_all + (s - s_first) * 1024, xch, ew, quad, opa, bslot, lane, nullptr, qinv0, qinv1, wait_half);
+          finish_halves();
           if (s < s_last || done < last) arrive_te(true, true);
           FB_TICK(4);
         }
       }
       if (done < last) {
         // ---- E3: h += d + bo, then OPA = fp16(h)
-        wait_tf(0); wait_tf(1);
         FB_TICK(5);
-        epi_reduce_h(trow, part, opa + (uint32_t)ew * (OPA_BYTES / NCW), &tm.hred, gc + quad * 32, bslot, lane, p.ca_bo, pending);
+        bar_sync(5, NCW * 32);                               // every warp is past E2: the parameter staging region is free
+        epi_reduce_h(trow, part, stg + (uint32_t)ew * 4096u, opa + (uint32_t)ew * (OPA_BYTES / NCW), &tm.hred, gc + quad * 32,
+                     bias4_s[ew], lane, p.ca_bo, pending, wait_half);
+        finish_halves();
         tc_fence_before();
         FB_TICK(6);
         drain_stores(true);
@@ -754,10 +814,12 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
             FB_TICK(9);
           }
           float v[32];
+          const long long e4a = prof ? clock64() : 0;
           tmem_ld_32x32(trow + (uint32_t)((q & 1) * 256 + part * QW + c * 32), v);
           const int nidx = (idx + 1) % (4 * QCH);
           const float bnxt = __ldg(p.f_b1 + (nidx / QCH) * 256 + part * QW + (nidx % QCH) * 32 + lane);
           tmem_ld_wait();
+          const long long e4b = prof ? clock64() : 0;
           // the staging region belongs to the hidden-tile stores in this phase: bias goes through a static slot
           if (NCW == 8) {
             add_bias32(bias4_s[NCW == 8 ? ew : 0], lane, bcur, v);
@@ -768,6 +830,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
             for (int j = 0; j < 32; ++j) v[j] = gelu_relu_erfc(v[j] + __shfl_sync(0xffffffffu, bcur, j));
           }
           bcur = bnxt;
+          const long long e4c = prof ? clock64() : 0;
           const uint32_t sl = stgw + (uint32_t)(idx & (E4_SLOTS - 1)) * 2048u;
           if (idx >= E4_SLOTS) {
             if (lane == 0) { if (E4_SLOTS == 2) tma_wait_read1(); else tma_wait_read0(); }
@@ -785,6 +848,10 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
             tma_store_3d(&tm.hidst, sl, q * 256 + part * QW + c * 32, (int)blockIdx.x * ROWS + quad * 32, 0);
             tma_commit();
           }
+          if (prof) {
+            const long long e4d = clock64();
+            tph[16] += e4b - e4a; tph[17] += e4c - e4b; tph[18] += e4d - e4c;
+          }
           if (c == QCH - 1) {
             if (q < 2 || done < last) arrive_te((q & 1) == 0, (q & 1) == 1);
             FB_TICK(10);
@@ -801,18 +868,19 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         bar_sync(5, NCW * 32);                               // all warps' staging slots are free
         stage_params(prm_all, nsamp, s_first, p.batch, p.f_pn_w, p.f_pn_b, p.f_scale, p.f_shift, p.mod_ld, ctid);
         bar_sync(5, NCW * 32);
-        wait_tf(0); wait_tf(1);
         FB_TICK(12);
-        epi_lnmod<true, false>(trow, part, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, p.f_b2, 1.f, 1.f);
+        epi_lnmod<true, false>(trow, part, row, true, prm_all + slot_row * 1024, xch, ew, quad, opa, bslot, lane, p.f_b2, 1.f, 1.f, wait_half);
+        finish_halves();
         if (++done < last) arrive_te(true, true);
         FB_TICK(13);
       }
       if (done < last) {
         // ---- E6
         bar_sync(5, NCW * 32);                               // nobody still reads the staged parameters / statistics
-        wait_tf(0); wait_tf(1);
         FB_TICK(14);
-        epi_reduce_h(trow, part, opa + (uint32_t)ew * (OPA_BYTES / NCW), &tm.hred, gc + quad * 32, bslot, lane, p.f_bo, pending);
+        epi_reduce_h(trow, part, stg + (uint32_t)ew * 4096u, opa + (uint32_t)ew * (OPA_BYTES / NCW), &tm.hred, gc + quad * 32,
+                     bias4_s[ew], lane, p.f_bo, pending, wait_half);
+        finish_halves();
         tc_fence_before();
         ++done;
         FB_TICK(15);
@@ -836,6 +904,8 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
 #pragma unroll
       for (int i = 0; i < 16; ++i) atomicAdd(p.prof + i, (unsigned long long)tph[i]);
       atomicAdd(p.prof + 19, (unsigned long long)tph[19]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) atomicAdd(p.prof + 20 + i, (unsigned long long)tph[16 + i]);
     }
 #undef FB_TICK
   }

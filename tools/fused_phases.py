@@ -34,3 +34,4 @@ print(f"  total per tile {(tot + out[19])/nw:10.0f} cyc")
 first = min(tiles, 74)
 print(f"  P0 of a CTA's FIRST tile: {out[19]/(NCW*2*first):.0f} cyc; later tiles: {out[0]/max(1,NCW*2*(tiles-first)):.0f} cyc")
 print(f"MMA warp per tile: wait tempty {out[16]/tiles:.0f}, wait full {out[17]/tiles:.0f}, total {out[18]/tiles:.0f}")
+print(f"E4 split per tile: TMEM load+wait {out[20]/nw:.0f}, bias+GELU {out[21]/nw:.0f}, staging wait+STS+fence+TMA issue {out[22]/nw:.0f}")
