@@ -207,33 +207,59 @@ class MCMTransformer(nn.Module):
         if self.use_text_proj:
             self.text_proj = nn.Sequential(nn.Linear(tl, self.time_embed_dim))
 
-    def encode_text(self, text, clip_feat, device):
-        # diffusion_transformer.py:147-172 -- once per batch, not part of the per-step hot path.
-        if self.clip is None:
-            try:
-                import clip  # noqa: F401
-            except ImportError as e:
-                raise McmError("text conditioning needs the `clip` package and its ViT-B/32 weights, which are not "
-                               "available offline; pass precomputed xf_proj / xf_out (mcm.py:65)") from e
-            self.clip, _ = clip.load("ViT-B/32", "cpu")
-            for p in self.clip.parameters():
-                p.requires_grad = False
-        import clip
-        tokens = clip.tokenize(text, truncate=True).to(device)
+    def _clip_module(self):
+        try:
+            import clip
+        except ImportError as e:
+            raise McmError("tokenising text / running the frozen CLIP tower needs the `clip` package and its ViT-B/32 "
+                           "weights, which are not available offline: pass precomputed xf_proj / xf_out (mcm.py:65), or "
+                           "clip_feat together with eos_index (the position of CLIP's end-of-text token)") from e
+        return clip
+
+    def encode_text(self, text, clip_feat, device, eos_index=None):
+        """diffusion_transformer.py:147-172 -- ONCE per sampling run, not part of the per-step hot path: the trainable
+        stack text_pre_proj -> nn.TransformerEncoder -> text_ln -> text_proj runs through torch's library kernels on the
+        model's device (the same policy as the WavEncoder).
+
+        `eos_index` (B,) is an extension: the reference takes the end-of-text position from `clip.tokenize(text).argmax(-1)`
+        (:165); callers that hold pre-computed `clip_feat` (the datasets' clip_feat_dir) can pass the position instead of
+        having the `clip` package tokenise again."""
+        tokens = None
+        if eos_index is None or clip_feat is None:
+            clip = self._clip_module()
+            tokens = clip.tokenize(text, truncate=True).to(device)
+            if eos_index is None:
+                eos_index = tokens.argmax(dim=-1)
+        dtype = self.text_ln.weight.dtype
         if clip_feat is None:
+            if self.clip is None:
+                self.clip, _ = clip.load("ViT-B/32", "cpu")
+                for p in self.clip.parameters():
+                    p.requires_grad = False
+                self.clip = self.clip.to(device)
             with torch.no_grad():
                 x = self.clip.token_embedding(tokens).type(self.clip.dtype)
                 x = x + self.clip.positional_embedding.type(self.clip.dtype)
-                x = self.clip.ln_final(self.clip.transformer(x.permute(1, 0, 2))).type(self.clip.dtype)
+                x = self.clip.ln_final(self.clip.transformer(x.permute(1, 0, 2))).type(dtype)
         else:
-            x = clip_feat.type(self.clip.dtype).to(device).permute(1, 0, 2)
-        xf_out = self.text_ln(self.textTransEncoder(self.text_pre_proj(x)))
-        xf_proj = self.text_proj(xf_out[tokens.argmax(dim=-1), torch.arange(xf_out.shape[1])])
-        return xf_proj, xf_out.permute(1, 0, 2)
+            x = clip_feat.to(device=device, dtype=dtype).permute(1, 0, 2)
+        with torch.no_grad():
+            x = self.text_pre_proj(x)
+            if self.use_text_finetune:
+                x = self.textTransEncoder(x)
+            xf_out = self.text_ln(x)
+            eos_index = torch.as_tensor(eos_index, device=xf_out.device).long()
+            if self.use_text_proj:
+                xf_proj = self.text_proj(xf_out[eos_index, torch.arange(xf_out.shape[1], device=xf_out.device)])
+                return xf_proj, xf_out.permute(1, 0, 2).contiguous()
+            return None, xf_out.permute(1, 0, 2).contiguous()
 
-    def get_precompute_condition(self, text=None, xf_proj=None, xf_out=None, device=None, clip_feat=None, **kwargs):
-        if xf_proj is None or xf_out is None:
-            xf_proj, xf_out = self.encode_text(text, clip_feat, device)
+    def get_precompute_condition(self, text=None, xf_proj=None, xf_out=None, device=None, clip_feat=None, eos_index=None,
+                                 **kwargs):
+        if xf_out is None or (xf_proj is None and self.use_text_proj):
+            if self._text_cfg is None:
+                raise McmError("this model was built without a text encoder: pass xf_proj / xf_out (mcm.py:65)")
+            xf_proj, xf_out = self.encode_text(text, clip_feat, device, eos_index=eos_index)
         return {"xf_proj": xf_proj, "xf_out": xf_out}
 
     def post_process(self, motion):
@@ -348,6 +374,18 @@ def state_shapes(seq_len=196, input_feats=322, latent_dim=512, time_embed_dim=20
         m = MCMTransformer(**mcm_config(seq_len, input_feats, latent_dim, time_embed_dim, ffn_dim, text_latent_dim,
                                         num_heads, num_layers))
     return {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+
+TEXT_ENCODER_CFG = dict(pretrained_model="clip", latent_dim=256, num_layers=4, num_heads=4, ff_size=2048, dropout=0,
+                        use_text_proj=True)      # configs/mcm/mcm_t2m_smplx.py:58-64
+
+
+def text_state_shapes(seq_len=60, text_encoder=None):
+    """name -> shape of the trainable text-side parameters (text_pre_proj / textTransEncoder / text_ln / text_proj)."""
+    with torch.device("meta"):
+        m = MCMTransformer(**mcm_config(seq_len, num_layers=1, text_encoder=dict(text_encoder or TEXT_ENCODER_CFG)))
+    return {k: tuple(v.shape) for k, v in m.state_dict().items()
+            if k.startswith(("text_pre_proj.", "textTransEncoder.", "text_ln.", "text_proj."))}
 
 
 def mcm_config(seq_len=196, input_feats=322, latent_dim=512, time_embed_dim=2048, ffn_dim=1024, text_latent_dim=256,

@@ -17,6 +17,7 @@ import torch
 # seeds fixed by SURVEY.md section 8(d)
 SEED_WEIGHTS, SEED_XT, SEED_XF_OUT, SEED_XF_PROJ, SEED_STEP_NOISE, SEED_C_EMB, SEED_C_M2D = 0, 123, 124, 125, 126, 127, 128
 SEED_REPAINT_GT, SEED_REPAINT_NOISE = 131, 132
+SEED_CLIP_FEAT = 133
 
 
 def _gen(seed, name):

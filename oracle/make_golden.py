@@ -177,6 +177,30 @@ def repaint(T=60, B=2, L=10):
     print("repaint", {k: (v.shape, float(np.abs(v).max())) for k, v in out.items() if v.dtype.kind == "f"})
 
 
+TEXTS = ["a person walks forward and stumbles .", "jump", "the person is squatting , bending at the knees , keeping their "
+         "back straight , while extending their arms ."]
+
+
+def text_stack(B=3):
+    """Trainable text-side stack (diffusion_transformer.py:157-171) of the reference with `clip_feat` supplied: the
+    reference's own encode_text through the clip stand-in of ref_shim (frozen CLIP tower absent; EOT position from the
+    stand-in tokenizer)."""
+    ref = ref_shim.build_reference_mcm(T=60, num_layers=1, text_encoder=dict(ref_shim.TEXT_ENCODER_CFG))
+    names = {k: v.shape for k, v in ref.state_dict().items()
+             if k.startswith(("text_pre_proj.", "textTransEncoder.", "text_ln.", "text_proj."))}
+    sd = synth.synth_state_dict(names)
+    ref.load_state_dict(sd, strict=False)
+    clip_feat = synth.synth_tensor("clip_feat", (B, 77, 512), synth.SEED_CLIP_FEAT)
+    with torch.no_grad():
+        xf_proj, xf_out = ref.encode_text(TEXTS[:B], clip_feat, "cpu")
+        cond = ref.get_precompute_condition(text=TEXTS[:B], clip_feat=clip_feat, device="cpu")
+    assert torch.equal(cond["xf_proj"], xf_proj) and torch.equal(cond["xf_out"], xf_out)
+    eos = ref_shim.stub_clip_tokenize(TEXTS[:B]).argmax(dim=-1)
+    np.savez_compressed(os.path.join(GOLD, "text_stack.npz"), xf_proj=xf_proj.numpy(), xf_out=xf_out.numpy(),
+                        eos_index=eos.numpy(), keys=np.array(sorted(names.keys())), texts=np.array(TEXTS[:B]))
+    print("text_stack: xf_proj", tuple(xf_proj.shape), "xf_out", tuple(xf_out.shape), "eos", eos.tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -185,3 +209,4 @@ if __name__ == "__main__":
     ctrl()
     repaint()
     wav_encoder()
+    text_stack()

@@ -225,6 +225,46 @@ def control_forward(sd, motion, timesteps, xf_proj, xf_out, c, num_heads=4, mm_r
 # ----------------------------------------------------------------------------------------------
 # diffusion schedule (float64 numpy, once)
 # ----------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# Trainable text-side stack (once per sampling run): DiffusionTransformer.encode_text with `clip_feat` supplied
+# (mogen/models/transformers/diffusion_transformer.py:157-171; modules built at :123-145).  The frozen CLIP tower
+# (:148-156) is an un-vendored third-party model (openai/CLIP, unpinned in requirements.txt:5) and is NOT restated:
+# its output `clip_feat` (B, 77, 512) is an input here, and so is the EOT position `text.argmax(-1)` (:165).
+# ---------------------------------------------------------------------------------------------
+def text_encoder_layer(x, sd, prefix, nhead):
+    """nn.TransformerEncoderLayer (post-norm, activation='gelu', dropout 0, batch_first=False: x is (N, B, E)) as
+    torch.nn.modules.transformer evaluates it on its non-fused path (batch_first=False rules the fused path out)."""
+    E = x.shape[-1]
+    sa, _ = F.multi_head_attention_forward(
+        x, x, x, E, nhead, sd[prefix + ".self_attn.in_proj_weight"], sd[prefix + ".self_attn.in_proj_bias"], None, None,
+        False, 0.0, sd[prefix + ".self_attn.out_proj.weight"], sd[prefix + ".self_attn.out_proj.bias"], training=False,
+        need_weights=False)
+    x = F.layer_norm(x + sa, (E,), sd[prefix + ".norm1.weight"], sd[prefix + ".norm1.bias"])
+    ff = F.linear(F.gelu(F.linear(x, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"])),
+                  sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"])
+    return F.layer_norm(x + ff, (E,), sd[prefix + ".norm2.weight"], sd[prefix + ".norm2.bias"])
+
+
+def encode_text_stack(sd, clip_feat, eos_index, nhead=4):
+    """clip_feat (B, 77, 512), eos_index (B,) -> (xf_proj (B, time_embed_dim), xf_out (B, 77, L))   [:157-171]"""
+    x = clip_feat.permute(1, 0, 2)                                                        # :155
+    if "text_pre_proj.weight" in sd:
+        # x is a NON-contiguous permuted view here, so at::linear takes its matmul + add_ route, and at::matmul folds the
+        # batch dimensions into one mm only when the weight `requires_grad` (it does in the reference: text_pre_proj is a
+        # trainable nn.Linear) -- a different fp32 summation order from the batched route.  Reproduce that property.
+        w = sd["text_pre_proj.weight"].detach().clone().requires_grad_(True)
+        with torch.no_grad():
+            x = F.linear(x, w, sd["text_pre_proj.bias"])                                 # :158
+    n_layers = 1 + max([int(k.split(".")[2]) for k in sd if k.startswith("textTransEncoder.layers.")], default=-1)
+    for i in range(n_layers):                                                             # :159
+        x = text_encoder_layer(x, sd, f"textTransEncoder.layers.{i}", nhead)
+    L = x.shape[-1]
+    xf_out = F.layer_norm(x, (L,), sd["text_ln.weight"], sd["text_ln.bias"])             # :160
+    sel = xf_out[eos_index.long(), torch.arange(xf_out.shape[1])]                         # :162-163
+    xf_proj = F.linear(sel, sd["text_proj.0.weight"], sd["text_proj.0.bias"])
+    return xf_proj, xf_out.permute(1, 0, 2)                                               # :165-166
+
+
 def linear_beta_schedule(num_steps=1000):
     """get_named_beta_schedule('linear', n), gaussian_diffusion.py:235-253."""
     scale = 1000 / num_steps

@@ -70,6 +70,37 @@ def _default_build(cfg, registry, default_args=None):
     return cls(**args)
 
 
+SOT_TOKEN, EOT_TOKEN = 49406, 49407     # CLIP's start / end-of-text ids; EOT is the largest id, which is what
+                                        # `text.argmax(dim=-1)` (diffusion_transformer.py:165) relies on
+
+
+def stub_clip_tokenize(texts, context_length=77, truncate=False):
+    """Stand-in for clip.tokenize (the BPE vocabulary is not available offline): one pseudo-token per whitespace-separated
+    word, framed by SOT / EOT and zero-padded to 77 -- enough to reproduce the ONE thing the trainable text stack takes
+    from the tokens, the position of EOT."""
+    import torch
+    if isinstance(texts, str):
+        texts = [texts]
+    out = torch.zeros(len(texts), context_length, dtype=torch.int)
+    for i, t in enumerate(texts):
+        words = t.split()[: context_length - 2]
+        ids = [SOT_TOKEN] + [1000 + (sum(map(ord, w)) % 40000) for w in words] + [EOT_TOKEN]
+        out[i, : len(ids)] = torch.tensor(ids, dtype=torch.int)
+    return out
+
+
+def stub_clip_load(name, device="cpu", **kw):
+    """Stand-in for clip.load: an object with the attributes `encode_text(..., clip_feat=...)` touches (`.dtype`);
+    the frozen CLIP tower itself is not available, so `clip_feat` must be supplied."""
+    import torch
+    import torch.nn as nn
+
+    class _FrozenClip(nn.Module):
+        dtype = torch.float32
+
+    return _FrozenClip(), None
+
+
 def install():
     """Idempotently install the shim; returns the reference root."""
     if "mogen" in sys.modules and getattr(sys.modules["mogen"], "_mcm_shim", False):
@@ -103,12 +134,8 @@ def install():
         sys.modules.setdefault(name, mod)
 
     clip = types.ModuleType("clip")
-
-    def _no_clip(*a, **k):
-        raise RuntimeError("clip is not available in this image (text encoder must be None)")
-
-    clip.load = _no_clip
-    clip.tokenize = _no_clip
+    clip.load = stub_clip_load
+    clip.tokenize = stub_clip_tokenize
     sys.modules.setdefault("clip", clip)
 
     def _pkg(name, rel):
@@ -126,9 +153,14 @@ def install():
     return REFERENCE_ROOT
 
 
+TEXT_ENCODER_CFG = dict(pretrained_model="clip", latent_dim=256, num_layers=4, num_heads=4, ff_size=2048, dropout=0,
+                        use_text_proj=True)      # configs/mcm/mcm_t2m_smplx.py:58-64
+
+
 def build_reference_mcm(T=196, num_layers=8, input_feats=322, latent_dim=512, time_embed_dim=2048,
-                        text_latent_dim=256, ff_size=1024, num_heads=4):
-    """Reference MCMTransformer built exactly as configs/mcm/mcm_t2m_smplx.py:37-58 does, minus CLIP."""
+                        text_latent_dim=256, ff_size=1024, num_heads=4, text_encoder=None):
+    """Reference MCMTransformer built exactly as configs/mcm/mcm_t2m_smplx.py:37-58 does, minus CLIP
+    (text_encoder=TEXT_ENCODER_CFG builds the trainable text stack around the clip stand-in)."""
     install()
     import mogen.models.attentions.efficient_attention  # noqa: F401  (registers the attention types)
     from mogen.models.transformers.mcm import MCMTransformer
@@ -141,7 +173,7 @@ def build_reference_mcm(T=196, num_layers=8, input_feats=322, latent_dim=512, ti
                           text_latent_dim=text_latent_dim, num_heads=num_heads, dropout=0,
                           time_embed_dim=time_embed_dim),
         ffn_cfg=dict(latent_dim=latent_dim, ffn_dim=ff_size, dropout=0, time_embed_dim=time_embed_dim),
-        text_encoder=None)
+        text_encoder=text_encoder)
     m.use_text_proj = True  # what text_encoder=dict(use_text_proj=True) sets (diffusion_transformer.py:117)
     return m.eval()
 

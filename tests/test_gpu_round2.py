@@ -288,3 +288,34 @@ def test_two_rank_nccl_gather_is_bit_equal_to_single_gpu(tmp_path):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "bit-equal" in r.stdout
+
+
+def test_text_conditioning_stack_on_device(golden_dir):
+    """text_pre_proj -> 4-layer encoder -> text_ln -> text_proj runs ONCE per sampling run on the
+    device (torch library kernels) from `clip_feat` + the EOT position; against the reference's encode_text output, then the
+    whole text -> x_0 chain through MotionDiffusion.forward against the oracle fed with the reference's embeddings."""
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "text_stack.npz"))
+    T, B = 60, int(g["xf_proj"].shape[0])
+    dt = dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon", model_var_type="fixed_small")
+    cfg = dict(type="MotionDiffusion",
+               model=dict(type="MCMTransformer", **modules.mcm_config(T, text_encoder=dict(modules.TEXT_ENCODER_CFG))),
+               loss_recon=dict(type="MSELoss", loss_weight=1, reduction="none"), diffusion_train=dt,
+               diffusion_test=dict(dt, respace="15,15,8,6,6"), inference_type="ddim")
+    arch = M.build_architecture(cfg)
+    sd = dict(C.base_state(T))
+    sd.update(synth.synth_state_dict(modules.text_state_shapes()))
+    arch.model.load_state_dict(sd)
+    arch = arch.cuda().eval()
+    clip_feat = synth.synth_tensor("clip_feat", (B, 77, 512), synth.SEED_CLIP_FEAT)
+    eos = torch.from_numpy(g["eos_index"])
+    cond = arch.model.get_precompute_condition(text=list(g["texts"]), clip_feat=clip_feat.cuda(), eos_index=eos, device="cuda")
+    assert C.rel_l2(cond["xf_proj"], g["xf_proj"]) < 1e-5 and C.rel_l2(cond["xf_out"], g["xf_out"]) < 1e-5
+    x = synth.synth_tensor("x_T", (B, T, 322), synth.SEED_XT)
+    out = arch(motion=torch.zeros(B, T, 322).cuda(), motion_mask=torch.ones(B, T).cuda(),
+               motion_length=torch.full((B,), T).cuda(), motion_metas=[{"text": t} for t in g["texts"]],
+               clip_feat=clip_feat.cuda(), eos_index=eos, inference_kwargs={"noise": x.cuda()}, return_loss=False)
+    got = torch.stack([o["pred_motion"] for o in out])
+    want = C.oracle_ddim(C.base_state(T), x, torch.from_numpy(g["xf_proj"]), torch.from_numpy(g["xf_out"]))
+    assert C.rel_l2(got, want) < TOL_FAST
+    assert out[0]["text"] == str(g["texts"][0])

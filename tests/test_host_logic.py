@@ -207,3 +207,20 @@ def test_repaint_front_end_argument_checks():
     assert (n_den, len(times) - 1 - n_den) == (138, 108) and scheduler.count_draws(times, 50) == 2 * 138 + 108
     assert scheduler.get_schedule_jump_cjm_ddim(25)[0] == 14 and scheduler.get_schedule_jump_cjm_ddim(50)[0] == 29
     assert scheduler.get_schedule_jump_cjm_ddim(50) == list(range(29, -2, -1))      # no resampling: straight walk down
+
+
+def test_text_stack_module_matches_reference_golden(golden_dir):
+    """MCMTransformer.encode_text / get_precompute_condition with clip_feat + eos_index (no `clip` package needed) against
+    the reference's encode_text output; same torch library modules -> bit-identical on the CPU."""
+    g = np.load(os.path.join(golden_dir, "text_stack.npz"))
+    m = M.MCMTransformer(**modules.mcm_config(60, num_layers=1, text_encoder=dict(modules.TEXT_ENCODER_CFG))).eval()
+    from motioncraft_b200 import synth
+    m.load_state_dict(synth.synth_state_dict(modules.text_state_shapes()), strict=False)
+    B = g["xf_proj"].shape[0]
+    clip_feat = synth.synth_tensor("clip_feat", (B, 77, 512), synth.SEED_CLIP_FEAT)
+    cond = m.get_precompute_condition(text=list(g["texts"]), clip_feat=clip_feat, eos_index=torch.from_numpy(g["eos_index"]),
+                                      device="cpu")
+    assert torch.equal(cond["xf_proj"], torch.from_numpy(g["xf_proj"]))
+    assert torch.equal(cond["xf_out"], torch.from_numpy(g["xf_out"]))
+    with pytest.raises(McmError):                      # neither the clip package nor the EOT position: loud failure
+        m.get_precompute_condition(text=list(g["texts"]), clip_feat=clip_feat, device="cpu")

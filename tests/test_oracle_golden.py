@@ -139,3 +139,20 @@ def test_repaint_oracle_matches_reference_golden(golden_dir):
         got = O.ddim_repaint_loop(lambda xx, tt: O.mcm_forward(sd, xx, tt, xf_proj, xf_out), x.clone(), tables, tmap,
                                   tables["betas"], gt, mask, [noise[i] for i in range(n_draw)], times=None, overlap_len=L)
     assert torch.equal(got, torch.from_numpy(g[f"{mode}_x0"])), "oracle must be bit-identical to the reference on this host"
+
+
+def test_text_stack_oracle_matches_reference_golden(golden_dir):
+    """the trainable text-side stack (text_pre_proj -> 4-layer nn.TransformerEncoder -> text_ln
+    -> text_proj at the EOT position, diffusion_transformer.py:157-171) restated in the oracle against outputs of the
+    reference's own encode_text(clip_feat=...) -- bit for bit."""
+    from motioncraft_b200 import modules
+    g = np.load(os.path.join(golden_dir, "text_stack.npz"))
+    shapes = modules.text_state_shapes()
+    assert sorted(shapes.keys()) == list(g["keys"])
+    sd = synth.synth_state_dict(shapes)
+    B = g["xf_proj"].shape[0]
+    clip_feat = synth.synth_tensor("clip_feat", (B, 77, 512), synth.SEED_CLIP_FEAT)
+    with torch.no_grad():
+        xf_proj, xf_out = O.encode_text_stack(sd, clip_feat, torch.from_numpy(g["eos_index"]))
+    assert torch.equal(xf_proj, torch.from_numpy(g["xf_proj"]))
+    assert torch.equal(xf_out, torch.from_numpy(g["xf_out"]))
