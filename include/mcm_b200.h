@@ -154,6 +154,23 @@ typedef struct mcm_repaint {
 int mcm_sample_repaint(mcm_ctx* ctx, const mcm_sampler* s, const mcm_repaint* r, int batch, const float* x_T,
                        float* x0_out, void* stream);
 
+/* Result hand-off, on the device before the one device->host copy.
+ *
+ * replaces: tools/visualize.py:219-249 (motionx branch) -- pred * std + mean, the repack of the 322-dim vector into SMPL-X
+ * poses (165) / expressions (100) / translation (3), and scipy.ndimage.gaussian_filter(col, sigma, mode="nearest") per
+ * column.  float64 and in scipy's accumulation order: bit-identical to the reference's numpy / scipy result.
+ *   pred [B, T, 322] fp32; lengths_dev [B] valid frames (rows beyond stay 0) or NULL; mean / std [322] float64;
+ *   denorm_f32 = 1 when the reference's mean / std arrays are float32 (numpy then de-normalises in float32);
+ *   w_* : normalised Gaussian taps [2 r + 1] (device), as scipy's _gaussian_kernel1d(sigma, 0, r), r = int(4 sigma + 0.5);
+ *   outputs float64 [B, T, 165], [B, T, 100], [B, T, 3]. */
+int mcm_handoff_smplx(const float* pred, int B, int T, const int* lengths_dev, const double* mean_dev, const double* std_dev,
+                      int denorm_f32, const double* w_pose_dev, int r_pose, const double* w_expr_dev, int r_expr,
+                      const double* w_trans_dev, int r_trans, double* pose_out, double* expr_out, double* trans_out,
+                      void* stream);
+/* replaces: BaseMotionDataset.evaluate's face alignment (mogen/datasets/base_dataset.py:121-125):
+ * pred[:, 156:309] = motion[:, 156:309]; pred[:, 312:] = motion[:, 312:]   (rows = B * T, feats = 322). */
+int mcm_handoff_align_faces(float* pred, const float* motion, long long rows, int feats, void* stream);
+
 /* Raw tensor-core GEMM, exposed for unit tests of the kernel itself:
  *   C[M,N] (fp32) = A[M,K] * W[N,K]^T + bias[N]   with A, W fp32 device tensors quantised to
  *   fmt 0 = fp16 (1 pass) or 1 = bf16 hi/lo (3 passes). */
