@@ -167,6 +167,11 @@ int mcm_handoff_smplx(const float* pred, int B, int T, const int* lengths_dev, c
                       int denorm_f32, const double* w_pose_dev, int r_pose, const double* w_expr_dev, int r_expr,
                       const double* w_trans_dev, int r_trans, double* pose_out, double* expr_out, double* trans_out,
                       void* stream);
+/* replaces: `pred_motion * std + mean` on the host (tools/visualize.py:221, tools/m2d_test.py:203, tools/s2g_test.py:216,
+ * MCMTransformer.post_process mcm.py:69-79) with numpy's promotion rules: float32 arithmetic when denorm_f32 = 1 (both
+ * arrays float32), float64 otherwise.  out64 [rows, feats] float64 and / or out32 = its float32 rounding (either may be NULL). */
+int mcm_handoff_denorm(const float* pred, const double* mean_dev, const double* std_dev, long long rows, int feats,
+                       int denorm_f32, double* out64, float* out32, void* stream);
 /* replaces: BaseMotionDataset.evaluate's face alignment (mogen/datasets/base_dataset.py:121-125):
  * pred[:, 156:309] = motion[:, 156:309]; pred[:, 312:] = motion[:, 312:]   (rows = B * T, feats = 322). */
 int mcm_handoff_align_faces(float* pred, const float* motion, long long rows, int feats, void* stream);

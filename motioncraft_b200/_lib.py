@@ -56,6 +56,7 @@ SIGNATURES = {
     "mcm_sample_host": (_I, [_VP, ctypes.POINTER(McmSampler), _I, _VP, _VP, _VP, _VP]),
     "mcm_sample_repaint": (_I, [_VP, ctypes.POINTER(McmSampler), ctypes.POINTER(McmRepaint), _I, _VP, _VP, _VP]),
     "mcm_handoff_smplx": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP]),
+    "mcm_handoff_denorm": (_I, [_VP, _VP, _VP, _LL, _I, _I, _VP, _VP, _VP]),
     "mcm_handoff_align_faces": (_I, [_VP, _VP, _LL, _I, _VP]),
     "mcm_test_randn": (_I, [_VP, _LL, ctypes.c_ulonglong, ctypes.c_ulonglong, _VP]),
     "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),

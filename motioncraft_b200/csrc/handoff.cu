@@ -81,6 +81,23 @@ handoff_smplx_kernel(const HandoffParams p) {
   }
 }
 
+// out = pred * std + mean per feature column, as numpy evaluates `pred_motion * std + mean` (tools/visualize.py:221,
+// tools/m2d_test.py:203, tools/s2g_test.py:216): float32 arithmetic when both arrays are float32, float64 otherwise; the
+// float64 result and its float32 rounding (what `torch.tensor(pred_motion)` assigned into a float32 tensor gives) are
+// both written when requested.
+__global__ void __launch_bounds__(256)
+denorm_kernel(const float* __restrict__ pred, const double* __restrict__ mean, const double* __restrict__ stdv, size_t rows,
+              int feats, int f32, double* __restrict__ out64, float* __restrict__ out32) {
+  const size_t total = rows * (size_t)feats;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % feats);
+    const double v = f32 ? (double)__fadd_rn(__fmul_rn(pred[i], (float)stdv[c]), (float)mean[c])
+                         : __dadd_rn(__dmul_rn((double)pred[i], stdv[c]), mean[c]);
+    if (out64) out64[i] = v;
+    if (out32) out32[i] = (float)v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 align_faces_kernel(float* __restrict__ pred, const float* __restrict__ motion, size_t rows, int feats) {
   const int lo0 = 156, hi0 = 309, lo1 = 312;
@@ -120,6 +137,17 @@ int mcm_handoff_smplx(const float* pred, int B, int T, const int* lengths_dev, c
   p.B = B; p.T = T; p.denorm_f32 = denorm_f32;
   p.pose = pose_out; p.expr = expr_out; p.trans = trans_out;
   handoff_smplx_kernel<<<dim3(N_OUT, B), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  MCM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mcm_handoff_denorm(const float* pred, const double* mean_dev, const double* std_dev, long long rows, int feats,
+                       int denorm_f32, double* out64, float* out32, void* stream) {
+  MCM_CHECK(pred && mean_dev && std_dev && rows >= 1 && feats >= 1 && (out64 || out32), "mcm_handoff_denorm: bad argument");
+  const size_t total = (size_t)rows * (size_t)feats;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  denorm_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, mean_dev, std_dev, (size_t)rows, feats,
+                                                                          denorm_f32, out64, out32);
   MCM_CUDA(cudaGetLastError());
   return 0;
 }

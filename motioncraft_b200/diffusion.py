@@ -130,6 +130,11 @@ class GaussianDiffusion:
         controls the reference's randn_like draws (the streams themselves differ: Philox per step inside the library)."""
         return int(torch.randint(0, 2 ** 62, (1,), device=dev).item())
 
+    def _draw_seed_async(self, salt=0):
+        """A seed for the on-device noise WITHOUT a device->host read (the long-form pipeline must not synchronise):
+        torch's CPU generator, which `torch.manual_seed` also controls."""
+        return int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (int(salt) * 0x9E3779B97F4A7C15 & (2 ** 62 - 1))
+
     def _run(self, model, shape, noise, model_kwargs, mode, eta, step_noise, device):
         B = shape[0]
         model_kwargs = dict(model_kwargs or {})

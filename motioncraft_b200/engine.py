@@ -212,7 +212,9 @@ class DenoiserEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mcm_sample_repaint(self._ctx, ctypes.byref(tables.struct), ctypes.byref(r), x_T.shape[0],
                                                    _ptr(x_T), _ptr(out), _stream(self.device)))
-            torch.cuda.current_stream(self.device).synchronize()     # host arrays / temporaries may go out of scope
+        # No host synchronisation: the host arrays (times, betas, tables) are read while the call ENQUEUES the loop, and
+        # the device temporaries are released to torch's stream-ordered allocator on the stream the loop runs on.
+        del keepalive
         return out
 
     def sample_host(self, tables: SamplerTables, x_T_host, out_host=None, step_noise_host=None):

@@ -70,6 +70,30 @@ def smplx_handoff(pred, mean=None, std=None, lengths=None):
     return {k: v[0] for k, v in out.items()} if squeeze else out
 
 
+class Denormaliser:
+    """`pred * std + mean` on the device with numpy's promotion rules (float32 when both arrays are float32, else float64);
+    the statistics are uploaded once."""
+
+    def __init__(self, mean, std, device):
+        mean, std = np.asarray(mean), np.asarray(std)
+        self.f32 = int(mean.dtype == np.float32 and std.dtype == np.float32)
+        self.device = torch.device(device)
+        self.mean = torch.from_numpy(mean.astype(np.float64)).to(self.device)
+        self.std = torch.from_numpy(std.astype(np.float64)).to(self.device)
+
+    def __call__(self, pred, want64=True, want32=False):
+        """pred (..., F) fp32 CUDA tensor -> (float64 result or None, its float32 rounding or None)."""
+        x = pred.detach().to(torch.float32).contiguous()
+        Fd = x.shape[-1]
+        o64 = torch.empty(x.shape, device=x.device, dtype=torch.float64) if want64 else None
+        o32 = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want32 else None
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mcm_handoff_denorm(_ptr(x), _ptr(self.mean), _ptr(self.std), x.numel() // Fd, Fd, self.f32, _ptr(o64),
+                                              _ptr(o32), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        return o64, o32
+
+
 def align_faces_(pred, motion):
     """In place on the device: pred[..., 156:309] = motion[..., 156:309]; pred[..., 312:] = motion[..., 312:]
     (base_dataset.py:121-125).  pred, motion: (..., 322) fp32 CUDA tensors of the same shape; returns pred."""

@@ -480,6 +480,39 @@ def ddim_repaint_loop(model_fn, x_T, tables, tmap, betas, gt, keep_mask, noise_s
 # ----------------------------------------------------------------------------------------------
 # candidate operand roundings for precision emulation
 # ----------------------------------------------------------------------------------------------
+def longform_windows(model_fn_for_window, n_windows, B, motion_length, pre_frames, overlap_len, tables, tmap, betas, mean, std,
+                     x_T_list, noise_seq_list, times=None, add_blend=True, first_gt=None, feats=322):
+    """The sliding-window driver of tools/m2d_test.py:145-222 / tools/s2g_test.py:144-241 with --repaint, for B sequences at
+    once (the tools run one): window i is a complete sampling run whose first `overlap_len` frames are pinned, through
+    y['gt'] / y['outpainting_mask'], to the tail of `outputs` -- the DE-NORMALISED prediction of window i - 1 (m2d_test.py:189,
+    203-205) -- and the result is concat(pred_i[:round_l] for i < last, pred_last) (:207-210, :219-220).
+    `model_fn_for_window(i)` returns the denoiser closure of window i (its text / control condition);
+    mean / std are numpy arrays, `pred * std + mean` follows numpy's promotion (:203)."""
+    import numpy as np
+    round_l = motion_length - pre_frames
+    outputs, out_motions = None, []
+    for i in range(n_windows):
+        gt = torch.zeros(B, motion_length, feats)
+        keep = torch.zeros(B, motion_length, feats, dtype=torch.bool)
+        if overlap_len > 0:
+            if i == 0 and first_gt is not None:                                              # --fix_very_first (:183-186)
+                keep[:, :overlap_len] = True
+                gt[:, :overlap_len] = first_gt[:, :overlap_len]
+            elif i > 0:                                                                       # :188-190
+                keep[:, :overlap_len] = True
+                gt[:, :overlap_len] = outputs[:, -overlap_len:]
+        fn = model_fn_for_window(i)
+        if bool(keep.any()):
+            x0 = ddim_repaint_loop(fn, x_T_list[i], tables, tmap, betas, gt, keep, noise_seq_list[i], times=times,
+                                   overlap_len=overlap_len, add_blend=add_blend)
+        else:
+            x0 = ddim_sample_loop(fn, x_T_list[i], tables, tmap)
+        pred = x0.numpy() * std + mean                                                        # :203
+        outputs = torch.tensor(pred)                                                          # :205
+        out_motions.append(pred if i == n_windows - 1 else pred[:, :round_l])                # :207-210
+    return np.concatenate(out_motions, axis=1)                                                # :219
+
+
 def round_fp16(x):
     return x.half().to(x.dtype)
 

@@ -319,3 +319,53 @@ def test_text_conditioning_stack_on_device(golden_dir):
     want = C.oracle_ddim(C.base_state(T), x, torch.from_numpy(g["xf_proj"]), torch.from_numpy(g["xf_out"]))
     assert C.rel_l2(got, want) < TOL_FAST
     assert out[0]["text"] == str(g["texts"][0])
+
+
+def test_longform_window_pipeline_vs_oracle():
+    """SURVEY.md 8 row f-2, the rest: the sliding-window drivers of tools/m2d_test.py:145-222 / tools/s2g_test.py:144-241 as a
+    device-side pipeline -- 3 overlapping windows of 2 sequences at once, window i + 1 pinned to the de-normalised tail of
+    window i on the device, harmonising RePaint loop in every pinned window, scripted noise -- against the oracle's
+    restatement of the tools' loop.  The pipeline must not wait for the GPU between windows."""
+    import argparse
+    import numpy as np
+    from motioncraft_b200 import diffusion, longform
+    T, B, W, pre, L = 60, 2, 3, 12, 10
+    sd = synth.synth_state_dict(C.ctrl_shapes(T, 2, 35))
+    base = M.MCMTransformer(**modules.mcm_config(T))
+    base.use_text_proj = True
+    cfg = dict(model=dict(model=modules.mcm_config(T)),
+               condition_encode_cfg=dict(dataset_name="finedance", condition_pre_encode=False, condition_cfg=True))
+    net = M.ControlT2MHalf_MCM(base, copy_blocks_num=2, control_cond_feats=35, cfg=cfg)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    opt = argparse.Namespace(no_repaint=False, same_overlap_noisy=False, addBlend=True, overlap_len=L, no_resample=False,
+                             timestep_respacing="ddim50", jump_length=3, jump_n_sample=5)
+    d = diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                                       model_var_type="fixed_small", respace="15,15,8,6,6"), opt=opt)
+    rng = np.random.default_rng(3)
+    mean, std = rng.standard_normal(322), 0.5 + rng.random(322)          # float64, as np.load of the datasets' statistics
+    round_l = T - pre
+    total = (W - 1) * round_l + T
+    music = synth.synth_tensor("music", (B, total, 35), synth.SEED_C_M2D)
+    _, xf_out, xf_proj = C.inputs(B, T)
+    x_T = [synth.synth_tensor(f"x_T_w{i}", (B, T, 322), synth.SEED_XT) for i in range(W)]
+    times = O.schedule_jump_cjm_ddim(50, 3, 5)
+    n_draws = 2 * sum(1 for a, b in zip(times[:-1], times[1:]) if b < a) + sum(1 for a, b in zip(times[:-1], times[1:]) if b >= a)
+    rnoise = [synth.synth_tensor(f"rp_w{i}", (n_draws, B, T, 322), synth.SEED_REPAINT_NOISE) for i in range(W)]
+    win_c = [music[:, i * round_l: i * round_l + T] for i in range(W)]
+    kwargs = [dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), c=win_c[i].cuda()) for i in range(W)]
+    torch.cuda.synchronize()
+    got = longform.sample_windows(net, d, kwargs, motion_length=T, pre_frames=pre, mean=mean, std=std,
+                                  noise=[x.cuda() for x in x_T], repaint_noise=[r.cuda() for r in rnoise])
+    done = torch.cuda.Event()
+    done.record()
+    still_running = not done.query()          # the host is back while the device still works through the windows
+    torch.cuda.synchronize()
+    assert got.shape == (B, total, 322) and got.dtype == torch.float64
+    tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
+    with torch.no_grad():
+        want = O.longform_windows(lambda i: (lambda xx, tt: O.control_forward(sd, xx, tt, xf_proj, xf_out, win_c[i])), W, B, T,
+                                  pre, L, tables, tmap, tables["betas"], mean, std, x_T,
+                                  [[r[j] for j in range(r.shape[0])] for r in rnoise], times=times)
+    assert C.rel_l2(got, want) < TOL_FAST
+    assert still_running, "sample_windows blocked on the device"
