@@ -59,6 +59,8 @@ typedef struct mcm_sampler {
   const float* posterior_log_variance_clipped;
   unsigned long long seed;                    /* stochastic samplers without explicit noise: Philox key; step i uses
                                                * stream i, so a run is reproducible from (seed, x_T) alone            */
+  int model_mean_type;                        /* 0 = the denoiser predicts eps (configs/mcm/*), 1 = it predicts x_0
+                                               * (ModelMeanType.START_X, configs/stmogen/*; gaussian_diffusion.py:555) */
 } mcm_sampler;
 
 /* replaces: MCMTransformer.__init__ / DiffusionTransformer.__init__
@@ -181,6 +183,15 @@ int mcm_handoff_align_faces(float* pred, const float* motion, long long rows, in
  *   fmt 0 = fp16 (1 pass) or 1 = bf16 hi/lo (3 passes). */
 int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const float* bias, float* C,
                     int fmt, void* stream);
+
+/* replaces: the classifier-free-guidance combine of STMoGenTransformer.forward_test (stmogen.py:755-759, with scale_func
+ * :655-659): out = out_text * text_coef + out_none * none_coef, the Python-float coefficients cast to float32 as torch does. */
+int mcm_cfg_combine(const float* out_text, const float* out_none, double text_coef, double none_coef, float* out,
+                    long long n, void* stream);
+
+/* replaces: the static human-topology branch of STMA.forward (mogen/models/attentions/st_attention.py:123-128):
+ * out[r, h, :] = sum_l softmax(body_weight, dim=1)[h, l] * v[r, l, :];  body_weight [H, H], v / out [rows, H, part_dim]. */
+int mcm_part_mix(const float* body_weight, const float* v, float* out, long long rows, int num_parts, int part_dim, void* stream);
 
 /* The on-device noise generator of the stochastic samplers, exposed for unit tests: out[0..n) ~ N(0,1), Philox4x32-10
  * keyed by `seed`, counter (element quad, sub), Box-Muller. */

@@ -31,7 +31,8 @@ class McmSampler(ctypes.Structure):
                 ("timestep_map", _IP), ("alphas_cumprod", _FP), ("alphas_cumprod_prev", _FP),
                 ("sqrt_recip_alphas_cumprod", _FP), ("sqrt_recipm1_alphas_cumprod", _FP),
                 ("posterior_mean_coef1", _FP), ("posterior_mean_coef2", _FP),
-                ("posterior_log_variance_clipped", _FP), ("seed", ctypes.c_ulonglong)]
+                ("posterior_log_variance_clipped", _FP), ("seed", ctypes.c_ulonglong),
+                ("model_mean_type", ctypes.c_int)]
 
 
 class McmRepaint(ctypes.Structure):
@@ -58,6 +59,8 @@ SIGNATURES = {
     "mcm_handoff_smplx": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP]),
     "mcm_handoff_denorm": (_I, [_VP, _VP, _VP, _LL, _I, _I, _VP, _VP, _VP]),
     "mcm_handoff_align_faces": (_I, [_VP, _VP, _LL, _I, _VP]),
+    "mcm_cfg_combine": (_I, [_VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _LL, _VP]),
+    "mcm_part_mix": (_I, [_VP, _VP, _VP, _LL, _I, _I, _VP]),
     "mcm_test_randn": (_I, [_VP, _LL, ctypes.c_ulonglong, ctypes.c_ulonglong, _VP]),
     "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
     "mcm_timing_enable": (None, [_I]),

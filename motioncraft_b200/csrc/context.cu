@@ -669,11 +669,12 @@ int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const NoiseSource& ns, 
     if (stochastic && i != 0) MCM_TRY(step_noise_ptr(c, ns, i, n, st, &noise));
     if (s->mode == 0) {
       DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
-                  s->alphas_cumprod_prev[i], s->eta, (s->eta != 0.f && i != 0) ? 1 : 0};
+                  s->alphas_cumprod_prev[i], s->eta, (s->eta != 0.f && i != 0) ? 1 : 0, s->model_mean_type == 1 ? 1 : 0};
       MCM_TRY(ddim_update_launch(x_io, c->eps32, noise, x_io, rows, c->IN, k, c->xop, c->fmt_prec(), st));
     } else {
       DdpmCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->posterior_mean_coef1[i],
-                  s->posterior_mean_coef2[i], s->posterior_log_variance_clipped[i], i != 0 ? 1 : 0};
+                  s->posterior_mean_coef2[i], s->posterior_log_variance_clipped[i], i != 0 ? 1 : 0,
+                  s->model_mean_type == 1 ? 1 : 0};
       MCM_TRY(ddpm_update_launch(x_io, c->eps32, noise, x_io, rows, c->IN, k, c->xop, c->fmt_prec(), st));
     }
   }
@@ -683,6 +684,7 @@ int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const NoiseSource& ns, 
 int check_sampler(const mcm_sampler* s) {
   MCM_CHECK(s != nullptr && s->n_steps > 0 && s->timestep_map != nullptr, "bad sampler description");
   MCM_CHECK(s->mode == 0 || s->mode == 1, "sampler mode must be 0 (DDIM) or 1 (DDPM)");
+  MCM_CHECK(s->model_mean_type == 0 || s->model_mean_type == 1, "model_mean_type must be 0 (epsilon) or 1 (start_x)");
   MCM_CHECK(s->sqrt_recip_alphas_cumprod && s->sqrt_recipm1_alphas_cumprod, "missing sampler tables");
   if (s->mode == 0) {
     MCM_CHECK(s->alphas_cumprod && s->alphas_cumprod_prev, "DDIM needs alphas_cumprod(_prev)");
@@ -1086,7 +1088,7 @@ int mcm_sample_repaint(mcm_ctx* c, const mcm_sampler* s, const mcm_repaint* r, i
     MCM_CHECK(ns.generate || draw + 2 <= r->n_draws, "mcm_sample_repaint: noise_seq too short");
     MCM_TRY(run_denoiser_step(c, B, s->timestep_map[i], st));
     DdimCoefs k{s->sqrt_recip_alphas_cumprod[i], s->sqrt_recipm1_alphas_cumprod[i], s->alphas_cumprod[i],
-                s->alphas_cumprod_prev[i], 0.f, 0};
+                s->alphas_cumprod_prev[i], 0.f, 0, s->model_mean_type == 1 ? 1 : 0};
     MCM_TRY(ddim_update_launch(x0_out, c->eps32, nullptr, x0_out, rows, c->IN, k, none, c->fmt_prec(), st));
     const float abp = s->alphas_cumprod_prev[i];
     const float noise_w = sqrtf(1.f - abp), gt_w = sqrtf(abp);
@@ -1135,6 +1137,17 @@ int mcm_sample_host(mcm_ctx* c, const mcm_sampler* s, int B, const float* x_T_ho
   MCM_CUDA(cudaMemcpyAsync(x0_out_host, c->x32, n * 4, cudaMemcpyDeviceToHost, st));
   MCM_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+int mcm_cfg_combine(const float* out_text, const float* out_none, double text_coef, double none_coef, float* out,
+                    long long n, void* stream) {
+  MCM_CHECK(out_text && out_none && out && n > 0, "bad argument");
+  return axpby_launch(out_text, out_none, (float)text_coef, (float)none_coef, out, (size_t)n, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mcm_part_mix(const float* body_weight, const float* v, float* out, long long rows, int num_parts, int part_dim, void* stream) {
+  MCM_CHECK(body_weight && v && out && rows > 0, "bad argument");
+  return part_mix_launch(body_weight, v, out, (size_t)rows, num_parts, part_dim, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mcm_test_randn(float* out_dev, long long n, unsigned long long seed, unsigned long long sub, void* stream) {

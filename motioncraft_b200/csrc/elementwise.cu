@@ -319,7 +319,7 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_mo
     if (c < cols) {
       const size_t j = r * cols + c;
       const float c1x = __fmul_rn(k.c1, x[j]);
-      const float x0 = __fsub_rn(c1x, __fmul_rn(k.c2, eps_model[j]));
+      const float x0 = k.start_x ? eps_model[j] : __fsub_rn(c1x, __fmul_rn(k.c2, eps_model[j]));
       const float eps = __fdiv_rn(__fsub_rn(c1x, x0), k.c2);
       xn = __fadd_rn(__fmul_rn(x0, s_abp), __fmul_rn(s_dir, eps));
       if (k.add_noise) xn = __fadd_rn(xn, __fmul_rn(sigma, noise[j]));
@@ -344,7 +344,7 @@ ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ eps_mo
     float xn = 0.f;
     if (c < cols) {
       const size_t j = r * cols + c;
-      const float x0 = __fsub_rn(__fmul_rn(k.c1, x[j]), __fmul_rn(k.c2, eps_model[j]));
+      const float x0 = k.start_x ? eps_model[j] : __fsub_rn(__fmul_rn(k.c1, x[j]), __fmul_rn(k.c2, eps_model[j]));
       xn = __fadd_rn(__fmul_rn(k.pm1, x0), __fmul_rn(k.pm2, x[j]));
       if (k.add_noise) xn = __fadd_rn(xn, __fmul_rn(sd, noise[j]));
       x_out[j] = xn;
@@ -449,6 +449,50 @@ randn_fill_kernel(float* __restrict__ out, size_t n, unsigned long long seed, un
   }
 }
 
+__global__ void __launch_bounds__(256)
+axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb, float* __restrict__ out, size_t n) {
+  pdl_trigger();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(a[i], wa), __fmul_rn(b[i], wb));
+}
+
+// Static human-topology mixing of STMA (st_attention.py:123-128): out[r, h, :] = sum_l softmax(body_weight, dim=1)[h, l] *
+// v[r, l, :] for the H (= 12) body parts of every token row r.  HBM-bound: one read and one write of the (rows, H, L) tensor;
+// the H x H graph is soft-maxed once per block in shared memory.
+__global__ void __launch_bounds__(256)
+part_mix_kernel(const float* __restrict__ body_weight, const float* __restrict__ v, float* __restrict__ out, size_t rows,
+                int H, int L) {
+  __shared__ float w[32 * 32];
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x < H) {
+    float m = -INFINITY;
+    for (int l = 0; l < H; ++l) m = fmaxf(m, body_weight[threadIdx.x * H + l]);
+    float sum = 0.f;
+    for (int l = 0; l < H; ++l) {
+      const float e = expf(body_weight[threadIdx.x * H + l] - m);
+      w[threadIdx.x * H + l] = e;
+      sum += e;
+    }
+    for (int l = 0; l < H; ++l) w[threadIdx.x * H + l] /= sum;
+  }
+  __syncthreads();
+  const size_t total = rows * (size_t)L;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / L;
+    const int d = (int)(i - r * L);
+    const float* src = v + r * (size_t)H * L + d;
+    float x[32];
+    for (int l = 0; l < H; ++l) x[l] = src[(size_t)l * L];
+    for (int h = 0; h < H; ++h) {
+      float acc = 0.f;
+      for (int l = 0; l < H; ++l) acc = fmaf(w[h * H + l], x[l], acc);
+      out[r * (size_t)H * L + (size_t)h * L + d] = acc;
+    }
+  }
+}
+
 __global__ void fill_timesteps_kernel(long long* __restrict__ t_buf, long long t, int B) {
   pdl_trigger();
   pdl_wait();
@@ -465,6 +509,24 @@ inline int grid_for(size_t total, int block) {
 int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream) {
   LaunchTimer lt(LK_ROW, stream);
   MCM_CUDA(launch_pdl(fill_timesteps_kernel, dim3((B + 255) / 256), dim3(256), (size_t)(0), stream, t_buf, t, B));
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int axpby_launch(const float* a, const float* b, float wa, float wb, float* out, size_t n, cudaStream_t stream) {
+  LaunchTimer lt(LK_ROW, stream);
+  MCM_CUDA(launch_pdl(axpby_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), stream, a, b, wa, wb, out, n));
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int part_mix_launch(const float* body_weight, const float* v, float* out, size_t rows, int H, int L, cudaStream_t stream) {
+  MCM_CHECK(H >= 1 && H <= 32 && L >= 1, "part_mix: at most 32 parts");
+  LaunchTimer lt(LK_ROW, stream);
+  MCM_CUDA(launch_pdl(part_mix_kernel, dim3(grid_for(rows * (size_t)L, 256)), dim3(256), (size_t)(0), stream, body_weight, v, out,
+                      rows, H, L));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

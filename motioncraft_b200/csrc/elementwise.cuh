@@ -32,8 +32,9 @@ int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu
 int timestep_embedding_launch(const long long* t_dev, int t_uniform, int B, int dim, OpPtr out, int out_fmt,
                               cudaStream_t stream);
 
-struct DdimCoefs { float c1, c2, alpha_bar, alpha_bar_prev, eta; int add_noise; };
-struct DdpmCoefs { float c1, c2, pm1, pm2, log_var; int add_noise; };
+// start_x: the denoiser predicts x_0 itself (ModelMeanType.START_X, gaussian_diffusion.py:555-556) instead of eps
+struct DdimCoefs { float c1, c2, alpha_bar, alpha_bar_prev, eta; int add_noise; int start_x; };
+struct DdpmCoefs { float c1, c2, pm1, pm2, log_var; int add_noise; int start_x; };
 // x <- DDIM / DDPM update from eps (fp32, n elements); writes x_out (may alias x) and, if xop.hi, the
 // operand copy [rows, cols -> xop.ld] the next step's joint_embed GEMM reads.
 int ddim_update_launch(const float* x, const float* eps, const float* noise, float* x_out, size_t rows, int cols,
@@ -54,6 +55,13 @@ int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t str
 
 // out[0..n) ~ N(0, 1): Philox4x32-10 keyed by (seed, sub) + Box-Muller; `sub` numbers the draw (sampler step / RePaint draw)
 int randn_fill_launch(float* out, size_t n, unsigned long long seed, unsigned long long sub, cudaStream_t stream);
+
+// out = a * wa + b * wb in fp32 without FMA contraction: the classifier-free-guidance combine of STMoGenTransformer.forward_test
+// (stmogen.py:755-759), out_text * text_coef + out_none * none_coef
+int axpby_launch(const float* a, const float* b, float wa, float wb, float* out, size_t n, cudaStream_t stream);
+
+// out[r, h, :] = sum_l softmax(body_weight (H x H), dim=1)[h, l] * v[r, l, :]   (STMA static branch, st_attention.py:123-128)
+int part_mix_launch(const float* body_weight, const float* v, float* out, size_t rows, int H, int L, cudaStream_t stream);
 
 int elementwise_init();
 unsigned long long elementwise_launch_count();

@@ -86,9 +86,10 @@ class GaussianDiffusion:
     """Schedule tables + on-device sampling loops.  Signature of gaussian_diffusion.py:319-344."""
 
     def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False, opt=None):
-        if model_mean_type != ModelMeanType.EPSILON or model_var_type != ModelVarType.FIXED_SMALL:
-            raise McmError("configs/mcm/* use epsilon prediction with fixed_small variance; other parameterisations "
-                           "(start_x / fixed_large are the stmogen Path B) are not implemented")
+        if model_mean_type not in (ModelMeanType.EPSILON, ModelMeanType.START_X) or \
+                model_var_type not in (ModelVarType.FIXED_SMALL, ModelVarType.FIXED_LARGE):
+            raise McmError("implemented parameterisations: epsilon / fixed_small (configs/mcm/*) and start_x / fixed_large "
+                           "(configs/stmogen/*); previous_x and learned variances are not used by the reference configs")
         if rescale_timesteps:
             raise McmError("rescale_timesteps is not used by the reference configs")
         self.opt = opt
@@ -115,7 +116,16 @@ class GaussianDiffusion:
 
     # ------------------------------------------------------------------ helpers
     def _tables(self):
-        return {k: getattr(self, k) for k in SamplerTables.FIELDS}
+        t = {k: getattr(self, k) for k in SamplerTables.FIELDS}
+        if self.model_var_type == ModelVarType.FIXED_LARGE:
+            # p_mean_variance :527-531: "for fixedlarge, we set the initial (log-)variance like so to get a better decoder
+            # log likelihood" -- only the DDPM update reads it (DDIM with eta = 0 uses no variance)
+            t["posterior_log_variance_clipped"] = np.log(np.append(self.posterior_variance[1], self.betas[1:]))
+        return t
+
+    @property
+    def _mean_name(self):
+        return "start_x" if self.model_mean_type == ModelMeanType.START_X else "epsilon"
 
     @staticmethod
     def _check_unsupported(model_kwargs, cond_fn, denoised_fn, pre_seq, transl_req, clip_denoised):
@@ -147,7 +157,7 @@ class GaussianDiffusion:
         stochastic = (mode == "ddpm" and self.num_timesteps > 1) or (mode == "ddim" and eta != 0.0)
         seed = self._draw_seed(dev) if (stochastic and step_noise is None) else 0
         eng = model.bind_for_sampling(B, model_kwargs, dev)
-        tables = SamplerTables(self._tables(), self.timestep_map, mode, eta, seed=seed)
+        tables = SamplerTables(self._tables(), self.timestep_map, mode, eta, seed=seed, model_mean=self._mean_name)
         if step_noise is not None and step_noise.device.type == "cpu" and step_noise.numel() * 4 > (1 << 30):
             # large scripted noise stays on the host and is streamed one step at a time
             x0 = eng.sample_host(tables, noise.detach().float().cpu().contiguous(), None,
@@ -209,7 +219,7 @@ class GaussianDiffusion:
         elif repaint_noise.shape[0] < n_draws:
             raise McmError(f"repaint_noise holds {repaint_noise.shape[0]} draws, the schedule needs {n_draws}")
         eng = model.bind_for_sampling(B, dict(model_kwargs), dev)
-        tables = SamplerTables(self._tables(), self.timestep_map, "ddim", 0.0, seed=seed)
+        tables = SamplerTables(self._tables(), self.timestep_map, "ddim", 0.0, seed=seed, model_mean=self._mean_name)
         return eng.sample_repaint(tables, noise.to(dev), torch.as_tensor(y["gt"]), torch.as_tensor(y["outpainting_mask"]),
                                   repaint_noise, times=times, betas=self.betas, overlap_len=int(getattr(opt, "overlap_len", 0)),
                                   add_blend=bool(getattr(opt, "addBlend", True)))
@@ -246,4 +256,4 @@ def build_diffusion(cfg, opt=None):
     if cfg.get("respace", None) is not None:
         return SpacedDiffusion(use_timesteps=space_timesteps(cfg["diffusion_steps"], cfg["respace"]), betas=betas,
                                model_mean_type=mean, model_var_type=var, loss_type=LossType.MSE, opt=opt)
-    return GaussianDiffusion(betas=betas, model_mean_type=mean, model_var_type=var, loss_type=LossType.MSE)
+    return GaussianDiffusion(betas=betas, model_mean_type=mean, model_var_type=var, loss_type=LossType.MSE, opt=opt)

@@ -30,7 +30,7 @@ class SamplerTables:
     FIELDS = ("alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
               "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped")
 
-    def __init__(self, tables, timestep_map, mode, eta=0.0, seed=0):
+    def __init__(self, tables, timestep_map, mode, eta=0.0, seed=0, model_mean="epsilon"):
         self.n_steps = len(timestep_map)
         self._tmap = np.ascontiguousarray(np.asarray(timestep_map, dtype=np.int32))
         # the float64 -> float32 cast _extract_into_tensor applies (gaussian_diffusion.py:1340)
@@ -41,6 +41,7 @@ class SamplerTables:
         s.n_steps = self.n_steps
         s.eta = float(eta)
         s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF      # key of the on-device noise of stochastic samplers (no explicit noise given)
+        s.model_mean_type = {"epsilon": 0, "start_x": 1}[model_mean]
         s.timestep_map = self._tmap.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
         for k in self.FIELDS:
             setattr(s, k, self._arrs[k].ctypes.data_as(ctypes.POINTER(ctypes.c_float)))

@@ -1,0 +1,178 @@
+"""First pieces of Path B -- the STMoGen family of configs/stmogen/* (SURVEY.md section 8 rows b1, b3, b8, b9 and the start_x /
+fixed_large sampler parameterisation), built on the same CUDA library as the configs/mcm path.
+
+What is here runs on the device and is pinned against the unmodified reference (tests/golden/pathb.npz):
+
+  PoseEncoder / PoseDecoder  stmogen.py:141-578 (motionx, 12 parts): the reference gathers eleven column slices of the 322-dim
+      vector, runs eleven small Linears plus a whole-body Linear and concatenates / scatters.  Here the twelve weight matrices
+      are laid out once as ONE block-structured matrix -- (12 L x 322) for the encoder, (322 x 12 L) with the
+      `(scatter + body) / 2` folded in for the decoder; the slices partition the 322 columns, so the structure is exact --
+      and the whole layer is one pass of the tcgen05 GEMM kernel in its 3-pass bf16-split mode (the precision class of
+      joint_embed / out).  Gather and scatter cost nothing: they are zero blocks of the operand.
+  static_body_mix            st_attention.py:123-128 -> `mcm_part_mix`
+  cfg_combine / scale_func   stmogen.py:655-659, 755-759 -> `mcm_cfg_combine`
+  start_x / fixed_large      diffusion.py (`SamplerTables(model_mean="start_x")`)
+
+NOT here: the mixture-of-experts of STMA (`tutel.moe.moe_layer`, st_attention.py:17-56) -- an un-vendored, unpinned
+third-party dependency whose routing cannot be pinned in this image -- and therefore STMoGenTransformer itself; the
+dynamic / temporal branches and SFFN follow once the MoE question is settled.  `STMoGenTransformer` raises accordingly.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import McmError
+from .engine import test_linear
+
+PART_ORDER = ("head", "stem", "larm", "rarm", "lleg", "rleg", "root", "trans", "face", "lhand", "rhand")
+
+
+def get_smplx_slice(name):
+    """stmogen.py:53-68."""
+    j = lambda k: [k * 3, k * 3 + 1, k * 3 + 2]  # noqa: E731
+    return {
+        "root": [0, 1, 2] + list(range(312, 322)), "trans": [309, 310, 311],
+        "head": j(12) + j(15) + [156, 157, 158], "stem": j(3) + j(6) + j(9),
+        "larm": j(14) + j(17) + j(19) + j(21), "rarm": j(13) + j(16) + j(18) + j(20),
+        "lleg": j(2) + j(5) + j(8) + j(11), "rleg": j(1) + j(4) + j(7) + j(10),
+        "face": list(range(159, 309)), "lhand": list(range(66, 111)), "rhand": list(range(111, 156)),
+    }[str(name)]
+
+
+def _body_slice():
+    out = []
+    for n in PART_ORDER:
+        out.extend(get_smplx_slice(n))
+    return out
+
+
+class _PackedLinear(nn.Module):
+    """Parameter container whose forward is one tcgen05 GEMM over a block-structured weight assembled from its Linears."""
+
+    def __init__(self):
+        super().__init__()
+        self._packed = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: setattr(self, "_packed", None))
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _gemm(self, x, n_out):
+        if x.device.type != "cuda":
+            raise McmError("motioncraft_b200 modules compute on an sm_100a CUDA device only (no CPU fallback)")
+        if self._packed is None or self._packed[0].device != x.device:
+            with torch.no_grad():
+                self._packed = self._pack(x.device)
+        W, b = self._packed
+        lead = x.shape[:-1]
+        y = test_linear(x.reshape(-1, x.shape[-1]), W, b, fmt=1)          # fmt 1 = bf16 hi/lo split, 3 passes
+        return y.view(*lead, n_out)
+
+
+class PoseEncoder(_PackedLinear):
+    """stmogen.py:141-378, `dataset_name='motionx'`, joints=False, body_graph=False (what configs/stmogen/* build)."""
+
+    def __init__(self, dataset_name="motionx", latent_dim=128, input_dim=322, patch_size=1, joints=False, body_graph=False,
+                 gnn_cfg=None):
+        super().__init__()
+        if dataset_name != "motionx" or joints or body_graph or patch_size != 1 or input_dim != 322:
+            raise McmError("PoseEncoder: the 12-part motionx layout (patch_size 1, no joint / graph variants) is implemented")
+        self.dataset_name, self.latent_dim, self.parts_num = dataset_name, latent_dim, 12
+        for n in PART_ORDER:
+            setattr(self, n + "_embed", nn.Linear(len(get_smplx_slice(n)), latent_dim))
+        self.body_embed = nn.Linear(input_dim, latent_dim)
+
+    def _pack(self, dev):
+        L = self.latent_dim
+        W = torch.zeros(12 * L, 322, device=dev)
+        b = torch.empty(12 * L, device=dev)
+        for i, n in enumerate(PART_ORDER):
+            lin = getattr(self, n + "_embed")
+            W[i * L:(i + 1) * L, get_smplx_slice(n)] = lin.weight.to(dev)
+            b[i * L:(i + 1) * L] = lin.bias.to(dev)
+        W[11 * L:, _body_slice()] = self.body_embed.weight.to(dev)
+        b[11 * L:] = self.body_embed.bias.to(dev)
+        return W, b
+
+    def forward(self, motion):
+        return self._gemm(motion, 12 * self.latent_dim)
+
+
+class PoseDecoder(_PackedLinear):
+    """stmogen.py:380-578, motionx, patch_size 1: output = (scatter(part outputs) + body_out(h_body)) / 2."""
+
+    def __init__(self, dataset_name="motionx", latent_dim=128, output_dim=322, patch_size=1, joints=False):
+        super().__init__()
+        if dataset_name != "motionx" or joints or patch_size != 1 or output_dim != 322:
+            raise McmError("PoseDecoder: the 12-part motionx layout (patch_size 1, no joint variant) is implemented")
+        self.dataset_name, self.latent_dim, self.output_dim = dataset_name, latent_dim, output_dim
+        for n in PART_ORDER:
+            setattr(self, n + "_out", nn.Linear(latent_dim, len(get_smplx_slice(n))))
+        self.body_out = nn.Linear(latent_dim, output_dim)
+
+    def _pack(self, dev):
+        L = self.latent_dim
+        W = torch.zeros(322, 12 * L, device=dev)
+        b = torch.zeros(322, device=dev)
+        for i, n in enumerate(PART_ORDER):
+            lin = getattr(self, n + "_out")
+            cols = get_smplx_slice(n)
+            W[cols, i * L:(i + 1) * L] = lin.weight.to(dev)
+            b[cols] = lin.bias.to(dev)
+        # body_out's output k is added to column k un-permuted (stmogen.py:516, 543); only the ENCODER's whole-body Linear
+        # reads its input through body_slice
+        W[:, 11 * L:] = self.body_out.weight.to(dev)
+        b = b + self.body_out.bias.to(dev)
+        return 0.5 * W, 0.5 * b            # (scatter + body) / 2: a power of two, exact in every operand format
+
+    def forward(self, h):
+        return self._gemm(h, self.output_dim)
+
+
+def static_body_mix(body_weight, body_value):
+    """STMA static branch (st_attention.py:123-128): body_value (B, T, H, L) fp32 CUDA -> same shape."""
+    if body_value.device.type != "cuda":
+        raise McmError("motioncraft_b200 runs on an sm_100a CUDA device only")
+    v = body_value.detach().float().contiguous()
+    w = body_weight.detach().to(v.device, torch.float32).contiguous()
+    H, L = v.shape[-2], v.shape[-1]
+    out = torch.empty_like(v)
+    lib = _lib.load()
+    with torch.cuda.device(v.device):
+        _lib.check(lib.mcm_part_mix(ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                    v.numel() // (H * L), H, L, ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)))
+    return out
+
+
+def scale_func(timestep, scale=6.5):
+    """STMoGenTransformer.scale_func (stmogen.py:655-659)."""
+    w = (1 - (1000 - timestep) / 1000) * scale + 1
+    return {"text_coef": w, "none_coef": 1 - w}
+
+
+def cfg_combine(out_text, out_none, timestep, scale=6.5):
+    """stmogen.py:755-759 on the device; `timestep` is the Python int the caller already holds (the reference reads
+    `int(timesteps[0])` from the device every step -- a host synchronisation this signature avoids)."""
+    if out_text.device.type != "cuda":
+        raise McmError("motioncraft_b200 runs on an sm_100a CUDA device only")
+    a, b = out_text.detach().float().contiguous(), out_none.detach().float().contiguous()
+    coef = scale_func(int(timestep), scale)
+    out = torch.empty_like(a)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.mcm_cfg_combine(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), float(coef["text_coef"]),
+                                       float(coef["none_coef"]), ctypes.c_void_p(out.data_ptr()), a.numel(),
+                                       ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)))
+    return out
+
+
+class STMoGenTransformer(nn.Module):
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise McmError("STMoGenTransformer (configs/stmogen/*) is not complete in motioncraft_b200: its STMA blocks route "
+                       "through tutel's mixture-of-experts layer, an un-vendored dependency whose semantics cannot be pinned "
+                       "here (SURVEY.md section 8 row b2).  Available pieces: PoseEncoder, PoseDecoder, static_body_mix, "
+                       "cfg_combine, the start_x / fixed_large samplers (motioncraft_b200/pathb.py)")

@@ -8,6 +8,7 @@ and weights are pure functions of seeds (motioncraft_b200/synth.py), so only OUT
 import contextlib
 import os
 import sys
+import types
 
 import numpy as np
 import torch
@@ -201,6 +202,58 @@ def text_stack(B=3):
     print("text_stack: xf_proj", tuple(xf_proj.shape), "xf_out", tuple(xf_out.shape), "eos", eos.tolist())
 
 
+def pathb(B=2, T=9, L=128):
+    """Pieces of Path B the reference can pin here (SURVEY.md 8 rows b1, b3, b8, b9 + the start_x sampler): the reference's
+    own PoseEncoder / PoseDecoder (motionx), the static human-topology mix of STMA, the CFG combine, and
+    SpacedDiffusion(START_X, FIXED_LARGE) DDIM-50 / DDPM-10 around a fixed x_0-predictor."""
+    ref_shim.install()
+    import mogen.models.transformers.stmogen as st
+    from mogen.models.utils import gaussian_diffusion as gd
+    import torch.nn.functional as Fn
+    enc = st.PoseEncoder(dataset_name="motionx", latent_dim=L, input_dim=322).eval()
+    dec = st.PoseDecoder(dataset_name="motionx", latent_dim=L, output_dim=322).eval()
+    names = {"joint_embed." + k: v.shape for k, v in enc.state_dict().items()}
+    names.update({"out." + k: v.shape for k, v in dec.state_dict().items()})
+    sd = synth.synth_state_dict(names)
+    enc.load_state_dict({k[len("joint_embed."):]: v for k, v in sd.items() if k.startswith("joint_embed.")})
+    dec.load_state_dict({k[len("out."):]: v for k, v in sd.items() if k.startswith("out.")})
+    x = synth.synth_tensor("pb_motion", (B, T, 322), synth.SEED_XT)
+    out = {"keys": np.array(sorted(names.keys()))}
+    with torch.no_grad():
+        h = enc(x)
+        out["pose_encode"] = h.numpy()
+        out["pose_decode"] = dec(h).numpy()
+        bw = synth.synth_tensor("body_weight", (12, 12), synth.SEED_WEIGHTS)
+        bv = h.reshape(B, T, 12, L)
+        out["static_mix"] = torch.einsum("hl,bnld->bnhd", Fn.softmax(bw, dim=1), bv).numpy()       # st_attention.py:123-128
+        a = synth.synth_tensor("cfg_text", (B, T, 322), synth.SEED_XT)
+        b = synth.synth_tensor("cfg_none", (B, T, 322), synth.SEED_XF_OUT)
+        holder = types.SimpleNamespace(scale_func_cfg=dict(scale=6.5))
+        for t in (999, 500, 14, 0):
+            coef = st.STMoGenTransformer.scale_func(holder, int(t))
+            out[f"cfg_t{t}"] = (a * coef["text_coef"] + b * coef["none_coef"]).numpy()              # stmogen.py:755-759
+        # start_x / fixed_large sampler around an x_0-predictor (the reference MCMTransformer used as a fixed function)
+        Tm = 60
+        net = ref_shim.build_reference_mcm(T=Tm, num_layers=2)
+        msd = synth.synth_state_dict({k: v.shape for k, v in net.state_dict().items()})
+        net.load_state_dict(msd)
+        xT, xf_out, xf_proj = inputs(1, Tm)
+        kw = dict(motion_mask=torch.ones(1, Tm), motion_length=torch.full((1,), Tm), xf_proj=xf_proj, xf_out=xf_out, y={})
+        betas = gd.get_named_beta_schedule("linear", 1000)
+        base = dict(betas=betas, model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_LARGE,
+                    loss_type=gd.LossType.MSE)
+        d50 = gd.SpacedDiffusion(use_timesteps=gd.space_timesteps(1000, "15,15,8,6,6"), opt=ref_shim.reference_opt(), **base)
+        out["startx_ddim50_x0"] = d50.ddim_sample_loop(net, (1, Tm, 322), noise=xT, clip_denoised=False, model_kwargs=kw,
+                                                       eta=0).numpy()
+        d10 = gd.SpacedDiffusion(use_timesteps=gd.space_timesteps(1000, "10"), opt=ref_shim.reference_opt(), **base)
+        noise = synth.synth_tensor("step_noise", (10, 1, Tm, 322), synth.SEED_STEP_NOISE)
+        with scripted_randn_like([noise[i] for i in reversed(range(10))]):
+            out["startx_ddpm10_x0"] = d10.p_sample_loop(net, (1, Tm, 322), noise=xT, clip_denoised=False,
+                                                        model_kwargs=kw).numpy()
+    np.savez_compressed(os.path.join(GOLD, "pathb.npz"), **out)
+    print("pathb", {k: v.shape for k, v in out.items() if v.dtype.kind == "f"})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -210,3 +263,4 @@ if __name__ == "__main__":
     repaint()
     wav_encoder()
     text_stack()
+    pathb()

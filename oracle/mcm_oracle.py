@@ -347,7 +347,7 @@ def _coef(arr, i, like):
 # ----------------------------------------------------------------------------------------------
 # sampler loops (epsilon prediction, fixed_small variance, clip_denoised=False)
 # ----------------------------------------------------------------------------------------------
-def ddim_sample_loop(model_fn, x_T, tables, tmap, eta=0.0, step_noise=None, trace=None):
+def ddim_sample_loop(model_fn, x_T, tables, tmap, eta=0.0, step_noise=None, trace=None, model_mean_type="epsilon"):
     """ddim_sample_loop_progressive + ddim_sample, gaussian_diffusion.py:799-852, 999-1049.
 
     `model_fn(x, t_original)` returns eps.  With eta = 0 (what MotionDiffusion passes,
@@ -362,7 +362,10 @@ def ddim_sample_loop(model_fn, x_T, tables, tmap, eta=0.0, step_noise=None, trac
         eps_model = model_fn(x, t_model)
         c1 = _coef(tables["sqrt_recip_alphas_cumprod"], i, x)
         c2 = _coef(tables["sqrt_recipm1_alphas_cumprod"], i, x)
-        pred_xstart = c1 * x - c2 * eps_model                         # _predict_xstart_from_eps :572-577
+        if model_mean_type == "start_x":                              # ModelMeanType.START_X :555-556 (configs/stmogen/*)
+            pred_xstart = eps_model
+        else:
+            pred_xstart = c1 * x - c2 * eps_model                     # _predict_xstart_from_eps :572-577
         eps = (c1 * x - pred_xstart) / c2                             # _predict_eps_from_xstart :587-591
         alpha_bar = _coef(tables["alphas_cumprod"], i, x)
         alpha_bar_prev = _coef(tables["alphas_cumprod_prev"], i, x)
@@ -377,7 +380,7 @@ def ddim_sample_loop(model_fn, x_T, tables, tmap, eta=0.0, step_noise=None, trac
     return x
 
 
-def p_sample_loop(model_fn, x_T, tables, tmap, step_noise, trace=None):
+def p_sample_loop(model_fn, x_T, tables, tmap, step_noise, trace=None, model_mean_type="epsilon", fixed_large=False):
     """p_sample_loop_progressive + p_sample + p_mean_variance (EPSILON / FIXED_SMALL),
     gaussian_diffusion.py:458-570, 634-696, 747-797.  `step_noise[i]` replaces the randn_like at
     :685 for retained step i (the reference draws from torch's global generator)."""
@@ -389,10 +392,13 @@ def p_sample_loop(model_fn, x_T, tables, tmap, step_noise, trace=None):
         eps_model = model_fn(x, t_model)
         c1 = _coef(tables["sqrt_recip_alphas_cumprod"], i, x)
         c2 = _coef(tables["sqrt_recipm1_alphas_cumprod"], i, x)
-        pred_xstart = c1 * x - c2 * eps_model
+        pred_xstart = eps_model if model_mean_type == "start_x" else c1 * x - c2 * eps_model
         mean = (_coef(tables["posterior_mean_coef1"], i, x) * pred_xstart +
                 _coef(tables["posterior_mean_coef2"], i, x) * x)      # q_posterior_mean_variance :445-449
-        log_var = _coef(tables["posterior_log_variance_clipped"], i, x)
+        if fixed_large:                                               # ModelVarType.FIXED_LARGE :527-531
+            log_var = _coef(np.log(np.append(tables["posterior_variance"][1], tables["betas"][1:])), i, x)
+        else:
+            log_var = _coef(tables["posterior_log_variance_clipped"], i, x)
         nonzero = 0.0 if i == 0 else 1.0
         x = mean + nonzero * torch.exp(0.5 * log_var) * step_noise[i]
         if trace is not None:

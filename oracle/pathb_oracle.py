@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the pieces of Path B (configs/stmogen/*, SURVEY.md section 8 rows b1, b3, b7,
+b8, b9) that the reference can still pin in this image (the `tutel` MoE of row b2 is an un-vendored, unpinned third-party
+dependency: **parity unpinned**, not restated).  Each function cites the reference lines it follows; validated bit for bit
+against the unmodified reference modules in oracle/make_golden.py::pathb (goldens in tests/golden/pathb.npz)."""
+import torch
+import torch.nn.functional as F
+
+PART_ORDER = ("head", "stem", "larm", "rarm", "lleg", "rleg", "root", "trans", "face", "lhand", "rhand")   # stmogen.py:344-349
+
+
+def smplx_slice(name):
+    """get_smplx_slice, mogen/models/transformers/stmogen.py:53-68: columns of the 322-dim SMPL-X vector per body part."""
+    j = lambda k: [k * 3, k * 3 + 1, k * 3 + 2]  # noqa: E731
+    table = {
+        "root": [0, 1, 2] + list(range(312, 322)),
+        "trans": [309, 310, 311],
+        "head": j(12) + j(15) + [156, 157, 158],
+        "stem": j(3) + j(6) + j(9),
+        "larm": j(14) + j(17) + j(19) + j(21),
+        "rarm": j(13) + j(16) + j(18) + j(20),
+        "lleg": j(2) + j(5) + j(8) + j(11),
+        "rleg": j(1) + j(4) + j(7) + j(10),
+        "face": list(range(159, 309)),
+        "lhand": list(range(66, 111)),
+        "rhand": list(range(111, 156)),
+    }
+    return table[name]
+
+
+def body_slice():
+    """PoseEncoder.body_slice for motionx (stmogen.py:306-308): the concatenation of the eleven part slices."""
+    out = []
+    for n in PART_ORDER:
+        out.extend(smplx_slice(n))
+    return out
+
+
+def pose_encode(sd, motion, prefix="joint_embed."):
+    """PoseEncoder.forward, motionx branch (stmogen.py:336-353, 376-378; gnn = identity): eleven gather + Linear(len(slice) ->
+    L) and the whole-body Linear(322 -> L), concatenated to (B, T, 12 L)."""
+    feats = [F.linear(motion[:, :, smplx_slice(n)].contiguous(), sd[f"{prefix}{n}_embed.weight"], sd[f"{prefix}{n}_embed.bias"])
+             for n in PART_ORDER]
+    feats.append(F.linear(motion[:, :, body_slice()].contiguous(), sd[prefix + "body_embed.weight"], sd[prefix + "body_embed.bias"]))
+    return torch.cat(feats, dim=-1)
+
+
+def pose_decode(sd, h, prefix="out.", out_dim=322):
+    """PoseDecoder.forward, motionx branch with patch_size = 1 (stmogen.py:505-544): eleven Linear(L -> len(slice)) scattered
+    into the 322 columns, the whole-body Linear(L -> 322) in body_slice order, output = (scatter + body) / 2."""
+    B, T, _ = h.shape
+    L = sd[prefix + "head_out.weight"].shape[1]
+    output = torch.zeros(B, T, out_dim, dtype=h.dtype)
+    for i, n in enumerate(PART_ORDER):
+        output[:, :, smplx_slice(n)] = F.linear(h[:, :, i * L:(i + 1) * L].contiguous(), sd[f"{prefix}{n}_out.weight"],
+                                                sd[f"{prefix}{n}_out.bias"])
+    body = F.linear(h[:, :, 11 * L:].contiguous(), sd[prefix + "body_out.weight"], sd[prefix + "body_out.bias"])
+    return (output + body) / 2.0
+
+
+def static_body_mix(body_weight, body_value):
+    """STMA.forward static branch (st_attention.py:123-128): softmax of the learned (H, H) human-topology graph over its
+    second index, then every part is a mixture of all parts' value vectors.  body_value (B, T, H, L)."""
+    w = F.softmax(body_weight, dim=1)
+    return torch.einsum("hl,bnld->bnhd", w, body_value)
+
+
+def scale_func(timestep, scale):
+    """STMoGenTransformer.scale_func (stmogen.py:655-659), in Python floats like the reference."""
+    w = (1 - (1000 - timestep) / 1000) * scale + 1
+    return w, 1 - w
+
+
+def cfg_combine(out_text, out_none, timestep, scale):
+    """stmogen.py:755-759: out_text * text_coef + out_none * none_coef."""
+    wt, wn = scale_func(int(timestep), scale)
+    return out_text * wt + out_none * wn

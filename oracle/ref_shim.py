@@ -150,6 +150,10 @@ def install():
     _pkg("mogen.models.attentions", "mogen/models/attentions")
     _pkg("mogen.models.transformers", "mogen/models/transformers")
     _pkg("mogen.models.utils", "mogen/models/utils")
+    _pkg("mogen.models.gnns", "mogen/models/gnns")
+    # mogen/models/gnns/stgcn.py (imported by stmogen.py) asks mmcv.cnn for layer factories at import / build time
+    mmcv_cnn.build_norm_layer = lambda cfg, n, postfix="": ("bn" + str(postfix), nn.BatchNorm2d(n))
+    mmcv_cnn.build_activation_layer = lambda cfg: nn.ReLU()
     return REFERENCE_ROOT
 
 

@@ -88,8 +88,8 @@ def test_diffusion_tables_match_oracle_and_reference(golden_dir):
 
 def test_unsupported_parameterisations_fail_loudly():
     with pytest.raises(McmError):
-        diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="start_x",
-                                       model_var_type="fixed_large"))
+        diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="previous_x",
+                                       model_var_type="learned_range"))
     d = diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
                                        model_var_type="fixed_small", respace="10"))
     with pytest.raises(McmError):
@@ -118,6 +118,7 @@ def test_struct_layouts_match_header():
     assert fields == [f[0] for f in _lib.McmConfig._fields_]
     smp_body = re.search(r"typedef struct mcm_sampler \{(.*?)\} mcm_sampler;", header, re.S).group(1)
     fields = re.findall(r"^\s*(?:const\s+)?(?:int|float|unsigned long long)\*?\s+([a-z_0-9]+);", smp_body, re.M)
+    assert fields[-1] == "model_mean_type"
     assert fields == [f[0] for f in _lib.McmSampler._fields_]
 
 

@@ -1,0 +1,126 @@
+"""First pieces of Path B (configs/stmogen/*, SURVEY.md section 8 rows b1, b3, b8, b9 + the start_x / fixed_large sampler):
+the oracle against outputs of the UNMODIFIED reference (tests/golden/pathb.npz, oracle/make_golden.py::pathb) bit for bit on
+the CPU, the CUDA path against the same goldens on the GPU.  The mixture-of-experts of row b2 (tutel) is parity-unpinned and
+absent."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from motioncraft_b200 import synth
+from oracle import mcm_oracle as O
+from oracle import pathb_oracle as P
+from tests import common as C
+
+TOL_FAST, TOL_SPLIT = 1e-3, 5e-5       # fp16-operand denoiser / bf16x2-split GEMMs (embed / out class)
+
+
+def _gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "pathb.npz"))
+
+
+def _pose_sd(g):
+    from motioncraft_b200 import pathb
+    enc, dec = pathb.PoseEncoder(latent_dim=128), pathb.PoseDecoder(latent_dim=128)
+    names = {"joint_embed." + k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    names.update({"out." + k: tuple(v.shape) for k, v in dec.state_dict().items()})
+    assert sorted(names) == list(g["keys"])                    # the reference's parameter names and shapes
+    return synth.synth_state_dict(names), enc, dec
+
+
+def test_pathb_oracle_matches_reference_golden(golden_dir):
+    g = _gold(golden_dir)
+    sd, _, _ = _pose_sd(g)
+    B, T = g["pose_encode"].shape[:2]
+    x = synth.synth_tensor("pb_motion", (B, T, 322), synth.SEED_XT)
+    with torch.no_grad():
+        h = P.pose_encode(sd, x)
+        assert torch.equal(h, torch.from_numpy(g["pose_encode"]))
+        assert torch.equal(P.pose_decode(sd, h), torch.from_numpy(g["pose_decode"]))
+        bw = synth.synth_tensor("body_weight", (12, 12), synth.SEED_WEIGHTS)
+        assert torch.equal(P.static_body_mix(bw, h.reshape(B, T, 12, 128)), torch.from_numpy(g["static_mix"]))
+        a = synth.synth_tensor("cfg_text", (B, T, 322), synth.SEED_XT)
+        b = synth.synth_tensor("cfg_none", (B, T, 322), synth.SEED_XF_OUT)
+        for t in (999, 500, 14, 0):
+            assert torch.equal(P.cfg_combine(a, b, t, 6.5), torch.from_numpy(g[f"cfg_t{t}"])), t
+    assert P.scale_func(999, 6.5)[0] == (1 - 1 / 1000) * 6.5 + 1 and sum(P.scale_func(123, 6.5)) == 1.0
+    assert sorted(P.body_slice()) == list(range(322))           # the eleven part slices partition the 322 columns
+
+
+def test_start_x_fixed_large_sampler_oracle_matches_reference_golden(golden_dir):
+    g = _gold(golden_dir)
+    T = 60
+    sd = C.base_state(T, 2)
+    x, xf_out, xf_proj = C.inputs(1, T)
+    fn = lambda xx, tt: O.mcm_forward(sd, xx, tt, xf_proj, xf_out)  # noqa: E731  (used as a fixed x_0-predictor)
+    tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
+    with torch.no_grad():
+        got = O.ddim_sample_loop(fn, x, tables, tmap, model_mean_type="start_x")
+        assert torch.equal(got, torch.from_numpy(g["startx_ddim50_x0"]))
+        tables, tmap = O.spaced_tables(1000, "10")
+        noise = synth.synth_tensor("step_noise", (10, 1, T, 322), synth.SEED_STEP_NOISE)
+        got = O.p_sample_loop(fn, x, tables, tmap, noise, model_mean_type="start_x", fixed_large=True)
+        assert torch.equal(got, torch.from_numpy(g["startx_ddpm10_x0"]))
+
+
+def test_pathb_modules_fail_loudly_without_gpu_and_for_moe():
+    from motioncraft_b200 import pathb
+    from motioncraft_b200._lib import McmError
+    with pytest.raises(McmError):
+        pathb.STMoGenTransformer()
+    if not torch.cuda.is_available():
+        with pytest.raises(McmError):
+            pathb.PoseEncoder()(torch.zeros(1, 2, 322))
+
+
+@pytest.mark.gpu
+def test_gpu_pathb_pieces_vs_reference_golden(golden_dir):
+    from motioncraft_b200 import pathb
+    g = _gold(golden_dir)
+    sd, enc, dec = _pose_sd(g)
+    enc.load_state_dict({k[len("joint_embed."):]: v for k, v in sd.items() if k.startswith("joint_embed.")})
+    dec.load_state_dict({k[len("out."):]: v for k, v in sd.items() if k.startswith("out.")})
+    enc, dec = enc.cuda(), dec.cuda()
+    B, T = g["pose_encode"].shape[:2]
+    x = synth.synth_tensor("pb_motion", (B, T, 322), synth.SEED_XT)
+    h = enc(x.cuda())
+    assert h.shape == (B, T, 1536) and C.rel_l2(h, g["pose_encode"]) < TOL_SPLIT
+    y = dec(torch.from_numpy(g["pose_encode"]).cuda())
+    assert y.shape == (B, T, 322) and C.rel_l2(y, g["pose_decode"]) < TOL_SPLIT
+    bw = synth.synth_tensor("body_weight", (12, 12), synth.SEED_WEIGHTS)
+    mix = pathb.static_body_mix(bw.cuda(), torch.from_numpy(g["pose_encode"]).cuda().view(B, T, 12, 128))
+    assert C.rel_l2(mix, g["static_mix"]) < 1e-6
+    a = synth.synth_tensor("cfg_text", (B, T, 322), synth.SEED_XT)
+    b = synth.synth_tensor("cfg_none", (B, T, 322), synth.SEED_XF_OUT)
+    for t in (999, 500, 14, 0):
+        assert torch.equal(pathb.cfg_combine(a.cuda(), b.cuda(), t).cpu(), torch.from_numpy(g[f"cfg_t{t}"])), t
+    # a larger, ragged batch of rows through the block-structured GEMMs against the oracle
+    x2 = synth.synth_tensor("pb_motion2", (3, 197, 322), synth.SEED_XT)
+    with torch.no_grad():
+        want = P.pose_decode(sd, P.pose_encode(sd, x2))
+    assert C.rel_l2(dec(enc(x2.cuda())), want) < TOL_SPLIT
+
+
+@pytest.mark.gpu
+def test_gpu_start_x_fixed_large_sampler_vs_reference_golden(golden_dir):
+    """ModelMeanType.START_X / ModelVarType.FIXED_LARGE (configs/stmogen/*): DDIM-50 and DDPM-10 through the front end
+    (build_diffusion -> SpacedDiffusion -> mcm_sample) with the denoiser as a fixed x_0-predictor."""
+    import motioncraft_b200 as M
+    from motioncraft_b200 import diffusion, modules
+    g = _gold(golden_dir)
+    T = 60
+    net = M.MCMTransformer(**modules.mcm_config(T, num_layers=2))
+    net.use_text_proj = True
+    net.load_state_dict(C.base_state(T, 2))
+    net = net.cuda().eval()
+    x, xf_out, xf_proj = C.inputs(1, T)
+    kw = dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    cfg = dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="start_x", model_var_type="fixed_large")
+    d = diffusion.build_diffusion(dict(cfg, respace="15,15,8,6,6"))
+    x0 = d.ddim_sample_loop(net, (1, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw, eta=0)
+    assert C.rel_l2(x0, g["startx_ddim50_x0"]) < TOL_FAST
+    d = diffusion.build_diffusion(dict(cfg, respace="10"))
+    noise = synth.synth_tensor("step_noise", (10, 1, T, 322), synth.SEED_STEP_NOISE)
+    x0 = d.p_sample_loop(net, (1, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw, step_noise=noise.cuda())
+    assert C.rel_l2(x0, g["startx_ddpm10_x0"]) < TOL_FAST
