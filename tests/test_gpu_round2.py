@@ -249,18 +249,19 @@ from motioncraft_b200 import dist as mdist, modules, synth
 from motioncraft_b200.engine import DenoiserEngine, SamplerTables
 from oracle import mcm_oracle as O
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
 T, N = 196, 24
 sd = {k: v for k, v in synth.synth_state_dict(modules.state_shapes(seq_len=T)).items() if ".ffn_channel." not in k}
 tables, tmap = O.spaced_tables(1000, "15,15,8,6,6")
 st = SamplerTables(tables, tmap, "ddim")
 def run(lo, hi):
-    eng = DenoiserEngine(sd, seq_len=T, max_batch=hi - lo)
+    eng = DenoiserEngine(sd, seq_len=T, max_batch=hi - lo, device=dev)
     eng.set_option("fused_min_rows", 0)     # one schedule for every launch size: results comparable bit for bit
-    eng.prepare_conditions(synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, lo, hi).cuda(),
-                           synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, lo, hi).cuda())
-    out = eng.sample(st, synth.synth_rows("x_T", (T, 322), synth.SEED_XT, lo, hi).cuda())
+    eng.prepare_conditions(synth.synth_rows("xf_out", (77, 256), synth.SEED_XF_OUT, lo, hi).to(dev),
+                           synth.synth_rows("xf_proj", (2048,), synth.SEED_XF_PROJ, lo, hi).to(dev))
+    out = eng.sample(st, synth.synth_rows("x_T", (T, 322), synth.SEED_XT, lo, hi).to(dev))
     eng.close()
     return out
 lo, hi = mdist.shard_range(N, rank, world)
@@ -286,7 +287,7 @@ def test_two_rank_nccl_gather_is_bit_equal_to_single_gpu(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[:3000] + r.stderr[-1500:]
     assert "bit-equal" in r.stdout
 
 
