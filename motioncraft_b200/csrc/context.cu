@@ -92,6 +92,7 @@ struct mcm_ctx {
   cudaStream_t s0 = nullptr;             // capture / replay stream used when the caller's stream is the legacy default
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int dual = 1;                          // MCM_DUAL=0: single stream
+  int split_sms = 0;                     // MCM_SPLIT_SMS=1: the two halves' persistent kernels each take half the SMs
   // CUDA graph of one denoise step (sampler loop): captured once per (batch, control on/off), replayed every step;
   // the step's timestep is read from `t_buf`, so the graph is identical for all steps.
   int use_graph = 1;                     // MCM_GRAPH=0: eager launches
@@ -103,7 +104,7 @@ struct mcm_ctx {
   float* noise_buf = nullptr;            // [Bmax*T*IN] per-step sampler noise staged / generated on the device (lazy)
   // every scheduling option that changes the captured launch sequence is part of the graph key
   long long graph_key() const {
-    return (long long)fused + 2ll * fused_sa + 16ll * (dual ? 1 : 0) + 32ll * fused_stop + 512ll * (long long)chunk +
+    return (long long)fused + 2ll * fused_sa + 16ll * (dual ? 1 : 0) + 32ll * fused_stop + 256ll * (split_sms ? 1 : 0) + 512ll * (long long)chunk +
            (1ll << 24) * (long long)fused_min_rows;
   }
   void drop_graphs() {
@@ -562,8 +563,14 @@ int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float
     const int B0 = (B + 1) / 2;
     MCM_CUDA(cudaEventRecord(c->ev_fork, st));
     MCM_CUDA(cudaStreamWaitEvent(c->s1, c->ev_fork, 0));
-    MCM_TRY(run_layers(c, c->ws[0], 0, B0, eps_out, st));
-    MCM_TRY(run_layers(c, c->ws[1], B0, B - B0, eps_out, c->s1));
+    // split_sms: every persistent kernel of the two halves is launched on HALF the SMs, so that the halves really run side
+    // by side (a 74-pair launch of one half otherwise occupies every SM and the other half queues behind it) and are in
+    // different phases -- all CTAs of one launch hit L2 / HBM in lock-step, two launches side by side smooth that demand
+    tc_set_sm_share(c->split_sms ? 2 : 1);
+    int rc = run_layers(c, c->ws[0], 0, B0, eps_out, st);
+    if (rc == 0) rc = run_layers(c, c->ws[1], B0, B - B0, eps_out, c->s1);
+    tc_set_sm_share(1);
+    MCM_TRY(rc);
     MCM_CUDA(cudaEventRecord(c->ev_join, c->s1));
     MCM_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
     return 0;
@@ -806,6 +813,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   int dual_env = -1;                     // MCM_DUAL only picks the default; the second scratch set always exists
   if (const char* e = getenv("MCM_DUAL")) dual_env = atoi(e);
   if (const char* e = getenv("MCM_GRAPH")) c->use_graph = atoi(e);
+  if (const char* e = getenv("MCM_SPLIT_SMS")) c->split_sms = atoi(e);
   if (dev_alloc(c, reinterpret_cast<void**>(&c->t_buf), (size_t)c->Bmax * sizeof(long long))) return fail(0);
   if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
@@ -855,6 +863,8 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     c->dual = value;
   } else if (n == "graph") {
     c->use_graph = value;
+  } else if (n == "split_sms") {
+    c->split_sms = value;
   } else if (n == "chunk") {
     c->chunk = value;
   } else if (n == "fused") {

@@ -1301,6 +1301,16 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
           __syncwarp();
           if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
         }
+      {
+        // pull the NEXT tile's [T x 128 channels] slab of h into L2 (one 512-byte row segment per lane and iteration).  Issued
+        // by this otherwise idle warp: in the compute warps the 196 prefetch instructions cost ~2 k cycles of every tile.
+        const int nt = tile + n_clusters;
+        if (nt < p.n_tiles) {
+          const float* nsrc = p.h + ((size_t)(nt >> 1) * p.T) * D + (nt & 1) * 2 * ROWS + rank * ROWS;
+          for (int t = lane; t < p.T; t += 32)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + (size_t)t * D) : "memory");
+        }
+      }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (leader)
@@ -1458,64 +1468,66 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(smem_u32(&pa_bar), 0u);
-        {
-          // pull the next tile's [T x 128 channels] slab of h into L2 (one 512-byte row segment per thread)
-          const int nt = tile + n_clusters;
-          if (nt < p.n_tiles) {
-            const float* nsrc = p.h + ((size_t)(nt >> 1) * p.T) * D + (nt & 1) * 2 * ROWS + rank * ROWS;
-            for (int t = ctid; t < p.T; t += NCW * 32)
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(nsrc + (size_t)t * D) : "memory");
-          }
-        }
         SF_TICK(1);
       }
       wait_tf(0);                                             // q complete
       SF_TICK(2);
       {
-        // ---- E_q: per-head softmax of q + bq.  The quadrant's two warps take two heads each; a head's T/H columns are
-        // read as ceil(hd/32) chunks ALIGNED TO THE HEAD START (TMEM columns are addressable one by one), so only a
-        // per-chunk valid count masks elements.  Pass 1: online max / sum; pass 2: normalised fp16 into the row staging.
+        // ---- E_q: per-head softmax of q + bq.  The quadrant's two warps take two heads each; a head's T/H <= 64 columns are
+        // read as TWO chunks ALIGNED TO THE HEAD START (TMEM columns are addressable one by one), both loads in flight
+        // together and kept in registers: one TMEM pass, one exp per element (max -> exp -> sum -> scale out of the same 64
+        // registers), only per-chunk valid counts mask elements.  Normalised fp16 rows go to the staging tile as packed pairs.
         if (part == 0) drain();                                // the staging rows may still be read by this warp's last store
         bar_sync(1 + quad, 64);
+        const int nv0 = min(32, p.hd), nv1 = p.hd - nv0;       // valid columns of the head's two chunks (hd <= 64)
 #pragma unroll 1
         for (int hh = 2 * part; hh < 2 * part + 2; ++hh) {
           const int lo = hh * p.hd;
-          const int nc = (p.hd + 31) >> 5;
-          float m = -INFINITY, ssum = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < nc; ++c) {
-            float v[32];
-            tmem_ld_32x32(trow + (uint32_t)(lo + c * 32), v);
-            const int nv = min(32, p.hd - c * 32);
-            const float bmine = lane < nv ? prm[2 * Tq + lo + c * 32 + lane] : 0.f;
-            tmem_ld_wait();
-            add_bias32(bslot, lane, bmine, v);
-            float cm = -INFINITY;
+          float v0[32], v1[32];
+          tmem_ld_32x32(trow + (uint32_t)lo, v0);
+          tmem_ld_32x32(trow + (uint32_t)(lo + 32), v1);       // may reach into the next head / stale columns: masked by nv1
+          const float b0 = lane < nv0 ? prm[2 * Tq + lo + lane] : 0.f;
+          const float b1 = lane < nv1 ? prm[2 * Tq + lo + 32 + lane] : 0.f;
+          tmem_ld_wait();
+          add_bias32(bslot, lane, b0, v0);
+          add_bias32(bslot, lane, b1, v1);
+          float m = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, j < nv ? v[j] : -INFINITY);
-            const float mn = fmaxf(m, cm);
-            const float mnl = mn * L2E;
-            float cs = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) cs += j < nv ? ex2_fast(fmaf(v[j], L2E, -mnl)) : 0.f;
-            ssum = ssum * ex2_fast((m - mn) * L2E) + cs;      // exp(-inf) = 0 on the first chunk
-            m = mn;
+          for (int j = 0; j < 32; ++j) {
+            m = fmaxf(m, j < nv0 ? v0[j] : -INFINITY);
+            m = fmaxf(m, j < nv1 ? v1[j] : -INFINITY);
           }
           const float ml = m * L2E;
-          const float inv = 1.f / ssum;
-#pragma unroll 1
-          for (int c = 0; c < nc; ++c) {
-            float v[32];
-            tmem_ld_32x32(trow + (uint32_t)(lo + c * 32), v);
-            const int nv = min(32, p.hd - c * 32);
-            const float bmine = lane < nv ? prm[2 * Tq + lo + c * 32 + lane] : 0.f;
-            tmem_ld_wait();
-            add_bias32(bslot, lane, bmine, v);
-            uint16_t* dst = stg_q_gen + lane * p.Tp + lo + c * 32;
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) dst[j] = f32_to_f16_bits(ex2_fast(fmaf(v[j], L2E, -ml)) * inv);
+          for (int j = 0; j < 32; ++j) {
+            v0[j] = j < nv0 ? ex2_fast(fmaf(v0[j], L2E, -ml)) : 0.f;
+            v1[j] = j < nv1 ? ex2_fast(fmaf(v1[j], L2E, -ml)) : 0.f;
+            s0 += v0[j];
+            s1 += v1[j];
           }
+          const float inv = 1.f / (s0 + s1);
+          // row `lane` of the staging tile, columns [lo, lo + hd): 4-byte stores of packed pairs where the halfword index
+          // is even (the pitch Tp is a multiple of 8, so the parity is that of lo), a single halfword at the ragged ends
+          uint16_t* const dst = stg_q_gen + lane * p.Tp + lo;
+          auto store_chunk = [&](const float* v, int nv, uint16_t* d) {
+            if ((lo & 1) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                if (j + 1 < nv) *reinterpret_cast<uint32_t*>(d + j) = pack_f16x2_sat(v[j] * inv, v[j + 1] * inv);
+                else if (j < nv) d[j] = f32_to_f16_bits(v[j] * inv);
+              }
+            } else {
+              if (0 < nv) d[0] = f32_to_f16_bits(v[0] * inv);
+#pragma unroll
+              for (int j = 1; j < 32; j += 2) {
+                if (j + 1 < 32 && j + 1 < nv) *reinterpret_cast<uint32_t*>(d + j) = pack_f16x2_sat(v[j] * inv, v[j + 1] * inv);
+                else if (j < nv) d[j] = f32_to_f16_bits(v[j] * inv);
+              }
+            }
+          };
+          store_chunk(v0, nv0, dst);
+          if (nv1 > 0) store_chunk(v1, nv1, dst + 32);
         }
         if (part == 1)
           for (int col = p.T; col < p.Tp; ++col) stg_q_gen[lane * p.Tp + col] = 0;   // operand pad columns
@@ -1920,7 +1932,7 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
             "fused block: unexpected operand pitch");
   MCM_CHECK(a.mod_ld % 4 == 0, "fused block: modulation pitch");
   const int n_tiles = (a.rows + 2 * ROWS - 1) / (2 * ROWS);
-  const int n_pairs = std::min(n_tiles, g_fb_max_pairs);
+  const int n_pairs = std::min(n_tiles, std::max(1, g_fb_max_pairs / tc_sm_share()));
   const int grid = 2 * n_pairs;
   MCM_CHECK((size_t)grid * ROWS * F * 2 <= fused_block_hid_bytes(), "fused block: hidden scratch too small");
 
@@ -1973,7 +1985,7 @@ int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
   std::memset(&p, 0, sizeof(p));
   p.T = T; p.Np = Np; p.nkb = (T + 63) / 64; p.nch = (T + 31) / 32; p.batch = a.batch; p.n_tiles = a.batch * 2;
   p.mod_ld = a.mod_ld; p.pn_w = a.pn_w; p.pn_b = a.pn_b; p.scale = a.scale; p.shift = a.shift; p.bo = a.bo;
-  const int n_pairs = std::min(p.n_tiles, max_pairs);
+  const int n_pairs = std::min(p.n_tiles, std::max(1, max_pairs / tc_sm_share()));
   const double flops = 2.0 * (double)a.batch * D * ((double)T * (T / 4) + (double)T * T);   // q ctx (per head) + out
   return launch_pairs(sa_tail_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
 }
@@ -1999,7 +2011,7 @@ int sa_front_launch(const SaFrontArgs& a, cudaStream_t stream) {
   p.h = a.h; p.T = T; p.Tp = Tp; p.Np = Np; p.nkb = (T + 63) / 64; p.nch = (T + 31) / 32; p.hd = T / H; p.batch = a.batch;
   p.n_tiles = a.batch * 2; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.bqkv = a.bqkv;
   p.prof = (g_fb_prof != nullptr && getenv("MCM_SF_PROF") != nullptr) ? g_fb_prof : nullptr;
-  const int n_pairs = std::min(p.n_tiles, max_pairs);
+  const int n_pairs = std::min(p.n_tiles, std::max(1, max_pairs / tc_sm_share()));
   const double flops = 2.0 * (double)a.batch * D * (double)T * 3.0 * T;
   return launch_pairs(sa_front_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
 }
@@ -2020,7 +2032,7 @@ int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream) {
   std::memset(&p, 0, sizeof(p));
   p.k32 = a.k32; p.ctxT = reinterpret_cast<uint16_t*>(a.ctxT.hi); p.Tp = Tp; p.rows = a.batch * T; p.T = T; p.Np = Np; p.hd = T / a.heads; p.nch = (T + 31) / 32; p.batch = a.batch;
   p.n_tiles = (p.rows + 2 * ROWS - 1) / (2 * ROWS);
-  const int n_pairs = std::min(p.n_tiles, max_pairs);
+  const int n_pairs = std::min(p.n_tiles, std::max(1, max_pairs / tc_sm_share()));
   const double flops = 2.0 * (double)a.batch * T * (T / a.heads) * D;      // only the per-head diagonal blocks are algorithmic
   return launch_pairs(sa_ctx_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
 }

@@ -665,6 +665,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
+int g_sm_share = 1;        // persistent kernels take 1 / g_sm_share of the SMs (two batch halves side by side: tc_set_sm_share)
 std::once_flag g_init_once;
 int g_init_status = 0;
 std::atomic<unsigned long long> g_launches{0};
@@ -886,6 +887,8 @@ int tc_make_box_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, lo
   return 0;
 }
 int tc_num_sms() { return gemm_tc_init() == 0 ? g_num_sms : 0; }
+void tc_set_sm_share(int share) { g_sm_share = share >= 1 ? share : 1; }
+int tc_sm_share() { return g_sm_share; }
 
 int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   MCM_TRY(gemm_tc_init());
@@ -994,7 +997,7 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
     tmAlo = tmA;
     tmBlo = tmB;
   }
-  const int n_clusters = std::min(p.total_tiles, p.pair ? g_max_pairs : g_max_clusters[cs]);
+  const int n_clusters = std::min(p.total_tiles, std::max(1, (p.pair ? g_max_pairs : g_max_clusters[cs]) / g_sm_share));
   const int grid = n_clusters * cs;
   double flops = q.algo_flops;
   if (flops <= 0.0) {

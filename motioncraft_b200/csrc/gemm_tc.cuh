@@ -70,6 +70,9 @@ int tc_make_operand_map(CUtensorMap* m, const void* ptr, int fmt, int k_dim, int
 int tc_make_tile_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
                      long long stride1_elems, long long stride2_elems, int swizzle_bytes);
 //   box map:     like the tile map but with an explicit {box0, box1, 1} box and no swizzle (row-staged stores)
+// Persistent kernels launched while share = n use 1 / n of the SMs, so that the kernels of n streams run side by side.
+void tc_set_sm_share(int share);
+int tc_sm_share();
 int tc_make_box_map(CUtensorMap* m, const void* ptr, int dtype, long long d0, long long d1, long long d2,
                     long long stride1_elems, long long stride2_elems, int box0, int box1);
 int tc_num_sms();
