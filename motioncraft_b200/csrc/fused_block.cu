@@ -90,6 +90,40 @@ __device__ __forceinline__ float silu_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + ex2_fast(-x * L2E)));
   return x * r;
 }
+// ---- packed fp32 pairs (sm_100a `fma.rn.f32x2` = one FFMA2 issue slot for two FMAs): the GELU phase is issue-bound
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// silu_fast for two elements (same operations per element)
+__device__ __forceinline__ f32x2 silu2(f32x2 x) {
+  float n0, n1;
+  upk2(mul2(x, pk2(-L2E, -L2E)), n0, n1);
+  float d0, d1;
+  upk2(add2(pk2(ex2_fast(n0), ex2_fast(n1)), pk2(1.f, 1.f)), d0, d1);
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return mul2(x, pk2(r0, r1));
+}
 // erf-GELU as relu(x) - 0.5 |x| erfc(|x| / sqrt 2) with the Abramowitz-Stegun 7.1.26 erfc (|abs err| < 5e-7, far below
 // the fp16 rounding of the result): 13 FP32 ops + 2 MUFU, no select
 __device__ __forceinline__ float gelu_relu_erfc(float x) {
@@ -103,6 +137,29 @@ __device__ __forceinline__ float gelu_relu_erfc(float x) {
   const float e = ex2_fast(ax * ax * (-0.5f * L2E));
   return fmaf(-0.5f * ax, poly * t * e, fmaxf(x, 0.f));
 }
+// gelu_relu_erfc for two elements at once: the same operations in the same order per element (bit-identical results), the
+// FMA / MUL chain issued as packed pairs
+__device__ __forceinline__ void gelu_relu_erfc2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const f32x2 ax = pk2(a0, a1);
+  const f32x2 one = pk2(1.f, 1.f);
+  float d0, d1;
+  upk2(fma2(pk2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f), ax, one), d0, d1);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const f32x2 t = pk2(t0, t1);
+  f32x2 poly = fma2(t, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
+  poly = fma2(t, poly, pk2(1.421413741f, 1.421413741f));
+  poly = fma2(t, poly, pk2(-0.284496736f, -0.284496736f));
+  poly = fma2(t, poly, pk2(0.254829592f, 0.254829592f));
+  float q0, q1;
+  upk2(mul2(mul2(ax, ax), pk2(-0.5f * L2E, -0.5f * L2E)), q0, q1);
+  const f32x2 e = pk2(ex2_fast(q0), ex2_fast(q1));
+  const f32x2 pte = mul2(mul2(poly, t), e);
+  const f32x2 mh = mul2(pk2(-0.5f, -0.5f), ax);
+  upk2(fma2(mh, pte, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
+}
 // shared-memory address of the 16-byte chunk holding columns [col, col + 8) of row `row` of the operand tile
 __device__ __forceinline__ uint32_t opa_addr(uint32_t opa, int row, int col) {
   return opa + (uint32_t)(col >> 6) * SLAB + (uint32_t)row * 128u + (((((uint32_t)col >> 3) & 7u) ^ ((uint32_t)row & 7u)) << 4);
@@ -114,7 +171,8 @@ __device__ __forceinline__ void add_bias32(float* slot, int lane, float mine, fl
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b4 = *reinterpret_cast<const float4*>(slot + 4 * q);
-    v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+    upk2(add2(pk2(v[4 * q], v[4 * q + 1]), pk2(b4.x, b4.y)), v[4 * q], v[4 * q + 1]);
+    upk2(add2(pk2(v[4 * q + 2], v[4 * q + 3]), pk2(b4.z, b4.w)), v[4 * q + 2], v[4 * q + 3]);
   }
   __syncwarp();
 }
@@ -240,12 +298,15 @@ __device__ __forceinline__ void epi_softmax(uint32_t trow, int part, int row, ui
       tmem_ld_wait();
       add_bias32(bslot, lane, bcur, v);
       bcur = bnxt;
+      const f32x2 l2 = pk2(L2E, L2E), nml = pk2(-ml, -ml);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        v[j] = ex2_fast(fmaf(v[j], L2E, -ml));         s0 += v[j];
-        v[j + 1] = ex2_fast(fmaf(v[j + 1], L2E, -ml)); s1 += v[j + 1];
-        v[j + 2] = ex2_fast(fmaf(v[j + 2], L2E, -ml)); s2 += v[j + 2];
-        v[j + 3] = ex2_fast(fmaf(v[j + 3], L2E, -ml)); s3 += v[j + 3];
+        float a0, a1, a2, a3;
+        upk2(fma2(pk2(v[j], v[j + 1]), l2, nml), a0, a1);
+        upk2(fma2(pk2(v[j + 2], v[j + 3]), l2, nml), a2, a3);
+        v[j] = ex2_fast(a0); v[j + 1] = ex2_fast(a1); v[j + 2] = ex2_fast(a2); v[j + 3] = ex2_fast(a3);
+        upk2(add2(pk2(s0, s1), pk2(v[j], v[j + 1])), s0, s1);
+        upk2(add2(pk2(s2, s3), pk2(v[j + 2], v[j + 3])), s2, s3);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -269,7 +330,7 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
   float K = 0.f, sd = 0.f, sq = 0.f;
   float bcur = BIAS ? __ldg(bias + ccol(part, 0) + lane) : 0.f;
   float bcur2 = BIAS ? __ldg(bias + ccol(part, 1) + lane) : 0.f;
-  float sd2 = 0.f, sq2 = 0.f;                 // second accumulator chain (tile pairs: two TMEM loads in flight)
+  f32x2 sdp = pk2(0.f, 0.f), sqp = pk2(0.f, 0.f), sdp2 = pk2(0.f, 0.f), sqp2 = pk2(0.f, 0.f);   // (tile pairs: two TMEM loads in flight)
 #pragma unroll 1
   for (int c = 0; c < NCH; c += 2) {
     float v[32], w[32];
@@ -287,18 +348,25 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
     bcur = bnxt; bcur2 = bnxt2;
     const float sc = SCALE ? ((c >> 2) ? inv1 : inv0) : 1.f;     // a pair of tiles never straddles a head (128 columns)
     if (c == 0) K = v[0] * sc;
+    // packed fp32 pairs (FFMA2): the phase is issue-bound; four independent accumulator chains per statistic
+    const f32x2 sc2 = pk2(sc, sc), nk2 = pk2(-K, -K);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = SCALE ? fmaf(v[j], sc, -K) : v[j] - K;
-      const float d2 = SCALE ? fmaf(w[j], sc, -K) : w[j] - K;
-      sd += d;
-      sq = fmaf(d, d, sq);
-      sd2 += d2;
-      sq2 = fmaf(d2, d2, sq2);
+    for (int j = 0; j < 32; j += 2) {
+      const f32x2 d = fma2(pk2(v[j], v[j + 1]), sc2, nk2);
+      const f32x2 d2 = fma2(pk2(w[j], w[j + 1]), sc2, nk2);
+      sdp = add2(sdp, d);
+      sqp = fma2(d, d, sqp);
+      sdp2 = add2(sdp2, d2);
+      sqp2 = fma2(d2, d2, sqp2);
     }
   }
-  sd += sd2;
-  sq += sq2;
+  {
+    float a0, a1, b0, b1;
+    upk2(add2(sdp, sdp2), a0, a1);
+    upk2(add2(sqp, sqp2), b0, b1);
+    sd = a0 + a1;
+    sq = b0 + b1;
+  }
   bcur = BIAS ? __ldg(bias + ccol(part, 0) + lane) : 0.f;
   const float mean_w = fmaf(sd, 1.f / (float)CPW, K);
   const float m2_w = fmaf(-sd * (1.f / (float)CPW), sd, sq);
@@ -337,14 +405,11 @@ __device__ __forceinline__ void epi_lnmod(uint32_t trow, int part, int row, bool
       const float4 ba = *reinterpret_cast<const float4*>(prm + D + col + 8 * q);
       const float4 bb = *reinterpret_cast<const float4*>(prm + D + col + 8 * q + 4);
       float y[8];
-      y[0] = silu_fast(fmaf(fmaf(v[8 * q], A, Bc), ga.x, ba.x));
-      y[1] = silu_fast(fmaf(fmaf(v[8 * q + 1], A, Bc), ga.y, ba.y));
-      y[2] = silu_fast(fmaf(fmaf(v[8 * q + 2], A, Bc), ga.z, ba.z));
-      y[3] = silu_fast(fmaf(fmaf(v[8 * q + 3], A, Bc), ga.w, ba.w));
-      y[4] = silu_fast(fmaf(fmaf(v[8 * q + 4], A, Bc), gb.x, bb.x));
-      y[5] = silu_fast(fmaf(fmaf(v[8 * q + 5], A, Bc), gb.y, bb.y));
-      y[6] = silu_fast(fmaf(fmaf(v[8 * q + 6], A, Bc), gb.z, bb.z));
-      y[7] = silu_fast(fmaf(fmaf(v[8 * q + 7], A, Bc), gb.w, bb.w));
+      const f32x2 A2 = pk2(A, A), B2 = pk2(Bc, Bc);
+      upk2(silu2(fma2(fma2(pk2(v[8 * q], v[8 * q + 1]), A2, B2), pk2(ga.x, ga.y), pk2(ba.x, ba.y))), y[0], y[1]);
+      upk2(silu2(fma2(fma2(pk2(v[8 * q + 2], v[8 * q + 3]), A2, B2), pk2(ga.z, ga.w), pk2(ba.z, ba.w))), y[2], y[3]);
+      upk2(silu2(fma2(fma2(pk2(v[8 * q + 4], v[8 * q + 5]), A2, B2), pk2(gb.x, gb.y), pk2(bb.x, bb.y))), y[4], y[5]);
+      upk2(silu2(fma2(fma2(pk2(v[8 * q + 6], v[8 * q + 7]), A2, B2), pk2(gb.z, gb.w), pk2(bb.z, bb.w))), y[6], y[7]);
       if (act)
         st_shared_v4u(opa_addr(opa, row, col + 8 * q), pack_f16x2_sat(y[0], y[1]), pack_f16x2_sat(y[2], y[3]),
                       pack_f16x2_sat(y[4], y[5]), pack_f16x2_sat(y[6], y[7]));
@@ -824,7 +889,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           if (NCW == 8) {
             add_bias32(bias4_s[NCW == 8 ? ew : 0], lane, bcur, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_relu_erfc(v[j]);
+            for (int j = 0; j < 32; j += 2) gelu_relu_erfc2(v[j], v[j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_relu_erfc(v[j] + __shfl_sync(0xffffffffu, bcur, j));
@@ -1149,14 +1214,11 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
             const float4 ba = *reinterpret_cast<const float4*>(prm + Tq + col + 8 * q);
             const float4 bb = *reinterpret_cast<const float4*>(prm + Tq + col + 8 * q + 4);
             float y[8];
-            y[0] = silu_fast(fmaf(fmaf(v[8 * q], rstd, Bc), ga.x, ba.x));
-            y[1] = silu_fast(fmaf(fmaf(v[8 * q + 1], rstd, Bc), ga.y, ba.y));
-            y[2] = silu_fast(fmaf(fmaf(v[8 * q + 2], rstd, Bc), ga.z, ba.z));
-            y[3] = silu_fast(fmaf(fmaf(v[8 * q + 3], rstd, Bc), ga.w, ba.w));
-            y[4] = silu_fast(fmaf(fmaf(v[8 * q + 4], rstd, Bc), gb.x, bb.x));
-            y[5] = silu_fast(fmaf(fmaf(v[8 * q + 5], rstd, Bc), gb.y, bb.y));
-            y[6] = silu_fast(fmaf(fmaf(v[8 * q + 6], rstd, Bc), gb.z, bb.z));
-            y[7] = silu_fast(fmaf(fmaf(v[8 * q + 7], rstd, Bc), gb.w, bb.w));
+            const f32x2 A2 = pk2(rstd, rstd), B2 = pk2(Bc, Bc);       // packed fp32 pairs (FFMA2): the phase is issue-bound
+            upk2(silu2(fma2(fma2(pk2(v[8 * q], v[8 * q + 1]), A2, B2), pk2(ga.x, ga.y), pk2(ba.x, ba.y))), y[0], y[1]);
+            upk2(silu2(fma2(fma2(pk2(v[8 * q + 2], v[8 * q + 3]), A2, B2), pk2(ga.z, ga.w), pk2(ba.z, ba.w))), y[2], y[3]);
+            upk2(silu2(fma2(fma2(pk2(v[8 * q + 4], v[8 * q + 5]), A2, B2), pk2(gb.x, gb.y), pk2(bb.x, bb.y))), y[4], y[5]);
+            upk2(silu2(fma2(fma2(pk2(v[8 * q + 6], v[8 * q + 7]), A2, B2), pk2(gb.z, gb.w), pk2(bb.z, bb.w))), y[6], y[7]);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               if (col + 8 * q + e >= p.T) y[e] = 0.f;           // K padding of the next GEMM must be exactly zero
@@ -1455,10 +1517,12 @@ sa_front_kernel(const __grid_constant__ SfMaps tm, const __grid_constant__ SfPar
               const float4 ga = *reinterpret_cast<const float4*>(prm + t8), gb = *reinterpret_cast<const float4*>(prm + t8 + 4);
               const float4 ba = *reinterpret_cast<const float4*>(prm + Tq + t8), bb = *reinterpret_cast<const float4*>(prm + Tq + t8 + 4);
               const float* xx = x + 8 * g8;
-              const float y0 = fmaf((xx[0] - mean) * rstd, ga.x, ba.x), y1 = fmaf((xx[1] - mean) * rstd, ga.y, ba.y);
-              const float y2 = fmaf((xx[2] - mean) * rstd, ga.z, ba.z), y3 = fmaf((xx[3] - mean) * rstd, ga.w, ba.w);
-              const float y4 = fmaf((xx[4] - mean) * rstd, gb.x, bb.x), y5 = fmaf((xx[5] - mean) * rstd, gb.y, bb.y);
-              const float y6 = fmaf((xx[6] - mean) * rstd, gb.z, bb.z), y7 = fmaf((xx[7] - mean) * rstd, gb.w, bb.w);
+              const f32x2 nm2 = pk2(-mean, -mean), r2 = pk2(rstd, rstd);     // packed fp32 pairs, same operations per element
+              float y0, y1, y2, y3, y4, y5, y6, y7;
+              upk2(fma2(mul2(add2(pk2(xx[0], xx[1]), nm2), r2), pk2(ga.x, ga.y), pk2(ba.x, ba.y)), y0, y1);
+              upk2(fma2(mul2(add2(pk2(xx[2], xx[3]), nm2), r2), pk2(ga.z, ga.w), pk2(ba.z, ba.w)), y2, y3);
+              upk2(fma2(mul2(add2(pk2(xx[4], xx[5]), nm2), r2), pk2(gb.x, gb.y), pk2(bb.x, bb.y)), y4, y5);
+              upk2(fma2(mul2(add2(pk2(xx[6], xx[7]), nm2), r2), pk2(gb.z, gb.w), pk2(bb.z, bb.w)), y6, y7);
               st_shared_v4u(opa_addr(opa, row, t8), pack_f16x2_sat(y0, y1), pack_f16x2_sat(y2, y3), pack_f16x2_sat(y4, y5),
                             pack_f16x2_sat(y6, y7));
             }

@@ -135,11 +135,18 @@ def ffn(x, emb, sd, prefix, mm_round=None):
     return x + stylization(y, emb, sd, prefix + ".proj_out", mm_round)
 
 
+# The reference EXECUTES ffn_channel and throws its result away (mcm.py:33-34).  The parity oracle skips it (same values);
+# the timed reference arm of bench.py sets this flag so that the CPU baseline does the work the reference really does.
+EXECUTE_DEAD_FFN_CHANNEL = False
+
+
 def decoder_layer(x, xf, emb, sd, prefix, num_heads, mm_round=None, ca_context=None):
     """mcm.py DecoderLayer.forward :25-41.  ffn_channel (:33-34) is computed and DISCARDED by the
-    reference (its result never re-enters kwargs['x']), so it is not evaluated here."""
+    reference (its result never re-enters kwargs['x']), so it is not evaluated here unless the timing flag asks for it."""
     x = efficient_self_attention(x.transpose(-1, -2), emb, sd, prefix + ".sa_block", num_heads,
                                  mm_round).transpose(-1, -2)
+    if EXECUTE_DEAD_FFN_CHANNEL and (prefix + ".ffn_channel.linear1.weight") in sd:
+        ffn(x, emb, sd, prefix + ".ffn_channel", mm_round)                      # :33-34, result discarded as in the reference
     x = efficient_cross_attention(x, xf, emb, sd, prefix + ".ca_block", num_heads, mm_round, ca_context)
     return ffn(x, emb, sd, prefix + ".ffn_temporal", mm_round)
 
