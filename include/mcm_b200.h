@@ -77,7 +77,9 @@ void mcm_destroy(mcm_ctx* ctx);
  *   "fused_sa" channel attention: 0 = separate kernels, 1 = fused tail kernel, 2 = fused head and tail (default),
  *               3 = also the token softmax + context in one kernel (experimental, slower)
  *   "fused_min_rows" n = use the persistent fused kernels only for launches of at least n rows (B*T, per
- *               stream: half the batch with "dual"); default 2048.  Results of the two schedules agree to ~2e-4, not bit for bit */
+ *               stream: half the batch with "dual"); default 2048.  Results of the two schedules agree to ~2e-4, not bit for bit
+ *   "fused_sa_min_rows" n = a separate threshold for the fused channel-attention kernels; default -1 = fused_min_rows
+ *   "split_sms" 1 = with "dual", every persistent kernel takes half the SMs so the halves run side by side (default 0: slower) */
 int mcm_set_option(mcm_ctx* ctx, const char* name, int value);
 
 /* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key

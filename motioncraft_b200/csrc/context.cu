@@ -67,6 +67,7 @@ struct mcm_ctx {
                           //     replaces: its per-sample rounds serialise behind the row softmax; opt-in until reworked)
   int fused_min_rows = 2048;   // the persistent tile kernels need enough 256-row tiles to fill the 74 CTA pairs: below this
                                // many rows (B*T) per launch the kernel-per-op path is faster (B=1: 66 vs 75 ms per 50-step run)
+  int fused_sa_min_rows = -1;  // threshold of the fused channel-attention kernels; -1 = fused_min_rows
   int fused_stop = 0;     // debug: truncate the fused kernel after this many phases and dump its operand tile
   void* fused_dbg = nullptr;
   int chunk = 0;          // samples per pass through the layer stack (0 = whole batch); MCM_CHUNK
@@ -105,7 +106,7 @@ struct mcm_ctx {
   // every scheduling option that changes the captured launch sequence is part of the graph key
   long long graph_key() const {
     return (long long)fused + 2ll * fused_sa + 16ll * (dual ? 1 : 0) + 32ll * fused_stop + 256ll * (split_sms ? 1 : 0) + 512ll * (long long)chunk +
-           (1ll << 24) * (long long)fused_min_rows;
+           (1ll << 24) * (long long)fused_min_rows + (1ll << 44) * (long long)(fused_sa_min_rows >= 0 ? 1 + fused_sa_min_rows / 64 : 0);
   }
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
@@ -276,7 +277,11 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
 
   // ---- channel attention (EfficientSelfAttention on x^T, efficient_attention.py:25-46) ----
   const bool big = (long long)B * T >= c->fused_min_rows || c->fused_stop != 0;
-  const bool sa_fused = big && c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D) && H == 4 && 32 * Tp * 2 <= 16384;
+  // (the channel-attention kernels may get their own threshold: under ncu they win at every batch size -- B = 1: head 20 us +
+  // tail 13 us against 23 + 28 us for the six launches they replace -- but in the replayed graph the gain is within noise at
+  // B = 1 and 3 % at B = 8, so by default they follow fused_min_rows and a launch takes one schedule or the other as a whole)
+  const bool big_sa = (long long)B * T >= (c->fused_sa_min_rows >= 0 ? c->fused_sa_min_rows : c->fused_min_rows) || c->fused_stop != 0;
+  const bool sa_fused = big_sa && c->fused && c->fused_sa && ff == OP_F16 && sa_tail_supported(T, D) && H == 4 && 32 * Tp * 2 <= 16384;
   if (sa_fused && c->fused_sa >= 2) {
     // ---- LN_T(h^T) -> q | k | v -> softmax(q): one persistent kernel (fused_block.cu); k (fp32) and v go back to [B, T', D]
     SaFrontArgs a;
@@ -806,6 +811,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   if (const char* e = getenv("MCM_FUSED")) c->fused = atoi(e);
   if (const char* e = getenv("MCM_FUSED_SA")) c->fused_sa = atoi(e);
   if (const char* e = getenv("MCM_FUSED_MIN_ROWS")) c->fused_min_rows = atoi(e);
+  if (const char* e = getenv("MCM_FUSED_SA_MIN_ROWS")) c->fused_sa_min_rows = atoi(e);
   c->ws[0].hid = nullptr;
   if (!lo && fused_block_supported(c->T, c->D, c->F, c->H)) {
     if (dev_alloc(c, &c->ws[0].hid, fused_block_hid_bytes())) return fail(0);
@@ -873,6 +879,8 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     c->fused_sa = value;
   } else if (n == "fused_min_rows") {
     c->fused_min_rows = value;
+  } else if (n == "fused_sa_min_rows") {
+    c->fused_sa_min_rows = value;
   } else if (n == "fused_stop") {
     MCM_CHECK(value >= 0 && value <= 7, "fused_stop must be 0..7");
     c->fused_stop = value;

@@ -950,7 +950,19 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   }
   p.cs = cs;
   p.m_supers = (p.m_tiles + cs - 1) / cs;
-  const int bn_cap = split ? 128 : 256;
+  int bn_cap = split ? 128 : 256;
+  {
+    // Latency regime (small batches: a GEMM of a few tiles leaves most SMs idle and its duration is the epilogue of ONE
+    // CTA -- 16 us per launch at B = 1): narrower N tiles spread the same work over more CTAs, each with a shorter epilogue.
+    static const int spread = [] { const char* e = getenv("MCM_GEMM_SPREAD"); return e ? atoi(e) : 1; }();
+    static const int min_bn = [] { const char* e = getenv("MCM_GEMM_MIN_BN"); return e ? atoi(e) : 64; }();
+    auto items = [&](int cap) {
+      long long t = 0;
+      for (int s2 = 0; s2 < q.nseg; ++s2) t += (p.seg[s2].n_pad + cap - 1) / cap;
+      return t * ((p.m_tiles + cs - 1) / cs) * q.batches;
+    };
+    while (spread && bn_cap > min_bn && items(bn_cap) * 2 <= g_num_sms) bn_cap /= 2;
+  }
   const int tiles_for_max = (nmax + bn_cap - 1) / bn_cap;
   // a segment split over several N tiles needs tiles of whole 32-column chunks: the TMA epilogue stores
   // 32-wide boxes and must not spill into the neighbouring tile's columns
