@@ -320,17 +320,19 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     MCM_TRY(sa_ctx_launch(a, st));
   } else {
   MCM_TRY(softmax_seg_launch(w.f32B, B * T, D, D, D, opD_d, ff, st));
-  {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, stored transposed: ctxT[b][l][dk]
+  {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, needed transposed (ctxT[b][l][dk], the B operand of q ctx).
+     // Computed AS the transpose -- A = v (rows l), B = softmax(k) (rows dk): D[l][dk] = sum_n v[l, n] ks[dk, n] -- so the
+     // epilogue takes the plain TMA-store path instead of the transposing one (46 -> us per launch at B = 256).
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));
-    g.a = opD_d; g.a_rows = T; g.a_k = D; g.a_batches = B;
-    g.b = opB_d; g.b_rows = T; g.b_k = D; g.b_batches = B; g.b_batched = 1;
+    g.a = opB_d; g.a_rows = T; g.a_k = D; g.a_batches = B;
+    g.b = opD_d; g.b_rows = T; g.b_k = D; g.b_batches = B; g.b_batched = 1;
     g.fmt = ff; g.M = T; g.K = D; g.batches = B; g.inner = 1;
-    g.out_rows_per_outer = T; g.trans_rows = T; g.head_dim = hdT;
+    g.out_rows_per_outer = T; g.head_dim = hdT;
     g.nseg = 1;
     g.seg[0] = seg_default(T, 0);
     g.seg[0].op = view(w.ctxT_sa, Tp); g.seg[0].op_fmt = ff;
-    g.seg[0].flags = EPI_TRANSPOSED | EPI_MASK_BLOCKDIAG;
+    g.seg[0].flags = EPI_MASK_BLOCKDIAG;
     g.algo_flops = 2.0 * T * hdT * D * B;      // only the per-head diagonal blocks are algorithmic work
     MCM_TRY(gemm_tc_launch(g, st));
   }
