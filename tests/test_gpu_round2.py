@@ -370,3 +370,30 @@ def test_longform_window_pipeline_vs_oracle():
                                   [[r[j] for j in range(r.shape[0])] for r in rnoise], times=times)
     assert C.rel_l2(got, want) < TOL_FAST
     assert still_running, "sample_windows blocked on the device"
+
+
+def test_ddpm_1000_steps_shipped_default_vs_oracle():
+    """configs/mcm/mcm_t2m_smplx.py:73-79 ships `inference_type='ddpm'` with the un-respaced 1000-step schedule: the full
+    ancestral chain (T = 60, B = 1, scripted per-step noise) against the fp32 oracle, and
+    the same run with noise generated on the device (finite, reproducible through torch.manual_seed)."""
+    from motioncraft_b200 import diffusion
+    T, B, n = 60, 1, 1000
+    sd = C.base_state(T)
+    x, xf_out, xf_proj = C.inputs(B, T)
+    noise = synth.synth_tensor("step_noise1000", (n, B, T, 322), synth.SEED_STEP_NOISE)
+    want = C.oracle_ddpm(sd, x, xf_proj, xf_out, noise, respace=None)
+    net = M.MCMTransformer(**modules.mcm_config(T))
+    net.use_text_proj = True
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    d = diffusion.build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_mean_type="epsilon",
+                                       model_var_type="fixed_small"))
+    assert d.num_timesteps == n
+    kw = dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    x0 = d.p_sample_loop(net, (B, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw, step_noise=noise.cuda())
+    print("ddpm-1000 pooled / worst / max:", check_all_norms(x0, want, what="ddpm1000"))
+    torch.manual_seed(11)
+    a = d.p_sample_loop(net, (B, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw)
+    torch.manual_seed(11)
+    b = d.p_sample_loop(net, (B, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw)
+    assert torch.isfinite(a).all() and torch.equal(a, b) and not torch.equal(a, x0)
