@@ -567,7 +567,24 @@ int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float
     // slots) and the issue-bound row kernels stress complementary resources, and the halves are independent, so half
     // A's GEMM co-resides with half B's row kernels on the same SMs.  Fork after the shared prologue, join before the
     // caller's next kernel; everything stays ordered with respect to the caller's stream.
-    const int B0 = (B + 1) / 2;
+    int B0 = (B + 1) / 2;
+    {
+      // Wave quantisation of the persistent tile kernels: a launch of `tiles` 256-row tiles on `pairs` CTA pairs takes
+      // ceil(tiles / pairs) tile times however empty the last wave is (s2g: 128 x 300 rows = 150 tiles on 74 pairs = three
+      // tile times for 2.03 waves of work, in halves 75 = 74 + 1 each).  When the last wave would be nearly empty, the
+      // batch is split unevenly instead: the first part fills whole waves, the few peeled samples (fewer than
+      // fused_min_rows rows) take the kernel-per-op schedule on the second stream meanwhile.
+      const int pairs = fused_block_max_pairs();
+      const long long tiles = ((long long)B * c->T + 255) / 256;
+      if (pairs > 0 && c->fused && (long long)B * c->T >= c->fused_min_rows && c->ws[0].hid != nullptr && c->fused_stop == 0) {
+        const long long full = tiles / pairs, rem = tiles % pairs;
+        if (full >= 1 && rem > 0 && rem * 8 <= pairs) {
+          const int b_fit = (int)(full * pairs * 256 / c->T);          // samples whose rows fit `full` whole waves
+          const int peel = B - b_fit;
+          if (b_fit >= 1 && peel >= 1 && peel <= c->Bmax / 2 && (long long)peel * c->T < c->fused_min_rows) B0 = b_fit;
+        }
+      }
+    }
     MCM_CUDA(cudaEventRecord(c->ev_fork, st));
     MCM_CUDA(cudaStreamWaitEvent(c->s1, c->ev_fork, 0));
     // split_sms: every persistent kernel of the two halves is launched on HALF the SMs, so that the halves really run side

@@ -1977,6 +1977,7 @@ bool fused_block_supported(int T, int Dm, int Fm, int Hm) {
   return Dm == D && Fm == F && Hm == H && (2 * ROWS - 1) / T + 2 <= MAX_SAMPLES;
 }
 size_t fused_block_hid_bytes() { return (size_t)160 * ROWS * F * 2; }
+int fused_block_max_pairs() { return fb_init() == 0 ? g_fb_max_pairs : 0; }
 unsigned long long fused_block_launch_count() { return g_fb_launches.load(); }
 int fused_block_prof_read(unsigned long long* out, int reset) {
   for (int i = 0; i < 32; ++i) out[i] = 0;

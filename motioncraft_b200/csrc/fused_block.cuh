@@ -77,6 +77,8 @@ int sa_ctx_launch(const SaCtxArgs& a, cudaStream_t stream);
 // true if the fused kernel covers this architecture (latent 512, ffn 1024, 4 heads, T >= 52)
 bool fused_block_supported(int T, int D, int F, int H);
 size_t fused_block_hid_bytes();
+// CTA pairs a launch can keep resident (74 on a 148-SM B200), 0 if the kernel cannot run on this device
+int fused_block_max_pairs();
 int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream);
 unsigned long long fused_block_launch_count();
 void fused_block_count_replayed(unsigned long long n);
