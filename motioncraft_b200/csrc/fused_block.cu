@@ -1000,6 +1000,9 @@ struct StMaps {
 struct StParams {
   int T, Np, nkb, nch, batch, n_tiles, mod_ld;
   const float *pn_w, *pn_b, *scale, *shift, *bo;
+  unsigned long long* prof;   // MCM_FUSED_PROF=1 MCM_ST_PROF=1: summed cycles per phase of the compute warps
+  const float* h;             // residual stream (L2 prefetch of the tile E_b reduces into)
+  int pf;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -1067,6 +1070,14 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
     for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++it) {
       const int b = tile >> 1;
       const int r0 = tile * 2 * ROWS + rank * ROWS;            // first row of this CTA in the [B*512, T] token space
+      if (p.pf && elect_one()) {
+        // E_b reduce-adds into h[b, :, n0 .. n0+128): a cold line makes the L2 reduction wait for HBM, so pull the tile into
+        // L2 while G_a / E_a / G_b run (this warp is otherwise idle here)
+        const float* src = p.h + (size_t)b * p.T * D + (tile & 1) * 2 * ROWS + rank * ROWS;
+        for (int t = 0; t < p.T; ++t)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(src + (size_t)t * D) : "memory");
+      }
+      __syncwarp();
       mbar_wait(smem_u32(&aempty_bar), ((uint32_t)it & 1u) ^ 1u);   // G_b of the previous tile has read the operand tile
       const uint32_t abar = smem_u32(&afull_bar);
       if (elect_one()) {
@@ -1149,6 +1160,12 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
     };
     arrive(1);                                                // TMEM half 1 starts out free
     int prev_b = -1;
+    long long tph[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tph[i] = 0;
+    const bool prof = p.prof != nullptr;
+    long long tlast = prof ? clock64() : 0;
+#define ST_TICK(i) do { if (prof) { const long long _n = clock64(); tph[i] += _n - tlast; tlast = _n; } } while (0)
 #pragma unroll 1
     for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters) {
       const int b = tile >> 1;
@@ -1170,9 +1187,11 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
         bar_sync(5, NCW * 32);
         prev_b = b;
       }
+      ST_TICK(0);
       // ---- E_a
       mbar_wait(smem_u32(&tfull_bar[0]), tf_par[0]); tf_par[0] ^= 1u;
       tc_fence_after();
+      ST_TICK(1);
       {
         float K = 0.f, sd = 0.f, sq = 0.f;
 #pragma unroll 1
@@ -1201,6 +1220,7 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
         const float m2 = (m2_w + m2_o) + delta * delta * (n_mine * n_o / (float)p.T);
         const float rstd = rsqrtf(m2 / (float)p.T + 1e-5f);
         const float Bc = -mean * rstd;
+        ST_TICK(2);
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           float v[32];
@@ -1228,9 +1248,11 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
         }
       }
       arrive(0);
+      ST_TICK(3);
       // ---- E_b
       mbar_wait(smem_u32(&tfull_bar[1]), tf_par[1]); tf_par[1] ^= 1u;
       tc_fence_after();
+      ST_TICK(4);
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         float v[32];
@@ -1260,11 +1282,18 @@ sa_tail_kernel(const __grid_constant__ StMaps tm, const __grid_constant__ StPara
         pending = true;
       }
       arrive(1);
+      ST_TICK(5);
     }
     if (pending) {
       if (lane == 0) tma_wait_all0();
       __syncwarp();
     }
+    ST_TICK(6);
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(p.prof + 8 * part + i, (unsigned long long)tph[i]);
+    }
+#undef ST_TICK
     (void)bslot;
   }
 
@@ -2023,7 +2052,7 @@ int fused_block_launch(const FusedBlockArgs& a, cudaStream_t stream) {
   p.dbg = reinterpret_cast<uint16_t*>(a.dbg);
   static const int stagger = [] { const char* e = getenv("MCM_FB_STAGGER"); return e ? atoi(e) : 0; }();
   p.stagger = stagger;
-  p.prof = getenv("MCM_SF_PROF") != nullptr ? nullptr : g_fb_prof;
+  p.prof = (getenv("MCM_SF_PROF") != nullptr || getenv("MCM_ST_PROF") != nullptr) ? nullptr : g_fb_prof;
 
   // algorithmic flops of the two sub-blocks (AdaLN emb GEMM is not in this kernel)
   const double flops = 2.0 * (double)a.rows * ((double)D * D * 2 + (double)D * HD + 2.0 * D * F + (double)D * D);
@@ -2050,6 +2079,10 @@ int sa_tail_launch(const SaTailArgs& a, cudaStream_t stream) {
   std::memset(&p, 0, sizeof(p));
   p.T = T; p.Np = Np; p.nkb = (T + 63) / 64; p.nch = (T + 31) / 32; p.batch = a.batch; p.n_tiles = a.batch * 2;
   p.mod_ld = a.mod_ld; p.pn_w = a.pn_w; p.pn_b = a.pn_b; p.scale = a.scale; p.shift = a.shift; p.bo = a.bo;
+  p.prof = (g_fb_prof != nullptr && getenv("MCM_ST_PROF") != nullptr) ? g_fb_prof : nullptr;
+  p.h = a.h;
+  static const int pf = [] { const char* e = getenv("MCM_ST_PREFETCH"); return e ? atoi(e) : 1; }();
+  p.pf = pf;
   const int n_pairs = std::min(p.n_tiles, std::max(1, max_pairs / tc_sm_share()));
   const double flops = 2.0 * (double)a.batch * D * ((double)T * (T / 4) + (double)T * T);   // q ctx (per head) + out
   return launch_pairs(sa_tail_kernel, n_pairs, LK_GEMM, flops, tm, p, stream);
