@@ -320,6 +320,25 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     MCM_TRY(sa_ctx_launch(a, st));
   } else {
   MCM_TRY(softmax_seg_launch(w.f32B, B * T, D, D, D, opD_d, ff, st));
+  // Wide heads (T / H a multiple of 64, >= 128: m2d's T = 1024): only the H diagonal (T/H x T/H) blocks of ctx are non-zero,
+  // so both contractions run per (sample, head) -- a quarter of the tensor-core work of the full T x T product.  The
+  // off-diagonal part of ctxT_sa is zero from its allocation on (every writer of that buffer stores zeros there).
+  static const int perhead_env = [] { const char* e = getenv("MCM_SA_PERHEAD"); return e ? atoi(e) : 1; }();
+  const bool per_head = perhead_env && hdT % 64 == 0 && hdT >= 128;
+  if (per_head) {
+    // ctxT[b][h*hd + l][h*hd + dk] = sum_n v[b, h*hd + l, n] ks[b, h*hd + dk, n]
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opB_d; g.a_rows = hdT; g.a_k = D; g.a_batches = B * H; g.a_batched = 1;
+    g.b = opD_d; g.b_rows = hdT; g.b_k = D; g.b_batches = B * H; g.b_batched = 1;
+    g.fmt = ff; g.M = hdT; g.K = D; g.batches = B * H; g.inner = H;
+    g.out_rows_per_outer = hdT; g.out_batched = 1; g.out_col_inner = hdT;
+    g.nseg = 1;
+    g.seg[0] = seg_default(hdT, 0);
+    g.seg[0].op = view(w.ctxT_sa, Tp); g.seg[0].op_fmt = ff;
+    g.algo_flops = 2.0 * T * hdT * D * B;
+    MCM_TRY(gemm_tc_launch(g, st));
+  } else
   {  // ctx[b] = softmax(k)^T v, kept block-diagonal per head, needed transposed (ctxT[b][l][dk], the B operand of q ctx).
      // Computed AS the transpose -- A = v (rows l), B = softmax(k) (rows dk): D[l][dk] = sum_n v[l, n] ks[dk, n] -- so the
      // epilogue takes the plain TMA-store path instead of the transposing one (46 -> us per launch at B = 256).
@@ -347,6 +366,21 @@ int run_block(mcm_ctx* c, Scratch& w, const Block& k, int B, float* h, const flo
     a.mod_ld = mod_ld;
     MCM_TRY(sa_tail_launch(a, st));
   } else {
+  static const int perhead_env2 = [] { const char* e = getenv("MCM_SA_PERHEAD"); return e ? atoi(e) : 1; }();
+  if (perhead_env2 && hdT % 64 == 0 && hdT >= 128) {
+    // y^T[b][:, head] = softmax(q)[b][:, head] ctx[b][head]: K runs over the head's T/H features only
+    GemmProblem g;
+    std::memset(&g, 0, sizeof(g));
+    g.a = opC_t; g.a_rows = D; g.a_k = Tp; g.a_batches = B; g.a_k_inner = hdT;
+    g.b = view(w.ctxT_sa, Tp); g.b_rows = hdT; g.b_k = Tp; g.b_batches = B * H; g.b_batched = 1; g.b_k_inner = hdT;
+    g.fmt = ff; g.M = D; g.K = hdT; g.batches = B * H; g.inner = H;
+    g.out_rows_per_outer = D; g.out_col_inner = hdT;
+    g.nseg = 1;
+    g.seg[0] = seg_default(hdT, 0);
+    g.seg[0].out32 = w.f32A; g.seg[0].ld32 = T;
+    g.algo_flops = 2.0 * D * T * hdT * B;
+    MCM_TRY(gemm_tc_launch(g, st));
+  } else
   {  // y^T[b] = softmax(q) ctx                                 -> f32A [B*D, T]
     GemmProblem g;
     std::memset(&g, 0, sizeof(g));

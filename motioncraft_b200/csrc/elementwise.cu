@@ -199,22 +199,25 @@ softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols
 }
 
 // ------------------------------------------------------------------------------------------ ln_transpose
-// grid (D/32, B), block (32, 8).  tile[t][dx] (+1 pad) holds h[b, t, d0 + dx].
-template <int FMT>
-__global__ void __launch_bounds__(256)
+// grid (D/32, B), block (32, NW).  tile[t][dx] (+1 pad) holds h[b, t, d0 + dx].  NW = 8 warps for short sequences (several
+// blocks per SM); long ones (T > 256: the tile is up to 135 KB, ONE block per SM) take 32 warps so that the strided loads
+// of the column statistics still have ~32 x 8 requests in flight per SM.
+template <int FMT, int NW>
+__global__ void __launch_bounds__(32 * NW)
 ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __restrict__ w,
                     const float* __restrict__ b, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float tile[];            // T * 33
-  __shared__ float red[8][33];
+  __shared__ float red[NW][33];
   __shared__ float mean_s[32], rstd_s[32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int d0 = blockIdx.x * 32;
   const int bidx = blockIdx.y;
   const float* src = h + (size_t)bidx * T * D + d0 + tx;
   float s = 0.f;
-  for (int t = ty; t < T; t += 8) {
+#pragma unroll 8
+  for (int t = ty; t < T; t += NW) {
     const float val = src[(size_t)t * D];
     tile[t * 33 + tx] = val;
     s += val;
@@ -224,13 +227,13 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
   if (ty == 0) {
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i][tx];
+    for (int i = 0; i < NW; ++i) tot += red[i][tx];
     mean_s[tx] = tot / (float)T;
   }
   __syncthreads();
   const float mean = mean_s[tx];
   float ss = 0.f;
-  for (int t = ty; t < T; t += 8) {
+  for (int t = ty; t < T; t += NW) {
     const float dlt = tile[t * 33 + tx] - mean;
     ss += dlt * dlt;
   }
@@ -239,13 +242,13 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
   if (ty == 0) {
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i][tx];
+    for (int i = 0; i < NW; ++i) tot += red[i][tx];
     rstd_s[tx] = rsqrtf(tot / (float)T + 1e-5f);
   }
   __syncthreads();
   // write: warp ty handles columns dl = ty, ty+8, ...; lanes run along t (conflict-free smem reads, stride 33);
   // neighbouring lanes exchange values so every even lane emits one packed 32-bit store of two consecutive t
-  for (int dl = ty; dl < 32; dl += 8) {
+  for (int dl = ty; dl < 32; dl += NW) {
     const float mu = mean_s[dl], rs = rstd_s[dl];
     const size_t obase = ((size_t)bidx * D + d0 + dl) * out_ld;
     for (int t0 = 0; t0 < out_ld; t0 += 32) {
@@ -541,8 +544,10 @@ int randn_fill_launch(float* out, size_t n, unsigned long long seed, unsigned lo
 }
 
 int elementwise_init() {
-  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
-  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_BF16X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_F16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_BF16X2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_F16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_BF16X2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
   return 0;
 }
 unsigned long long elementwise_launch_count() { return g_ew_launches.load(); }
@@ -616,14 +621,20 @@ int softmax_seg_launch(const float* in, int rows, int ncols, int ld_in, int seg,
 int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, const float* b, OpPtr out, int out_fmt,
                         cudaStream_t stream) {
   MCM_CHECK(D % 32 == 0 && T <= 1024 && out.ld >= T && out.ld % 2 == 0, "ln_transpose: need D % 32 == 0, T <= 1024");
-  dim3 grid(D / 32, B), block(32, 8);
+  static const int wide_min = [] { const char* e = getenv("MCM_LNT_WIDE_MIN_T"); return e ? atoi(e) : 257; }();
+  const bool wide = T >= wide_min;
+  dim3 grid(D / 32, B), block(32, wide ? 32 : 8);
   uint16_t* hi = reinterpret_cast<uint16_t*>(out.hi);
   uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
+  const size_t smem = (size_t)T * 33 * sizeof(float);
   LaunchTimer lt(LK_ROW, stream);
-  if (out_fmt == OP_F16)
-    MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_F16>, dim3(grid), dim3(block), (size_t)((size_t)T * 33 * sizeof(float)), stream, h, T, D, w, b, hi, lo, out.ld));
-  else
-    MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_BF16X2>, dim3(grid), dim3(block), (size_t)((size_t)T * 33 * sizeof(float)), stream, h, T, D, w, b, hi, lo, out.ld));
+  if (out_fmt == OP_F16) {
+    if (wide) MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_F16, 32>, dim3(grid), dim3(block), smem, stream, h, T, D, w, b, hi, lo, out.ld));
+    else MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_F16, 8>, dim3(grid), dim3(block), smem, stream, h, T, D, w, b, hi, lo, out.ld));
+  } else {
+    if (wide) MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_BF16X2, 32>, dim3(grid), dim3(block), smem, stream, h, T, D, w, b, hi, lo, out.ld));
+    else MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_BF16X2, 8>, dim3(grid), dim3(block), smem, stream, h, T, D, w, b, hi, lo, out.ld));
+  }
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

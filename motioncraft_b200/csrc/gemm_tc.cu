@@ -33,7 +33,7 @@ constexpr int SMEM_TOTAL = 230400;         // dynamic shared memory request (+ ~
 
 struct KParams {
   int M, M_pad, K, batches, inner, a_k_inner, b_batched, out_col_inner, out_rows_per_outer,
-      trans_rows, head_dim;
+      trans_rows, head_dim, b_k_inner, a_batched, out_batched;
   int block_n, m_tiles, n_tiles, num_kb, stages, split, total_tiles;
   int stg_bytes;        // per-warp epilogue staging bytes (4096 or 8192)
   int pair;             // 1: cta_group::2 -- a CTA pair computes a 256 x block_n tile, each CTA holds half of B
@@ -131,7 +131,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         while (si + 1 < p.nseg && n_tile >= p.seg[si + 1].tile0) ++si;
         const int b_row = p.seg[si].w_row0 + (n_tile - p.seg[si].tile0) * p.block_n;
         const int a_k0 = inner * p.a_k_inner;
-        const int a_z = outer;
+        const int b_k0 = inner * p.b_k_inner;
+        const int a_z = p.a_batched ? batch : outer;
         const int b_z = p.b_batched ? batch : 0;
         if (p.prefetch && lane == 0) {
           // pull the NEXT work item's A rows (activations, usually DRAM-resident) into L2 while this one is loaded
@@ -142,9 +143,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nbatch = nt2 / p.m_supers;
             const int nouter = nbatch / p.inner;
             const int nk0 = (nbatch - nouter * p.inner) * p.a_k_inner;
+            const int nz = p.a_batched ? nbatch : nouter;
             for (int kb = 0; kb < p.num_kb; ++kb) {
-              tma_prefetch_3d(&tmA, nk0 + kb * BLOCK_K, nm * BLOCK_M, nouter);
-              if (p.split) tma_prefetch_3d(&tmAlo, nk0 + kb * BLOCK_K, nm * BLOCK_M, nouter);
+              tma_prefetch_3d(&tmA, nk0 + kb * BLOCK_K, nm * BLOCK_M, nz);
+              if (p.split) tma_prefetch_3d(&tmAlo, nk0 + kb * BLOCK_K, nm * BLOCK_M, nz);
             }
           }
         }
@@ -163,11 +165,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int b_rp = b_row + crank * (p.block_n / 2);
             tma_load_3d_2sm(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
             if (!p.split) {
-              tma_load_3d_2sm(&tmB, bar, sa + p.a_bytes, kb * BLOCK_K, b_rp, b_z);
+              tma_load_3d_2sm(&tmB, bar, sa + p.a_bytes, b_k0 + kb * BLOCK_K, b_rp, b_z);
             } else {
               tma_load_3d_2sm(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-              tma_load_3d_2sm(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_rp, b_z);
-              tma_load_3d_2sm(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_rp, b_z);
+              tma_load_3d_2sm(&tmB, bar, sa + 2 * p.a_bytes, b_k0 + kb * BLOCK_K, b_rp, b_z);
+              tma_load_3d_2sm(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, b_k0 + kb * BLOCK_K, b_rp, b_z);
             }
             }   // elect_one
             __syncwarp();
@@ -183,17 +185,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t b_off = (uint32_t)(crank * slice_rows) * (BLOCK_K * 2);
           if (!p.split) {
             tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            if (p.cs > 1) tma_load_3d_mc(&tmB, bar, sa + p.a_bytes + b_off, kb * BLOCK_K, b_r, b_z, cmask);
-            else tma_load_3d(&tmB, bar, sa + p.a_bytes, kb * BLOCK_K, b_row, b_z);
+            if (p.cs > 1) tma_load_3d_mc(&tmB, bar, sa + p.a_bytes + b_off, b_k0 + kb * BLOCK_K, b_r, b_z, cmask);
+            else tma_load_3d(&tmB, bar, sa + p.a_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
           } else {
             tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
             tma_load_3d(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
             if (p.cs > 1) {
-              tma_load_3d_mc(&tmB, bar, sa + 2 * p.a_bytes + b_off, kb * BLOCK_K, b_r, b_z, cmask);
-              tma_load_3d_mc(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes + b_off, kb * BLOCK_K, b_r, b_z, cmask);
+              tma_load_3d_mc(&tmB, bar, sa + 2 * p.a_bytes + b_off, b_k0 + kb * BLOCK_K, b_r, b_z, cmask);
+              tma_load_3d_mc(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes + b_off, b_k0 + kb * BLOCK_K, b_r, b_z, cmask);
             } else {
-              tma_load_3d(&tmB, bar, sa + 2 * p.a_bytes, kb * BLOCK_K, b_row, b_z);
-              tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, kb * BLOCK_K, b_row, b_z);
+              tma_load_3d(&tmB, bar, sa + 2 * p.a_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
+              tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
             }
           }
           }   // elect_one
@@ -317,8 +319,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t2 = tile / p.n_tiles;
       const int m_blk = (t2 % p.m_supers) * p.cs + crank;
       const int batch = t2 / p.m_supers;
-      const int outer = batch / p.inner;
-      const int inner = batch - outer * p.inner;
+      const int outer_i = batch / p.inner;
+      const int inner = batch - outer_i * p.inner;
+      const int outer = p.out_batched ? batch : outer_i;       // z coordinate / row block of the OUTPUT
       int si = 0;
       while (si + 1 < p.nseg && n_tile >= p.seg[si + 1].tile0) ++si;
       const EpiSeg& sg = p.seg[si];
@@ -776,7 +779,7 @@ int setup_epi_maps(const GemmProblem& q, const EpiSeg& sg, int M_pad, int* mode,
   *mode = 0;
   const bool transposed = (sg.flags & EPI_TRANSPOSED) != 0;
   const bool bcast = (sg.flags & EPI_ADDEND_BCAST) != 0;
-  const long long outer = q.batches / q.inner;
+  const long long outer = q.out_batched ? q.batches : q.batches / q.inner;
   if (sg.out32 == nullptr && sg.op.hi == nullptr) return 0;
   int md = TM_TMA;
   bool ok = true;
@@ -905,6 +908,10 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   p.batches = q.batches;
   p.inner = q.inner;
   p.a_k_inner = q.a_k_inner;
+  p.b_k_inner = q.b_k_inner;
+  p.a_batched = q.a_batched;
+  p.out_batched = q.out_batched;
+  MCM_CHECK(q.a_k_inner % 8 == 0 && q.b_k_inner % 8 == 0, "per-inner K offsets must be multiples of 8 elements (TMA start alignment)");
   p.b_batched = q.b_batched;
   p.out_col_inner = q.out_col_inner;
   p.out_rows_per_outer = q.out_rows_per_outer;

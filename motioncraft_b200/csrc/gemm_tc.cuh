@@ -47,6 +47,9 @@ struct GemmProblem {
   int batches;           // outer * inner
   int inner;             // e.g. heads; batch = outer * inner + inner_idx
   int a_k_inner;         // A k-offset per inner index (per-head slices of a shared A)
+  int b_k_inner;         // B k-offset per inner index (per-head diagonal blocks of a block-diagonal B)
+  int a_batched;         // 0: A batch index = outer; 1: A batch index = batch (A described per (outer, inner))
+  int out_batched;       // 1: output row = batch * out_rows_per_outer + r (columns still + inner * out_col_inner)
   int b_batched;         // 0: B shared by all batches (weights); 1: B batch index = batch
   int out_col_inner;     // output column offset per inner index
   int out_rows_per_outer;// output row = outer * out_rows_per_outer + r
