@@ -84,7 +84,7 @@ __device__ __forceinline__ void st2(uint16_t* hi, uint16_t* lo, size_t idx, floa
 
 // ------------------------------------------------------------------------------------------ ln_rows
 template <int MAXV, int FMT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MAXV >= 8 ? 4 : 1)
 ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const float* __restrict__ w,
                const float* __restrict__ b, const float* __restrict__ scale, const float* __restrict__ shift,
                int mod_ld, int rows_per_batch, int act_silu, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo,
@@ -260,6 +260,70 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
   }
 }
 
+// Long sequences (T > 512): 16 channels per block -> a 17-float pitch tile of <= 70 KB, so THREE 512-thread blocks share
+// an SM and one block's strided loads overlap another's write phase (with the 135 KB tile of the 32-channel version one
+// block owns the SM and its load / statistics / write phases run strictly one after the other).  A half-warp covers the 16
+// channels (64 contiguous bytes) of one frame; in the write phase a warp owns one channel and every lane two frames.
+template <int FMT>
+__global__ void __launch_bounds__(512)
+ln_transpose16_kernel(const float* __restrict__ h, int T, int D, const float* __restrict__ w,
+                      const float* __restrict__ b, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int CH = 16, NW = 16, P = CH + 1;
+  extern __shared__ float tile[];            // T * 17
+  __shared__ float red[NW][33];
+  __shared__ float mean_s[CH], rstd_s[CH];
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int cx = lane & (CH - 1), tsub = lane >> 4;
+  const int d0 = blockIdx.x * CH;
+  const int bidx = blockIdx.y;
+  const float* src = h + (size_t)bidx * T * D + d0 + cx;
+  float s = 0.f;
+#pragma unroll 8
+  for (int t = ty * 2 + tsub; t < T; t += NW * 2) {
+    const float val = src[(size_t)t * D];
+    tile[t * P + cx] = val;
+    s += val;
+  }
+  red[ty][lane] = s;
+  __syncthreads();
+  if (ty == 0 && lane < CH) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) tot += red[i][lane] + red[i][lane + CH];
+    mean_s[lane] = tot / (float)T;
+  }
+  __syncthreads();
+  const float mean = mean_s[cx];
+  float ss = 0.f;
+  for (int t = ty * 2 + tsub; t < T; t += NW * 2) {
+    const float dlt = tile[t * P + cx] - mean;
+    ss += dlt * dlt;
+  }
+  red[ty][lane] = ss;
+  __syncthreads();
+  if (ty == 0 && lane < CH) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) tot += red[i][lane] + red[i][lane + CH];
+    rstd_s[lane] = rsqrtf(tot / (float)T + 1e-5f);
+  }
+  __syncthreads();
+  {
+    const int dl = ty;
+    const float mu = mean_s[dl], rs = rstd_s[dl];
+    const size_t obase = ((size_t)bidx * D + d0 + dl) * out_ld;
+    for (int t0 = 0; t0 < out_ld; t0 += 64) {
+      const int t = t0 + 2 * lane;
+      if (t >= out_ld) break;
+      const float y0 = (t < T) ? fmaf((tile[t * P + dl] - mu) * rs, __ldg(w + t), __ldg(b + t)) : 0.f;
+      const float y1 = (t + 1 < T) ? fmaf((tile[(t + 1) * P + dl] - mu) * rs, __ldg(w + t + 1), __ldg(b + t + 1)) : 0.f;
+      st2<FMT>(ohi, olo, obase + t, y0, y1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ pack_op
 __global__ void __launch_bounds__(256)
 pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, int act_silu, OpPtr out, int out_fmt) {
@@ -275,6 +339,33 @@ pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, i
       if (act_silu) v = silu(v);
     }
     op_store1(out, out_fmt, i, v);
+  }
+}
+
+// 8 elements per thread (two 16-byte loads, one 16-byte store per half): cols, both pitches and the bases 8-element aligned
+__global__ void __launch_bounds__(256)
+pack_op8_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, int act_silu, OpPtr out, int out_fmt) {
+  pdl_trigger();
+  pdl_wait();
+  const int gpr = out.ld >> 3;
+  const size_t total = rows * (size_t)gpr;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / gpr;
+    const int c = (int)(i - r * gpr) * 8;
+    float v[8];
+    if (c < cols) {
+      const float4 a = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+      const float4 b = *reinterpret_cast<const float4*>(in + r * ld_in + c + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      if (act_silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu(v[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    op_store8(out, out_fmt, r * out.ld + c, v);
   }
 }
 
@@ -548,6 +639,8 @@ int elementwise_init() {
   MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_BF16X2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
   MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_F16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
   MCM_CUDA(cudaFuncSetAttribute(ln_transpose_kernel<OP_BF16X2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose16_kernel<OP_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 17 * 4));
+  MCM_CUDA(cudaFuncSetAttribute(ln_transpose16_kernel<OP_BF16X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 17 * 4));
   return 0;
 }
 unsigned long long elementwise_launch_count() { return g_ew_launches.load(); }
@@ -622,13 +715,19 @@ int ln_transpose_launch(const float* h, int B, int T, int D, const float* w, con
                         cudaStream_t stream) {
   MCM_CHECK(D % 32 == 0 && T <= 1024 && out.ld >= T && out.ld % 2 == 0, "ln_transpose: need D % 32 == 0, T <= 1024");
   static const int wide_min = [] { const char* e = getenv("MCM_LNT_WIDE_MIN_T"); return e ? atoi(e) : 257; }();
+  static const int narrow_min = [] { const char* e = getenv("MCM_LNT16_MIN_T"); return e ? atoi(e) : 513; }();
   const bool wide = T >= wide_min;
   dim3 grid(D / 32, B), block(32, wide ? 32 : 8);
   uint16_t* hi = reinterpret_cast<uint16_t*>(out.hi);
   uint16_t* lo = reinterpret_cast<uint16_t*>(out.lo);
   const size_t smem = (size_t)T * 33 * sizeof(float);
   LaunchTimer lt(LK_ROW, stream);
-  if (out_fmt == OP_F16) {
+  if (T >= narrow_min) {
+    const dim3 g16(D / 16, B), b16(32, 16);
+    const size_t sm16 = (size_t)T * 17 * sizeof(float);
+    if (out_fmt == OP_F16) MCM_CUDA(launch_pdl(ln_transpose16_kernel<OP_F16>, dim3(g16), dim3(b16), sm16, stream, h, T, D, w, b, hi, lo, out.ld));
+    else MCM_CUDA(launch_pdl(ln_transpose16_kernel<OP_BF16X2>, dim3(g16), dim3(b16), sm16, stream, h, T, D, w, b, hi, lo, out.ld));
+  } else if (out_fmt == OP_F16) {
     if (wide) MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_F16, 32>, dim3(grid), dim3(block), smem, stream, h, T, D, w, b, hi, lo, out.ld));
     else MCM_CUDA(launch_pdl(ln_transpose_kernel<OP_F16, 8>, dim3(grid), dim3(block), smem, stream, h, T, D, w, b, hi, lo, out.ld));
   } else {
@@ -645,6 +744,11 @@ int pack_op_launch(const float* in, int rows, int cols, int ld_in, bool act_silu
   MCM_CHECK(out.ld >= cols, "pack_op: output pitch too small");
   const size_t total = (size_t)rows * out.ld;
   LaunchTimer lt(LK_ROW, stream);
+  const bool vec8 = cols % 8 == 0 && ld_in % 4 == 0 && out.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out.hi) & 15) == 0 && (out.lo == nullptr || (reinterpret_cast<uintptr_t>(out.lo) & 15) == 0);
+  if (vec8)
+    MCM_CUDA(launch_pdl(pack_op8_kernel, dim3(grid_for(total / 8, 256)), dim3(256), (size_t)0, stream, in, (size_t)rows, cols, ld_in, act_silu ? 1 : 0, out, out_fmt));
+  else
   MCM_CUDA(launch_pdl(pack_op_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)0, stream, in, (size_t)rows, cols, ld_in, act_silu ? 1 : 0, out, out_fmt));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);

@@ -397,3 +397,45 @@ def test_ddpm_1000_steps_shipped_default_vs_oracle():
     torch.manual_seed(11)
     b = d.p_sample_loop(net, (B, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw)
     assert torch.isfinite(a).all() and torch.equal(a, b) and not torch.equal(a, x0)
+
+
+_ROW_KERNEL_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, sys.argv[1])
+from motioncraft_b200 import modules, synth
+from motioncraft_b200.engine import DenoiserEngine
+outs = {}
+for T, B in ((196, 3), (300, 3), (1024, 2)):
+    sd = {k: v for k, v in synth.synth_state_dict(modules.state_shapes(seq_len=T, num_layers=1)).items() if ".ffn_channel." not in k}
+    eng = DenoiserEngine(sd, seq_len=T, max_batch=B, num_layers=1)
+    eng.set_option("fused", 0); eng.set_option("fused_sa", 0); eng.set_option("dual", 0); eng.set_option("graph", 0)
+    g = torch.Generator().manual_seed(T)
+    h = torch.randn(B, T, 512, generator=g).cuda(); emb = torch.randn(B, 2048, generator=g).cuda()
+    eng.prepare_conditions(torch.randn(B, 77, 256, generator=g).cuda(), torch.randn(B, 2048, generator=g).cuda())
+    outs[str(T)] = eng.block_forward(0, 0, h, emb).cpu()
+    eng.close()
+torch.save(outs, sys.argv[2])
+"""
+
+
+def _run_row_kernel_script(tmp_path, tag, **env):
+    script = tmp_path / "rows.py"
+    script.write_text(_ROW_KERNEL_SCRIPT)
+    out = tmp_path / f"rows_{tag}.pt"
+    e = dict(os.environ)
+    e.update({k: str(v) for k, v in env.items()})
+    r = subprocess.run([sys.executable, str(script), ROOT, str(out)], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return torch.load(out)
+
+
+def test_per_head_channel_attention_contractions_match_the_masked_product(tmp_path):
+    """The shape-dependent kernel choice must not change results: the per-head channel-attention contractions (wide heads,
+    T = 1024) match the masked full product (same products, the fp32 accumulation only skips exact zeros); narrow heads
+    (T = 196, 300) do not take that path at all."""
+    base = _run_row_kernel_script(tmp_path, "base")
+    full = _run_row_kernel_script(tmp_path, "full", MCM_SA_PERHEAD=0)
+    for k in base:
+        assert torch.isfinite(base[k]).all()
+    assert torch.equal(full["196"], base["196"]) and torch.equal(full["300"], base["300"])
+    assert C.rel_l2(base["1024"], full["1024"]) < 1e-6
