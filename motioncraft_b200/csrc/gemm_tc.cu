@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace mcm {
 
@@ -44,6 +46,8 @@ struct KParams {
   unsigned long long* dbg;   // MCM_DEBUG_EPI=3: per-phase clock totals of the epilogue warps
   int prefetch;         // producer issues L2 prefetches for the next work item's A tile
   int debug;            // MCM_DEBUG_EPI: 1 = skip staging + stores, 2 = also skip the TMEM read (timing experiments only)
+  unsigned long long* trace;   // MCM_GEMM_TRACE=<file>: stamps of CTA 0 of this launch (8 x globaltimer ns, 8 x clock64, then
+                               // clock64 per k-block: [16, 32) MMA warp after its full-barrier wait, [32, 48) producer after issue)
   int tma_mode[3];      // per segment: 0 = generic epilogue, else bit0 TMA epilogue, bit1 residual via TMA reduce-add,
                         // bit2 addend TMA-loaded, bit3 addend broadcast over batches
 };
@@ -72,6 +76,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+#define MCM_STAMP(i)                                                                                     \
+  do {                                                                                                   \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) {                                            \
+      unsigned long long _g;                                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g));                                             \
+      p.trace[i] = _g;                                                                                   \
+      p.trace[8 + (i)] = (unsigned long long)clock64();                                                  \
+    }                                                                                                    \
+  } while (0)
+  if (warp == 0) MCM_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -104,6 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.cs > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
   pdl_wait();                                         // prologue done; from here on global memory is touched
+  if (warp == 0) MCM_STAMP(1);
   const uint32_t tmem_base = tmem_slot;
   const int crank = p.cs > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / p.cs;
@@ -198,6 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
             }
           }
+          if (p.trace != nullptr && blockIdx.x == 0 && tile == cluster_id && kb < 16) p.trace[32 + kb] = (unsigned long long)clock64();
           }   // elect_one
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -228,6 +244,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           long long tf0 = (p.debug == 3) ? clock64() : 0;
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           if (p.debug == 3) mm_wfull += clock64() - tf0;
+          if (it == 0 && kb == 0) MCM_STAMP(2);
+          if (p.trace != nullptr && blockIdx.x == 0 && it == 0 && kb < 16 && lane == 0) p.trace[16 + kb] = (unsigned long long)clock64();
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const int kleft = p.K - kb * BLOCK_K;
@@ -287,6 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
+      MCM_STAMP(3);
       if (p.debug == 3 && p.dbg != nullptr && lane == 0) {
         atomicAdd(p.dbg + 11, (unsigned long long)mm_wacc);
         atomicAdd(p.dbg + 12, (unsigned long long)mm_wfull);
@@ -346,6 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
+      if (ew == 0 && it == 0) MCM_STAMP(4);
       MCM_TICK(0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
 
@@ -642,8 +662,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(smem_u32(&tempty_bar[acc]));
       }
     }
+    if (ew == 0) MCM_STAMP(5);
     if (lane == 0) tma_wait_all0();   // bulk stores must have fully completed before the CTA exits
     __syncwarp();
+    if (ew == 0) MCM_STAMP(6);
     if (prof && lane == 0 && p.dbg != nullptr) {
       for (int i = 0; i < 6; ++i) atomicAdd(p.dbg + i, (unsigned long long)tph[i]);
     }
@@ -657,7 +679,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
+    MCM_STAMP(7);
   }
+#undef MCM_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -674,6 +698,28 @@ int g_init_status = 0;
 std::atomic<unsigned long long> g_launches{0};
 int g_debug_epi = 0;
 unsigned long long* g_dbg = nullptr;
+// MCM_GEMM_TRACE=<file>: per-launch time stamps of CTA 0 (development aid for the launch-bound small-batch regime); the file is
+// written at process exit, one line per launch slot (a CUDA-graph replay overwrites the slots of its nodes).
+constexpr int TRACE_SLOTS = 4096, TRACE_WORDS = 64;
+unsigned long long* g_trace = nullptr;
+std::atomic<unsigned long long> g_trace_n{0};
+std::vector<std::string>* g_trace_meta = nullptr;
+const char* g_trace_path = nullptr;
+void trace_dump() {
+  if (g_trace == nullptr || g_trace_path == nullptr) return;
+  if (cudaDeviceSynchronize() != cudaSuccess) return;
+  std::vector<unsigned long long> h((size_t)TRACE_SLOTS * TRACE_WORDS);
+  if (cudaMemcpy(h.data(), g_trace, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  FILE* f = fopen(g_trace_path, "w");
+  if (!f) return;
+  const size_t n = std::min<size_t>(g_trace_meta->size(), TRACE_SLOTS);
+  for (size_t i = 0; i < n; ++i) {
+    fprintf(f, "%zu %s |", i, (*g_trace_meta)[i].c_str());
+    for (int j = 0; j < TRACE_WORDS; ++j) fprintf(f, " %llu", h[i * TRACE_WORDS + j]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+}
 int g_pair = 0;                     // MCM_PAIR=1 enables cta_group::2 pair tiles (256 x block_n per CTA pair; validated,
                                     // -5..10 % mainloop time but a slower epilogue overlap: net neutral this round)
 int g_prefetch = 0;                 // MCM_PREFETCH=1: producer issues L2 prefetches one work item ahead (measured: no gain)
@@ -922,6 +968,16 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   p.debug = g_debug_epi;
   p.prefetch = g_prefetch;
   p.dbg = g_dbg;
+  p.trace = nullptr;
+  static const bool trace_on = [] {
+    g_trace_path = getenv("MCM_GEMM_TRACE");
+    if (g_trace_path == nullptr) return false;
+    if (cudaMalloc(&g_trace, (size_t)TRACE_SLOTS * TRACE_WORDS * 8) != cudaSuccess) return false;
+    cudaMemset(g_trace, 0, (size_t)TRACE_SLOTS * TRACE_WORDS * 8);
+    g_trace_meta = new std::vector<std::string>();
+    atexit(trace_dump);
+    return true;
+  }();
 
   int nmax = 0;
   for (int s = 0; s < q.nseg; ++s) {
@@ -1018,6 +1074,16 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   }
   const int n_clusters = std::min(p.total_tiles, std::max(1, (p.pair ? g_max_pairs : g_max_clusters[cs]) / g_sm_share));
   const int grid = n_clusters * cs;
+  if (trace_on) {
+    const unsigned long long ti = g_trace_n.fetch_add(1);
+    if (ti < (unsigned long long)TRACE_SLOTS) {
+      p.trace = g_trace + ti * TRACE_WORDS;
+      char buf[160];
+      snprintf(buf, sizeof(buf), "M=%d K=%d batches=%d nseg=%d n0=%d bn=%d tiles=%d grid=%d cs=%d stages=%d", q.M, q.K, q.batches,
+               q.nseg, q.seg[0].n, p.block_n, p.total_tiles, grid, p.cs, p.stages);
+      g_trace_meta->push_back(buf);
+    }
+  }
   double flops = q.algo_flops;
   if (flops <= 0.0) {
     long long ncols = 0;

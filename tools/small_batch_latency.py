@@ -11,6 +11,9 @@ d = build_diffusion(dict(beta_scheduler="linear", diffusion_steps=1000, model_me
 st = SamplerTables(d._tables(), d.timestep_map, "ddim", 0.0)
 for B in (1, 8, 32):
     eng = DenoiserEngine(sd, seq_len=T, max_batch=B)
+    for kv in sys.argv[1:]:                       # e.g. fused_sa_min_rows=0
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     x = torch.randn(B, T, 322).cuda()
     eng.prepare_conditions(torch.randn(B, 77, 256).cuda(), torch.randn(B, 2048).cuda())
     for _ in range(3):
