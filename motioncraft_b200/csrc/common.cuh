@@ -146,6 +146,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// Non-blocking probe of a barrier phase (1 = the phase with this parity has completed).  Issued one ring stage AHEAD of its use,
+// the ~300-cycle round trip of the barrier unit overlaps the instructions in between instead of heading every k-block.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// two probes in flight at once (their round trips overlap)
+__device__ __forceinline__ void mbar_test2(uint32_t bar0, uint32_t par0, uint32_t bar1, uint32_t par1, uint32_t& d0, uint32_t& d1) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "selp.b32 %1, 1, 0, q;\n\t}"
+      : "=r"(d0), "=r"(d1)
+      : "r"(bar0), "r"(par0), "r"(bar1), "r"(par1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
 }

@@ -86,6 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }                                                                                                    \
   } while (0)
   if (warp == 0) MCM_STAMP(0);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -165,58 +166,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          long long tp0 = 0;
-          if (p.debug == 3) tp0 = clock64();
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          if (p.debug == 3) { const long long n = clock64(); pr_wait += n - tp0; pr_kb += 1; }
-          const uint32_t bar = smem_u32(&full_bar[stage]);
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          if constexpr (PAIR) {
-            // CTA pair: each CTA loads its own A rows and its half of the B rows into its OWN smem; all bytes are
-            // accounted on the LEADER's barrier, which its MMA thread waits on.
-            if (elect_one()) {
-            if (crank == 0) mbar_expect_tx(bar, 2u * tx);
-            const int b_rp = b_row + crank * (p.block_n / 2);
-            tma_load_3d_2sm(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            if (!p.split) {
-              tma_load_3d_2sm(&tmB, bar, sa + p.a_bytes, b_k0 + kb * BLOCK_K, b_rp, b_z);
-            } else {
-              tma_load_3d_2sm(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-              tma_load_3d_2sm(&tmB, bar, sa + 2 * p.a_bytes, b_k0 + kb * BLOCK_K, b_rp, b_z);
-              tma_load_3d_2sm(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, b_k0 + kb * BLOCK_K, b_rp, b_z);
-            }
-            }   // elect_one
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            continue;
-          }
+        // Everything that does not depend on kb is computed here: the k loop is ONE warp issuing dependent scalar instructions
+        // (measured with MCM_GEMM_TRACE: 710 cycles per k-block with the address / mode arithmetic inside the loop).
+        const int num_kb = p.num_kb, stages = p.stages;
+        const uint32_t stage_bytes = p.stage_bytes;
+        const int a_row = m_blk * BLOCK_M;
+        const bool b_mc = p.cs > 1;
+        const int b_row_l = PAIR ? b_row + crank * (p.block_n / 2) : (b_mc ? b_row + crank * (p.block_n / p.cs) : b_row);
+        const uint32_t b_dst = (p.split ? 2u * p.a_bytes : p.a_bytes) +
+                               ((!PAIR && b_mc) ? (uint32_t)(crank * (p.block_n / p.cs)) * (BLOCK_K * 2) : 0u);
+        const uint32_t alo_dst = p.a_bytes, blo_dst = b_dst + p.b_bytes;
+        const bool split = p.split != 0;
+        const bool dbg3 = p.debug == 3;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && tile == cluster_id;
+        auto load_kb = [&](int st, int kb) {
+          const uint32_t bar = full0 + (uint32_t)st * 8u;
+          const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
+          const int ka = a_k0 + kb * BLOCK_K, kbk = b_k0 + kb * BLOCK_K;
           if (elect_one()) {
-          mbar_expect_tx(bar, tx);
-          // A: this CTA's own 128 rows.  B: this CTA fetches rows [crank, crank+1) * block_n / cs of the tile and
-          // multicasts them to every CTA of the cluster (each CTA's barrier counts the whole tile's bytes).
-          const int slice_rows = p.block_n / p.cs;
-          const int b_r = b_row + crank * slice_rows;
-          const uint32_t b_off = (uint32_t)(crank * slice_rows) * (BLOCK_K * 2);
-          if (!p.split) {
-            tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            if (p.cs > 1) tma_load_3d_mc(&tmB, bar, sa + p.a_bytes + b_off, b_k0 + kb * BLOCK_K, b_r, b_z, cmask);
-            else tma_load_3d(&tmB, bar, sa + p.a_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
-          } else {
-            tma_load_3d(&tmA, bar, sa, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            tma_load_3d(&tmAlo, bar, sa + p.a_bytes, a_k0 + kb * BLOCK_K, m_blk * BLOCK_M, a_z);
-            if (p.cs > 1) {
-              tma_load_3d_mc(&tmB, bar, sa + 2 * p.a_bytes + b_off, b_k0 + kb * BLOCK_K, b_r, b_z, cmask);
-              tma_load_3d_mc(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes + b_off, b_k0 + kb * BLOCK_K, b_r, b_z, cmask);
+            if constexpr (PAIR) {
+              // CTA pair: each CTA loads its own A rows and its half of the B rows into its OWN smem; all bytes are
+              // accounted on the LEADER's barrier, which its MMA thread waits on.
+              if (crank == 0) mbar_expect_tx(bar, 2u * tx);
+              tma_load_3d_2sm(&tmA, bar, sa, ka, a_row, a_z);
+              if (split) tma_load_3d_2sm(&tmAlo, bar, sa + alo_dst, ka, a_row, a_z);
+              tma_load_3d_2sm(&tmB, bar, sa + b_dst, kbk, b_row_l, b_z);
+              if (split) tma_load_3d_2sm(&tmBlo, bar, sa + blo_dst, kbk, b_row_l, b_z);
             } else {
-              tma_load_3d(&tmB, bar, sa + 2 * p.a_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
-              tma_load_3d(&tmBlo, bar, sa + 2 * p.a_bytes + p.b_bytes, b_k0 + kb * BLOCK_K, b_row, b_z);
+              // A: this CTA's own 128 rows.  B: this CTA fetches rows [crank, crank+1) * block_n / cs of the tile and
+              // multicasts them to every CTA of the cluster (each CTA's barrier counts the whole tile's bytes).
+              mbar_expect_tx(bar, tx);
+              tma_load_3d(&tmA, bar, sa, ka, a_row, a_z);
+              if (split) tma_load_3d(&tmAlo, bar, sa + alo_dst, ka, a_row, a_z);
+              if (b_mc) {
+                tma_load_3d_mc(&tmB, bar, sa + b_dst, kbk, b_row_l, b_z, cmask);
+                if (split) tma_load_3d_mc(&tmBlo, bar, sa + blo_dst, kbk, b_row_l, b_z, cmask);
+              } else {
+                tma_load_3d(&tmB, bar, sa + b_dst, kbk, b_row_l, b_z);
+                if (split) tma_load_3d(&tmBlo, bar, sa + blo_dst, kbk, b_row_l, b_z);
+              }
+              if (tr && kb < 16) p.trace[32 + kb] = (unsigned long long)clock64();
             }
-          }
-          if (p.trace != nullptr && blockIdx.x == 0 && tile == cluster_id && kb < 16) p.trace[32 + kb] = (unsigned long long)clock64();
           }   // elect_one
+        };
+        // two k-blocks per trip, their empty-barrier probes in flight together (see the MMA warp; four per trip measured slower)
+        for (int kb = 0; kb < num_kb; kb += 2) {
+          long long tp0 = 0;
+          if (dbg3) tp0 = clock64();
+          const bool two = kb + 1 < num_kb;
+          const int s0 = stage;
+          const uint32_t ph0 = phase;
+          const int s1 = (s0 + 1 == stages) ? 0 : s0 + 1;
+          const uint32_t ph1 = (s0 + 1 == stages) ? ph0 ^ 1u : ph0;
+          uint32_t r0, r1;
+          mbar_test2(empty0 + (uint32_t)s0 * 8u, ph0 ^ 1u, empty0 + (uint32_t)s1 * 8u, ph1 ^ 1u, r0, r1);
+          if (stages < 2) r1 = 0u;
+          if (!r0) mbar_wait(empty0 + (uint32_t)s0 * 8u, ph0 ^ 1u);
+          if (dbg3) { const long long n = clock64(); pr_wait += n - tp0; pr_kb += two ? 2 : 1; }
+          load_kb(s0, kb);
+          if (two) {
+            if (!r1) {
+              const long long tp1 = dbg3 ? clock64() : 0;
+              mbar_wait(empty0 + (uint32_t)s1 * 8u, ph1 ^ 1u);
+              if (dbg3) pr_wait += clock64() - tp1;
+            }
+            load_kb(s1, kb + 1);
+          }
           __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          stage = two ? ((s1 + 1 == stages) ? 0 : s1 + 1) : s1;
+          phase = two ? ((s1 + 1 == stages) ? ph1 ^ 1u : ph1) : ph1;
         }
       }
       if (p.debug == 3 && p.dbg != nullptr && lane == 0) {
@@ -240,64 +258,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.debug == 3) mm_wacc += clock64() - tm0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(acc * ACC_STRIDE);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          long long tf0 = (p.debug == 3) ? clock64() : 0;
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          if (p.debug == 3) mm_wfull += clock64() - tf0;
-          if (it == 0 && kb == 0) MCM_STAMP(2);
-          if (p.trace != nullptr && blockIdx.x == 0 && it == 0 && kb < 16 && lane == 0) p.trace[16 + kb] = (unsigned long long)clock64();
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const int kleft = p.K - kb * BLOCK_K;
+        // Descriptors by arithmetic: the low word of a swizzle-128B descriptor is (address >> 4) | const and shared-memory
+        // addresses stay below 2^18, so the descriptor of (stage, k) is the stage-0 descriptor plus (offset >> 4).  The loop is one
+        // warp of dependent scalar instructions: per k-block it must stay well under the tensor time of the four MMAs.
+        const int num_kb = p.num_kb, stages = p.stages;
+        const uint32_t idesc = p.idesc;
+        const uint64_t dA0 = make_smem_desc_sw128(smem_base);
+        const uint64_t st_step = (uint64_t)(p.stage_bytes >> 4);
+        const uint64_t offAlo = (uint64_t)(p.a_bytes >> 4);
+        const uint64_t offB = (uint64_t)((p.split ? 2u * p.a_bytes : p.a_bytes) >> 4);
+        const uint64_t offBlo = offB + (uint64_t)(p.b_bytes >> 4);
+        const bool split = p.split != 0, dbg3 = p.debug == 3, mc = p.cs > 1;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && it == 0;
+        // One k-block = the MMAs of ring stage `st` + the commit that hands the stage back to the producer.
+        auto issue_kb = [&](int st, int kb, int kleft) {
           const int nk = kleft >= BLOCK_K ? BLOCK_K / UMMA_K : (kleft + UMMA_K - 1) / UMMA_K;
-          if constexpr (PAIR) {
-            if (elect_one()) {
-            if (!p.split) {
-              const uint32_t sb = sa + p.a_bytes;
-              for (int k = 0; k < nk; ++k)
-                umma_f16_2sm(taddr, make_smem_desc_sw128(sa + k * UMMA_K * 2), make_smem_desc_sw128(sb + k * UMMA_K * 2),
-                             p.idesc, (uint32_t)((kb | k) != 0));
+          const uint64_t dA = dA0 + (uint64_t)st * st_step;
+          if (elect_one()) {
+            if (!split) {
+              const uint64_t dB = dA + offB;
+              if (nk == BLOCK_K / UMMA_K) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  if constexpr (PAIR) umma_f16_2sm(taddr, dA + 2 * k, dB + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                  else umma_f16(taddr, dA + 2 * k, dB + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                }
+              } else {
+                for (int k = 0; k < nk; ++k) {
+                  if constexpr (PAIR) umma_f16_2sm(taddr, dA + 2 * k, dB + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                  else umma_f16(taddr, dA + 2 * k, dB + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                }
+              }
             } else {
-              const uint32_t sal = sa + p.a_bytes, sb = sa + 2 * p.a_bytes, sbl = sb + p.b_bytes;
               for (int k = 0; k < nk; ++k) {
-                const uint32_t o = k * UMMA_K * 2;
-                const uint64_t ah = make_smem_desc_sw128(sa + o), al = make_smem_desc_sw128(sal + o);
-                const uint64_t bh = make_smem_desc_sw128(sb + o), bl = make_smem_desc_sw128(sbl + o);
-                umma_f16_2sm(taddr, al, bh, p.idesc, (uint32_t)((kb | k) != 0));
-                umma_f16_2sm(taddr, ah, bl, p.idesc, 1u);
-                umma_f16_2sm(taddr, ah, bh, p.idesc, 1u);
+                const uint64_t ah = dA + 2 * k, al = ah + offAlo, bh = ah + offB, bl = ah + offBlo;
+                if constexpr (PAIR) {
+                  umma_f16_2sm(taddr, al, bh, idesc, (uint32_t)((kb | k) != 0));   // small terms first
+                  umma_f16_2sm(taddr, ah, bl, idesc, 1u);
+                  umma_f16_2sm(taddr, ah, bh, idesc, 1u);
+                } else {
+                  umma_f16(taddr, al, bh, idesc, (uint32_t)((kb | k) != 0));
+                  umma_f16(taddr, ah, bl, idesc, 1u);
+                  umma_f16(taddr, ah, bh, idesc, 1u);
+                }
               }
             }
-            umma_commit_2sm(smem_u32(&empty_bar[stage]), (uint16_t)3);   // frees the stage in BOTH CTAs
-            }   // elect_one
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            continue;
-          }
-          if (elect_one()) {
-          if (!p.split) {
-            const uint32_t sb = sa + p.a_bytes;
-            for (int k = 0; k < nk; ++k) {
-              umma_f16(taddr, make_smem_desc_sw128(sa + k * UMMA_K * 2), make_smem_desc_sw128(sb + k * UMMA_K * 2),
-                       p.idesc, (uint32_t)((kb | k) != 0));
-            }
-          } else {
-            const uint32_t sal = sa + p.a_bytes, sb = sa + 2 * p.a_bytes, sbl = sb + p.b_bytes;
-            for (int k = 0; k < nk; ++k) {
-              const uint32_t o = k * UMMA_K * 2;
-              const uint64_t ah = make_smem_desc_sw128(sa + o), al = make_smem_desc_sw128(sal + o);
-              const uint64_t bh = make_smem_desc_sw128(sb + o), bl = make_smem_desc_sw128(sbl + o);
-              umma_f16(taddr, al, bh, p.idesc, (uint32_t)((kb | k) != 0));   // small terms first
-              umma_f16(taddr, ah, bl, p.idesc, 1u);
-              umma_f16(taddr, ah, bh, p.idesc, 1u);
-            }
-          }
-          // the stage is rewritten by multicasts from every CTA of the cluster: release it on all of them
-          if (p.cs > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), cmask);
-          else umma_commit(smem_u32(&empty_bar[stage]));
+            // release the stage: pair mode in BOTH CTAs; multicast mode on every CTA of the cluster (they all write into it)
+            if constexpr (PAIR) umma_commit_2sm(empty0 + (uint32_t)st * 8u, (uint16_t)3);
+            else if (mc) umma_commit_mc(empty0 + (uint32_t)st * 8u, cmask);
+            else umma_commit(empty0 + (uint32_t)st * 8u);
           }   // elect_one
+        };
+        // Two k-blocks per trip: the barrier probes of both stages are in flight together (a probe's round trip through the
+        // barrier unit is ~230 cycles even when the phase completed long ago; per k-block the serial chain probe -> fence ->
+        // 4 MMA issues -> commit -> reconverge measured 700+ cycles against 512 cycles of tensor time at N = 256).
+        int kleft = p.K;
+        for (int kb = 0; kb < num_kb; kb += 2, kleft -= 2 * BLOCK_K) {
+          long long tf0 = dbg3 ? clock64() : 0;
+          const bool two = kb + 1 < num_kb;
+          const int s0 = stage;
+          const uint32_t ph0 = phase;
+          const int s1 = (s0 + 1 == stages) ? 0 : s0 + 1;
+          const uint32_t ph1 = (s0 + 1 == stages) ? ph0 ^ 1u : ph0;
+          uint32_t r0, r1;
+          mbar_test2(full0 + (uint32_t)s0 * 8u, ph0, full0 + (uint32_t)s1 * 8u, ph1, r0, r1);
+          if (stages < 2) r1 = 0u;            // a one-stage ring wraps inside the trip: that probe's parity would be ambiguous
+          if (!r0) mbar_wait(full0 + (uint32_t)s0 * 8u, ph0);
+          if (dbg3) mm_wfull += clock64() - tf0;
+          if (it == 0 && kb == 0) MCM_STAMP(2);
+          if (tr && kb < 16 && lane == 0) p.trace[16 + kb] = (unsigned long long)clock64();
+          tc_fence_after();
+          issue_kb(s0, kb, kleft);
+          if (two) {
+            if (!r1) {
+              const long long tf1 = dbg3 ? clock64() : 0;
+              mbar_wait(full0 + (uint32_t)s1 * 8u, ph1);
+              if (dbg3) mm_wfull += clock64() - tf1;
+              tc_fence_after();
+            }
+            if (tr && kb + 1 < 16 && lane == 0) p.trace[16 + kb + 1] = (unsigned long long)clock64();
+            issue_kb(s1, kb + 1, kleft - BLOCK_K);
+          }
           __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          stage = two ? ((s1 + 1 == stages) ? 0 : s1 + 1) : s1;
+          phase = two ? ((s1 + 1 == stages) ? ph1 ^ 1u : ph1) : ph1;
         }
         if (elect_one()) {
           if constexpr (PAIR) umma_commit_2sm(smem_u32(&tfull_bar[acc]), (uint16_t)3);   // both CTAs' epilogues

@@ -12,12 +12,12 @@ def read(path):
     for ln in open(path):
         meta, st = ln.split("|")
         v = [int(x) for x in st.split()]
-        rows.append((meta.strip(), v[:8], v[8:16], v[16:32], v[32:48]))
+        rows.append((meta.strip(), v[:8], v[8:16], v[16:32], v[32:48], v[48:64]))
     rows = [r for r in rows if r[1][0] and r[1][7]]
     rows.sort(key=lambda r: r[1][0])
     print("per launch (ns, globaltimer): start->pdl_wait_done | ->first slab | ->mma issued | ->acc ready | ->stores issued | ->stores done | ->exit   || gap to next start, next pdl_wait_done")
     tot = {}
-    for i, (meta, g, c, mk, pk) in enumerate(rows):
+    for i, (meta, g, c, mk, pk, fine) in enumerate(rows):
         d = [g[1] - g[0], g[2] - g[1], g[3] - g[2], g[4] - g[3], g[5] - g[4], g[6] - g[5], g[7] - g[6]]
         nxt = rows[i + 1][1] if i + 1 < len(rows) else None
         gap = (nxt[0] - g[7], nxt[1] - g[7]) if nxt else (0, 0)
@@ -26,6 +26,9 @@ def read(path):
             base = c[1]
             print("      producer issue (clk after pdl_wait): " + " ".join(str(x - base) for x in pk if x))
             print("      mma full-wait done               : " + " ".join(str(x - base) for x in mk if x))
+            if fine[0]:
+                print("      mma warp, kb = 2: wait %d | fence %d | 4 x MMA issue %d | commit %d | syncwarp %d" % (
+                    mk[2] - fine[0], fine[1] - mk[2], fine[2] - fine[1], fine[3] - fine[2], fine[4] - fine[3]))
         for k, x in zip(("wait_pdl", "first_slab", "mma", "acc", "epi", "drain", "exit"), d):
             tot[k] = tot.get(k, 0) + x
         tot["gap_exit_to_next_ready"] = tot.get("gap_exit_to_next_ready", 0) + gap[1]
