@@ -635,6 +635,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
       int slot = 0;
       uint32_t ph = 0;
       uint32_t te_par[2] = {0u, 0u};
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       // instruction descriptors: fp32 accumulate, fp16 A/B, K-major, N >> 3, M = 256 >> 4
       const uint32_t idesc256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -652,22 +653,45 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
         if (elect_one()) umma_commit_2sm(smem_u32(&tfull_bar[hh]), (uint16_t)3);
         __syncwarp();
       };
-      // one ring slab as the B operand against the resident A slab `a_addr`
-      auto step = [&](uint32_t a_addr, uint32_t dcol, uint32_t idesc, bool fresh) {
+      // TWO consecutive ring slabs per trip.  The serial chain of one slab -- barrier probe (~295 cycles through the barrier unit
+      // even when the phase completed long ago), fence, four MMA issues, commit, reconvergence -- measured ~700 cycles against
+      // 512 cycles of tensor time for the four 256 x 256 x 16 pair MMAs: the G phases were ISSUE-bound (116 slabs x 700 = the
+      // 80 k cycles per tile of the phase clocks; the 34 k "waiting for ring slabs" was the probe latency).  Here both probes are
+      // in flight together, descriptors are formed by adding to the slab-0 descriptor (a swizzle-128B descriptor's low word is
+      // address >> 4), and the warp reconverges once per trip.  Every caller consumes an even number of slabs starting at an
+      // even slot, so a trip never wraps the ring.
+      const uint64_t d_ring0 = make_smem_desc_sw128(ring), d_opa0 = make_smem_desc_sw128(opa);
+      auto step2 = [&](uint32_t a_off0, uint32_t a_off1, uint32_t dcol0, uint32_t dcol1, uint32_t idesc, bool fresh0, bool fresh1) {
         const long long t0 = prof ? clock64() : 0;
-        mbar_wait(smem_u32(&full_bar[slot]), ph);
+        uint32_t r0, r1;
+        mbar_test2(full0 + (uint32_t)slot * 8u, ph, full0 + (uint32_t)slot * 8u + 8u, ph, r0, r1);
+        if (!r0) mbar_wait(full0 + (uint32_t)slot * 8u, ph);
         if (prof) m_full += clock64() - t0;
         tc_fence_after();
+        const uint64_t dB0 = d_ring0 + (uint64_t)((uint32_t)slot * (SLAB >> 4));
         if (elect_one()) {
-          const uint32_t b_addr = ring + (uint32_t)slot * SLAB;
+          const uint64_t dA = d_opa0 + (uint64_t)(a_off0 >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_2sm(tmem_base + dcol, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
-                         (fresh && k == 0) ? 0u : 1u);
-          umma_commit_2sm(smem_u32(&empty_bar[slot]), (uint16_t)3);
+            umma_f16_2sm(tmem_base + dcol0, dA + 2 * k, dB0 + 2 * k, idesc, (fresh0 && k == 0) ? 0u : 1u);
+          umma_commit_2sm(empty0 + (uint32_t)slot * 8u, (uint16_t)3);
+        }
+        if (!r1) {
+          const long long t1 = prof ? clock64() : 0;
+          mbar_wait(full0 + (uint32_t)slot * 8u + 8u, ph);
+          if (prof) m_full += clock64() - t1;
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          const uint64_t dA = d_opa0 + (uint64_t)(a_off1 >> 4), dB1 = dB0 + (uint64_t)(SLAB >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(tmem_base + dcol1, dA + 2 * k, dB1 + 2 * k, idesc, (fresh1 && k == 0) ? 0u : 1u);
+          umma_commit_2sm(empty0 + (uint32_t)slot * 8u + 8u, (uint16_t)3);
         }
         __syncwarp();
-        if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+        slot += 2;
+        if (slot == NSLOT) { slot = 0; ph ^= 1u; }
       };
       // a full-width GEMM out of the resident operand tile: D[128(x2) x 512] = OPA[.. x 512] W[512 x 512]^T
       // (each 256-column half is published as soon as its MMAs are issued: the E phase of half 0 overlaps half 1)
@@ -675,7 +699,8 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
 #pragma unroll 1
         for (int n = 0; n < 2; ++n) {
 #pragma unroll 1
-          for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)(n * 256), idesc256, kb == 0);
+          for (int kb = 0; kb < D / 64; kb += 2)
+            step2((uint32_t)kb * SLAB, (uint32_t)(kb + 1) * SLAB, (uint32_t)(n * 256), (uint32_t)(n * 256), idesc256, kb == 0, false);
           commit_tf(n);
         }
       };
@@ -694,9 +719,8 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
             wait_te(0); wait_te(1);
 #pragma unroll 1
             for (int hd = 0; hd < H; ++hd) {
-#pragma unroll 1
-              for (int kb = 0; kb < HD / 64; ++kb)
-                step(opa + (uint32_t)(hd * 2 + kb) * SLAB, (uint32_t)(hd * HD), idesc128, kb == 0);
+              static_assert(HD / 64 == 2, "G2 consumes one slab pair per head");
+              step2((uint32_t)(hd * 2) * SLAB, (uint32_t)(hd * 2 + 1) * SLAB, (uint32_t)(hd * HD), (uint32_t)(hd * HD), idesc128, true, false);
               if (hd & 1) commit_tf(hd >> 1);                 // heads 0, 1 = TMEM half 0; heads 2, 3 = half 1
             }
           }
@@ -710,7 +734,8 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
           for (int q = 0; q < 4; ++q) {
             wait_te(q & 1);
 #pragma unroll 1
-            for (int kb = 0; kb < D / 64; ++kb) step(opa + (uint32_t)kb * SLAB, (uint32_t)((q & 1) * 256), idesc256, kb == 0);
+            for (int kb = 0; kb < D / 64; kb += 2)
+              step2((uint32_t)kb * SLAB, (uint32_t)(kb + 1) * SLAB, (uint32_t)((q & 1) * 256), (uint32_t)((q & 1) * 256), idesc256, kb == 0, false);
             commit_tf(q & 1);
           }
         }
@@ -722,8 +747,7 @@ fused_block_kernel(const __grid_constant__ FbMaps tm, const __grid_constant__ Fb
             const long long t0 = prof ? clock64() : 0;
             mbar_wait(smem_u32(&afull_bar[sa]), (uint32_t)(kb >> 3));
             if (prof) m_full += clock64() - t0;
-            step(opa + (uint32_t)sa * SLAB, 0u, idesc256, kb == 0);
-            step(opa + (uint32_t)sa * SLAB, 256u, idesc256, kb == 0);
+            step2((uint32_t)sa * SLAB, (uint32_t)sa * SLAB, 0u, 256u, idesc256, kb == 0, kb == 0);
             if (elect_one()) umma_commit_2sm(smem_u32(&aempty_bar[sa]), (uint16_t)3);
             __syncwarp();
           }
