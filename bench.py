@@ -35,7 +35,7 @@ WORKLOADS = {
 }
 RESPACE = "15,15,8,6,6"
 # ncu (--set full, single stream, B=256 x T=196): dram__bytes_read.sum + dram__bytes_write.sum of one fused_block_kernel launch
-FUSED_DRAM_BYTES_PER_LAUNCH = 439.7e6    # profiles/r02_fused_kernels_metrics.csv: 218.04 MB read + 221.66 MB written
+FUSED_DRAM_BYTES_PER_LAUNCH = 441.4e6    # profiles/r02_fused_kernels_metrics.csv: 218.33 MB read + 223.05 MB written
 N_STEPS = 50
 
 
