@@ -195,6 +195,18 @@ int mcm_cfg_combine(const float* out_text, const float* out_none, double text_co
  * out[r, h, :] = sum_l softmax(body_weight, dim=1)[h, l] * v[r, l, :];  body_weight [H, H], v / out [rows, H, part_dim]. */
 int mcm_part_mix(const float* body_weight, const float* v, float* out, long long rows, int num_parts, int part_dim, void* stream);
 
+/* replaces: SFFN.forward of the STMoGen family (mogen/models/transformers/stmogen.py:581-607) incl. its StylizationBlock
+ * (mogen/models/utils/stylization_block.py:29-40):
+ *   y[:, :, h] = linear2_h(GELU(linear1_h(x[:, :, h])))  for the H body parts (x viewed as [B, T, H, L]) -- two block-diagonal
+ *   tcgen05 GEMMs (one launch each, per-part biases), then  out = x + Linear(SiLU(LN(y) (1 + scale) + shift))  with
+ *   (scale | shift) = Linear(SiLU(emb)).
+ * All pointers are device fp32: x / out [B, T, H*L]; emb [B, E]; w1 [H, F, L], b1 [H, F]; w2 [H, L, F], b2 [H, L];
+ * emb_w [2*H*L, E], emb_b [2*H*L]; ln_w / ln_b [H*L]; out_w [H*L, H*L], out_b [H*L].  H*L <= 1024, L and F multiples of 8.
+ * Weights are packed per call (a first Path-B piece: functional and parity-pinned, not yet a resident operator). */
+int mcm_sffn_forward(int B, int T, int H, int L, int F, int E, const float* x, const float* emb, const float* w1, const float* b1,
+                     const float* w2, const float* b2, const float* emb_w, const float* emb_b, const float* ln_w, const float* ln_b,
+                     const float* out_w, const float* out_b, float* out, void* stream);
+
 /* The on-device noise generator of the stochastic samplers, exposed for unit tests: out[0..n) ~ N(0,1), Philox4x32-10
  * keyed by `seed`, counter (element quad, sub), Box-Muller. */
 int mcm_test_randn(float* out_dev, long long n, unsigned long long seed, unsigned long long sub, void* stream);

@@ -35,7 +35,7 @@ constexpr int SMEM_TOTAL = 230400;         // dynamic shared memory request (+ ~
 
 struct KParams {
   int M, M_pad, K, batches, inner, a_k_inner, b_batched, out_col_inner, out_rows_per_outer,
-      trans_rows, head_dim, b_k_inner, a_batched, out_batched;
+      trans_rows, head_dim, b_k_inner, a_batched, out_batched, bias_inner;
   int block_n, m_tiles, n_tiles, num_kb, stages, split, total_tiles;
   int stg_bytes;        // per-warp epilogue staging bytes (4096 or 8192)
   int pair;             // 1: cta_group::2 -- a CTA pair computes a 256 x block_n tile, each CTA holds half of B
@@ -388,6 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int si = 0;
       while (si + 1 < p.nseg && n_tile >= p.seg[si + 1].tile0) ++si;
       const EpiSeg& sg = p.seg[si];
+      const float* const bias_p = sg.bias != nullptr ? sg.bias + (size_t)inner * p.bias_inner : nullptr;
       const int nbase = (n_tile - sg.tile0) * p.block_n;
       const int row0 = m_blk * BLOCK_M + quad * 32;             // first row (within the batch) of this warp
       const int r = row0 + lane;                                // this thread's row in the TMEM layout
@@ -401,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int cb = nbase + chunk_phase * 32 + k * CSTRIDE + lane;
-        bias_pre[k] = (sg.bias != nullptr && chunk_phase * 32 + k * CSTRIDE + lane < p.block_n && cb < sg.n) ? __ldg(sg.bias + cb) : 0.f;
+        bias_pre[k] = (bias_p != nullptr && chunk_phase * 32 + k * CSTRIDE + lane < p.block_n && cb < sg.n) ? __ldg(bias_p + cb) : 0.f;
       }
       const int tmode_t = p.tma_mode[si];
       // staging layout: a chunk that needs <= 4 KB (fp32 only, or 16-bit only) alternates between two 4 KB slots
@@ -583,7 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nrows = min(32, p.M - row0);      // valid rows of this warp (<= 0: none)
           const bool col_ok = lane < nvalid;
           const bool col_pad = !col_ok && lane < ncover && (cbase + lane) < sg.n_pad;
-          const float bias_v = (sg.bias != nullptr && col_ok) ? __ldg(sg.bias + cbase + lane) : 0.f;
+          const float bias_v = (bias_p != nullptr && col_ok) ? __ldg(bias_p + cbase + lane) : 0.f;
           const size_t rowg0 = (size_t)outer * p.out_rows_per_outer + row0;
           const int colg = colg0 + lane;
           if (sg.addend != nullptr && col_ok) {
@@ -644,7 +645,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (sg.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < nvalid) v[j] += __ldg(sg.bias + cbase + j);
+              if (j < nvalid) v[j] += __ldg(bias_p + cbase + j);
           }
           const size_t trow0 = (size_t)outer * p.trans_rows + (size_t)colg0;
           if (row_valid) {
@@ -1001,6 +1002,7 @@ int gemm_tc_launch(const GemmProblem& q, cudaStream_t stream) {
   p.b_k_inner = q.b_k_inner;
   p.a_batched = q.a_batched;
   p.out_batched = q.out_batched;
+  p.bias_inner = q.bias_inner;
   MCM_CHECK(q.a_k_inner % 8 == 0 && q.b_k_inner % 8 == 0, "per-inner K offsets must be multiples of 8 elements (TMA start alignment)");
   p.b_batched = q.b_batched;
   p.out_col_inner = q.out_col_inner;

@@ -50,6 +50,7 @@ struct GemmProblem {
   int b_k_inner;         // B k-offset per inner index (per-head diagonal blocks of a block-diagonal B)
   int a_batched;         // 0: A batch index = outer; 1: A batch index = batch (A described per (outer, inner))
   int out_batched;       // 1: output row = batch * out_rows_per_outer + r (columns still + inner * out_col_inner)
+  int bias_inner;        // bias offset per inner index (per-group biases of a block-diagonal Linear); 0: one bias per segment
   int b_batched;         // 0: B shared by all batches (weights); 1: B batch index = batch
   int out_col_inner;     // output column offset per inner index
   int out_rows_per_outer;// output row = outer * out_rows_per_outer + r

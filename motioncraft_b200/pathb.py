@@ -9,13 +9,16 @@ What is here runs on the device and is pinned against the unmodified reference (
       `(scatter + body) / 2` folded in for the decoder; the slices partition the 322 columns, so the structure is exact --
       and the whole layer is one pass of the tcgen05 GEMM kernel in its 3-pass bf16-split mode (the precision class of
       joint_embed / out).  Gather and scatter cost nothing: they are zero blocks of the operand.
+  SFFN                       stmogen.py:581-607 (+ its StylizationBlock): the twelve per-part Linear -> GELU -> Linear pairs as TWO
+      block-diagonal tcgen05 GEMM launches (batch = body part, per-part biases), LayerNorm + AdaLN + SiLU, output Linear with the
+      residual in its epilogue -> `mcm_sffn_forward`
   static_body_mix            st_attention.py:123-128 -> `mcm_part_mix`
   cfg_combine / scale_func   stmogen.py:655-659, 755-759 -> `mcm_cfg_combine`
   start_x / fixed_large      diffusion.py (`SamplerTables(model_mean="start_x")`)
 
 NOT here: the mixture-of-experts of STMA (`tutel.moe.moe_layer`, st_attention.py:17-56) -- an un-vendored, unpinned
 third-party dependency whose routing cannot be pinned in this image -- and therefore STMoGenTransformer itself; the
-dynamic / temporal branches and SFFN follow once the MoE question is settled.  `STMoGenTransformer` raises accordingly.
+dynamic / temporal branches follow once the MoE question is settled.  `STMoGenTransformer` raises accordingly.
 """
 import ctypes
 
@@ -169,10 +172,67 @@ def cfg_combine(out_text, out_none, timestep, scale=6.5):
     return out
 
 
+class _Stylization(nn.Module):
+    """Parameter container with the reference's StylizationBlock key names (stylization_block.py:14-27)."""
+
+    def __init__(self, latent_dim, time_embed_dim):
+        super().__init__()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(time_embed_dim, 2 * latent_dim))
+        self.norm = nn.LayerNorm(latent_dim)
+        self.out_layers = nn.Sequential(nn.SiLU(), nn.Dropout(p=0.0), nn.Linear(latent_dim, latent_dim))
+
+
+class SFFN(nn.Module):
+    """stmogen.py:581-607 -- same constructor arguments and state_dict keys; forward runs on the device in `mcm_sffn_forward`
+    (inference: dropout is the identity).  x (B, T, num_heads * latent_dim), emb (B, time_embed_dim)."""
+
+    def __init__(self, latent_dim, ffn_dim, dropout, time_embed_dim, **kwargs):
+        super().__init__()
+        self.num_heads = kwargs["num_heads"]
+        self.latent_dim, self.ffn_dim, self.time_embed_dim = latent_dim, ffn_dim, time_embed_dim
+        self.linear1_list = nn.ModuleList(nn.Linear(latent_dim, ffn_dim) for _ in range(self.num_heads))
+        self.linear2_list = nn.ModuleList(nn.Linear(ffn_dim, latent_dim) for _ in range(self.num_heads))
+        self.proj_out = _Stylization(latent_dim * self.num_heads, time_embed_dim)
+        self._stacked = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: setattr(self, "_stacked", None))
+
+    def _apply(self, fn, *a, **k):
+        self._stacked = None
+        return super()._apply(fn, *a, **k)
+
+    def _stack(self, dev):
+        if self._stacked is None or self._stacked[0].device != dev:
+            f = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+            po = self.proj_out
+            self._stacked = tuple(f(t) for t in (
+                torch.stack([m.weight for m in self.linear1_list]), torch.stack([m.bias for m in self.linear1_list]),
+                torch.stack([m.weight for m in self.linear2_list]), torch.stack([m.bias for m in self.linear2_list]),
+                po.emb_layers[1].weight, po.emb_layers[1].bias, po.norm.weight, po.norm.bias,
+                po.out_layers[2].weight, po.out_layers[2].bias))
+        return self._stacked
+
+    def forward(self, x, emb, **kwargs):
+        if x.device.type != "cuda":
+            raise McmError("motioncraft_b200 runs on an sm_100a CUDA device only")
+        B, T, D = x.shape
+        if D != self.num_heads * self.latent_dim:
+            raise McmError(f"SFFN: x has {D} features, expected {self.num_heads * self.latent_dim}")
+        xc = x.detach().float().contiguous()
+        ec = emb.detach().to(x.device, torch.float32).contiguous()
+        out = torch.empty_like(xc)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mcm_sffn_forward(B, T, self.num_heads, self.latent_dim, self.ffn_dim, self.time_embed_dim, ptr(xc), ptr(ec),
+                                            *[ptr(t) for t in self._stack(x.device)], ptr(out),
+                                            ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        return out
+
+
 class STMoGenTransformer(nn.Module):
     def __init__(self, *a, **k):
         super().__init__()
         raise McmError("STMoGenTransformer (configs/stmogen/*) is not complete in motioncraft_b200: its STMA blocks route "
                        "through tutel's mixture-of-experts layer, an un-vendored dependency whose semantics cannot be pinned "
-                       "here (SURVEY.md section 8 row b2).  Available pieces: PoseEncoder, PoseDecoder, static_body_mix, "
+                       "here (SURVEY.md section 8 row b2).  Available pieces: PoseEncoder, PoseDecoder, SFFN, static_body_mix, "
                        "cfg_combine, the start_x / fixed_large samplers (motioncraft_b200/pathb.py)")

@@ -250,6 +250,15 @@ def pathb(B=2, T=9, L=128):
         with scripted_randn_like([noise[i] for i in reversed(range(10))]):
             out["startx_ddpm10_x0"] = d10.p_sample_loop(net, (1, Tm, 322), noise=xT, clip_denoised=False,
                                                         model_kwargs=kw).numpy()
+        # SFFN (stmogen.py:581-607) of the latent_dim = 64 configs (12 parts, D = 768), reduced ffn / time-embedding widths
+        sf = st.SFFN(latent_dim=64, ffn_dim=128, dropout=0.0, time_embed_dim=256, num_heads=12).eval()
+        sf_names = {"ffn." + k: v.shape for k, v in sf.state_dict().items()}
+        sf_sd = synth.synth_state_dict(sf_names)           # (the zero-initialised output Linear gets real weights too)
+        sf.load_state_dict({k[len("ffn."):]: v for k, v in sf_sd.items()})
+        sx = synth.synth_tensor("sffn_x", (B, T, 768), synth.SEED_XT)
+        se = synth.synth_tensor("sffn_emb", (B, 256), synth.SEED_XF_PROJ)
+        out["sffn_keys"] = np.array(sorted(sf_names.keys()))
+        out["sffn_out"] = sf(sx, se).numpy()
     np.savez_compressed(os.path.join(GOLD, "pathb.npz"), **out)
     print("pathb", {k: v.shape for k, v in out.items() if v.dtype.kind == "f"})
 

@@ -74,3 +74,21 @@ def cfg_combine(out_text, out_none, timestep, scale):
     """stmogen.py:755-759: out_text * text_coef + out_none * none_coef."""
     wt, wn = scale_func(int(timestep), scale)
     return out_text * wt + out_none * wn
+
+
+def sffn(sd, x, emb, num_heads, prefix=""):
+    """SFFN.forward (stmogen.py:596-607) with its StylizationBlock (stylization_block.py:29-40), inference (dropout = identity):
+    per body part Linear -> GELU -> Linear, concatenated, then x + out_layers(LN(y) (1 + scale) + shift)."""
+    B, T, D = x.shape
+    xs = x.reshape(B, T, num_heads, -1)
+    outs = []
+    for i in range(num_heads):
+        feat = xs[:, :, i].contiguous()
+        feat = F.gelu(F.linear(feat, sd[f"{prefix}linear1_list.{i}.weight"], sd[f"{prefix}linear1_list.{i}.bias"]))
+        outs.append(F.linear(feat, sd[f"{prefix}linear2_list.{i}.weight"], sd[f"{prefix}linear2_list.{i}.bias"]))
+    y = torch.cat(outs, dim=-1)
+    emb_out = F.linear(F.silu(emb), sd[prefix + "proj_out.emb_layers.1.weight"], sd[prefix + "proj_out.emb_layers.1.bias"]).unsqueeze(1)
+    scale, shift = torch.chunk(emb_out, 2, dim=2)
+    h = F.layer_norm(y, (D,), sd[prefix + "proj_out.norm.weight"], sd[prefix + "proj_out.norm.bias"]) * (1 + scale) + shift
+    h = F.linear(F.silu(h), sd[prefix + "proj_out.out_layers.2.weight"], sd[prefix + "proj_out.out_layers.2.bias"])
+    return x.reshape(B, T, D) + h

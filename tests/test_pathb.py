@@ -124,3 +124,45 @@ def test_gpu_start_x_fixed_large_sampler_vs_reference_golden(golden_dir):
     noise = synth.synth_tensor("step_noise", (10, 1, T, 322), synth.SEED_STEP_NOISE)
     x0 = d.p_sample_loop(net, (1, T, 322), noise=x.cuda(), clip_denoised=False, model_kwargs=kw, step_noise=noise.cuda())
     assert C.rel_l2(x0, g["startx_ddpm10_x0"]) < TOL_FAST
+
+
+def _sffn_setup(g):
+    from motioncraft_b200 import pathb
+    mod = pathb.SFFN(latent_dim=64, ffn_dim=128, dropout=0.0, time_embed_dim=256, num_heads=12)
+    names = {"ffn." + k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    assert sorted(names) == list(g["sffn_keys"])                # the reference's parameter names and shapes (stmogen.py:583-594)
+    sd = synth.synth_state_dict(names)
+    B, T = g["sffn_out"].shape[:2]
+    x = synth.synth_tensor("sffn_x", (B, T, 768), synth.SEED_XT)
+    emb = synth.synth_tensor("sffn_emb", (B, 256), synth.SEED_XF_PROJ)
+    return mod, sd, x, emb
+
+
+def test_sffn_oracle_matches_reference_golden(golden_dir):
+    """SFFN + StylizationBlock (stmogen.py:581-607): the restatement against the unmodified reference module, bit for bit."""
+    g = _gold(golden_dir)
+    _, sd, x, emb = _sffn_setup(g)
+    with torch.no_grad():
+        got = P.sffn(sd, x, emb, 12, prefix="ffn.")
+    assert torch.equal(got, torch.from_numpy(g["sffn_out"]))
+
+
+@pytest.mark.gpu
+def test_gpu_sffn_vs_reference_golden(golden_dir):
+    """mcm_sffn_forward (two block-diagonal tcgen05 GEMM launches + AdaLN row kernel + output GEMM with the residual) against
+    the reference SFFN's output; also at a batch that fills several tiles, against the oracle."""
+    g = _gold(golden_dir)
+    mod, sd, x, emb = _sffn_setup(g)
+    mod.load_state_dict({k[len("ffn."):]: v for k, v in sd.items()})
+    mod = mod.cuda()
+    got = mod(x.cuda(), emb.cuda())
+    want = torch.from_numpy(g["sffn_out"])
+    assert C.rel_l2(got, want) < TOL_FAST, C.rel_l2(got, want)
+    # the FFN branch alone (the residual x dominates the norm of the output): same tolerance on out - x
+    assert C.rel_l2(got.cpu() - x, want - x) < 2 * TOL_FAST, C.rel_l2(got.cpu() - x, want - x)
+    xb = synth.synth_tensor("sffn_xb", (5, 196, 768), synth.SEED_XT)
+    eb = synth.synth_tensor("sffn_eb", (5, 256), synth.SEED_XF_PROJ)
+    with torch.no_grad():
+        wb = P.sffn(sd, xb, eb, 12, prefix="ffn.")
+    gb = mod(xb.cuda(), eb.cuda())
+    assert C.rel_l2(gb, wb) < TOL_FAST and C.rel_l2(gb.cpu() - xb, wb - xb) < 2 * TOL_FAST
