@@ -207,6 +207,24 @@ int mcm_sffn_forward(int B, int T, int H, int L, int F, int E, const float* x, c
                      const float* w2, const float* b2, const float* emb_w, const float* emb_b, const float* ln_w, const float* ln_b,
                      const float* out_w, const float* out_b, float* out, void* stream);
 
+/* replaces: everything of STMA.forward (mogen/models/attentions/st_attention.py:105-175) AFTER its two mixture-of-experts
+ * layers (tutel, un-vendored: not part of this library): the MoE outputs are inputs here.
+ *   motion_feat [B, T, H, 4L] = motion_moe(norm(x)) : (body value | key | value | query) per body part
+ *   text_feat   [B, Nt, Ht, 2L] = text_moe(text_norm(xf)) : (key | value); Ht = 1 (repeated over the parts, :150, :158) or H
+ *   y_s = softmax(body_weight, 1) mixed body values (static_body, :123-128) [+ the 8-head EfficientSelfAttention over the H part
+ *         tokens of every frame (dynamic body, :130-135; dyn_* = its LayerNorm and stacked q | k | v Linear, NULL = off)]
+ *   y_t = softmax_L(query) (softmax_n([key_text + (1-text_cond) -1e6 ; key_motion + (1-src_mask) -1e6])^T [value_text text_cond ;
+ *         value_motion src_mask])   per (sample, part)                                            (:146-171)
+ *   out = x + StylizationBlock(y_s + y_t, emb)                                                     (:172)
+ * All pointers device fp32; x / out [B, T, H*L]; emb [B, E]; src_mask [B, T]; text_cond [B] (= cond_type % 10 > 0);
+ * body_weight [H, H]; dyn_wqkv [3L, L], dyn_bqkv [3L]; StylizationBlock parameters as in mcm_sffn_forward.
+ * L in {32, 64, 96, 128}, H*L <= 1024, Nt + T <= 1024.  Weights are packed per call. */
+int mcm_stma_mix(int B, int T, int H, int L, int Nt, int Ht, int E, int static_body, const float* x, const float* motion_feat,
+                 const float* text_feat, const float* emb, const float* src_mask, const float* text_cond, const float* body_weight,
+                 const float* dyn_ln_w, const float* dyn_ln_b, const float* dyn_wqkv, const float* dyn_bqkv, const float* emb_w,
+                 const float* emb_b, const float* ln_w, const float* ln_b, const float* out_w, const float* out_b, float* out,
+                 void* stream);
+
 /* The on-device noise generator of the stochastic samplers, exposed for unit tests: out[0..n) ~ N(0,1), Philox4x32-10
  * keyed by `seed`, counter (element quad, sub), Box-Muller. */
 int mcm_test_randn(float* out_dev, long long n, unsigned long long seed, unsigned long long sub, void* stream);

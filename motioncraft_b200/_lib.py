@@ -62,6 +62,7 @@ SIGNATURES = {
     "mcm_cfg_combine": (_I, [_VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _LL, _VP]),
     "mcm_part_mix": (_I, [_VP, _VP, _VP, _LL, _I, _I, _VP]),
     "mcm_sffn_forward": (_I, [_I] * 6 + [_VP] * 14),
+    "mcm_stma_mix": (_I, [_I] * 8 + [_VP] * 19),
     "mcm_test_randn": (_I, [_VP, _LL, ctypes.c_ulonglong, ctypes.c_ulonglong, _VP]),
     "mcm_test_linear": (_I, [_I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
     "mcm_timing_enable": (None, [_I]),

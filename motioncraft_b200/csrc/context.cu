@@ -1256,88 +1256,4 @@ int mcm_test_linear(int M, int N, int K, const float* A, const float* W, const f
   return rc;
 }
 
-// SFFN of the STMoGen family (stmogen.py:581-607) + its StylizationBlock (stylization_block.py:29-40); see the header.
-int mcm_sffn_forward(int B, int T, int H, int L, int F, int E, const float* x, const float* emb, const float* w1, const float* b1,
-                     const float* w2, const float* b2, const float* emb_w, const float* emb_b, const float* ln_w, const float* ln_b,
-                     const float* out_w, const float* out_b, float* out, void* stream) {
-  MCM_CHECK(B > 0 && T > 0 && H > 0 && L > 0 && F > 0 && E > 0, "mcm_sffn_forward: bad shape");
-  MCM_CHECK(x && emb && w1 && b1 && w2 && b2 && emb_w && emb_b && ln_w && ln_b && out_w && out_b && out, "mcm_sffn_forward: null pointer");
-  const int D = H * L, rows = B * T;
-  MCM_CHECK(L % 8 == 0 && F % 8 == 0 && E % 8 == 0 && D <= 1024, "mcm_sffn_forward: need L, F, E multiples of 8 and H*L <= 1024");
-  MCM_TRY(gemm_tc_init());
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  std::vector<void*> tmp;
-  auto alloc = [&](void** ptr, size_t bytes) -> int {
-    MCM_CUDA(cudaMalloc(ptr, bytes));
-    tmp.push_back(*ptr);
-    return 0;
-  };
-  auto alloc_op16 = [&](OpPtr* o, size_t elems, int ld, bool lo) -> int {
-    o->ld = ld; o->lo = nullptr;
-    MCM_TRY(alloc(&o->hi, elems * 2));
-    if (lo) MCM_TRY(alloc(&o->lo, elems * 2));
-    return 0;
-  };
-  int rc = 0;
-  OpPtr xa, w1p, hid, w2p, embp, ewp, zop, owp;
-  float *y = nullptr, *mod = nullptr;
-  rc = rc || alloc_op16(&xa, (size_t)rows * D, D, false) || alloc_op16(&w1p, (size_t)H * F * L, L, false) ||
-       alloc_op16(&hid, (size_t)rows * H * F, H * F, false) || alloc_op16(&w2p, (size_t)H * L * F, F, false) ||
-       alloc_op16(&embp, (size_t)B * E, E, true) || alloc_op16(&ewp, (size_t)2 * D * E, E, true) ||
-       alloc_op16(&zop, (size_t)rows * D, D, false) || alloc_op16(&owp, (size_t)D * D, D, false) ||
-       alloc(reinterpret_cast<void**>(&y), (size_t)rows * D * 4) || alloc(reinterpret_cast<void**>(&mod), (size_t)B * 2 * D * 4);
-  // operands: activations / FFN weights fp16 (one pass), the AdaLN emb GEMM bf16 hi + lo (three passes) -- the precision
-  // classes of the configs/mcm path
-  if (!rc) rc = pack_op_launch(x, rows, D, D, false, xa, OP_F16, st);
-  if (!rc) rc = pack_op_launch(w1, H * F, L, L, false, w1p, OP_F16, st);
-  if (!rc) rc = pack_op_launch(w2, H * L, F, F, false, w2p, OP_F16, st);
-  if (!rc) rc = pack_op_launch(emb, B, E, E, true, embp, OP_BF16X2, st);      // SiLU(emb)
-  if (!rc) rc = pack_op_launch(emb_w, 2 * D, E, E, false, ewp, OP_BF16X2, st);
-  if (!rc) rc = pack_op_launch(out_w, D, D, D, false, owp, OP_F16, st);
-  if (!rc) {  // hid[:, h*F : (h+1)*F] = GELU(x[:, h*L : (h+1)*L] W1_h^T + b1_h): one block-diagonal launch, batch = part
-    GemmProblem g;
-    std::memset(&g, 0, sizeof(g));
-    g.a = xa; g.a_rows = rows; g.a_k = D; g.a_batches = 1; g.a_k_inner = L;
-    g.b = w1p; g.b_rows = F; g.b_k = L; g.b_batches = H; g.b_batched = 1;
-    g.fmt = OP_F16; g.M = rows; g.K = L; g.batches = H; g.inner = H;
-    g.out_rows_per_outer = rows; g.out_col_inner = F; g.bias_inner = F;
-    g.nseg = 1;
-    g.seg[0] = seg_default(F, 0);
-    g.seg[0].bias = b1; g.seg[0].op = hid; g.seg[0].op_fmt = OP_F16; g.seg[0].flags = EPI_GELU;
-    rc = gemm_tc_launch(g, st);
-  }
-  if (!rc) {  // y[:, h*L : (h+1)*L] = hid[:, h*F : (h+1)*F] W2_h^T + b2_h
-    GemmProblem g;
-    std::memset(&g, 0, sizeof(g));
-    g.a = hid; g.a_rows = rows; g.a_k = H * F; g.a_batches = 1; g.a_k_inner = F;
-    g.b = w2p; g.b_rows = L; g.b_k = F; g.b_batches = H; g.b_batched = 1;
-    g.fmt = OP_F16; g.M = rows; g.K = F; g.batches = H; g.inner = H;
-    g.out_rows_per_outer = rows; g.out_col_inner = L; g.bias_inner = L;
-    g.nseg = 1;
-    g.seg[0] = seg_default(L, 0);
-    g.seg[0].bias = b2; g.seg[0].out32 = y; g.seg[0].ld32 = D;
-    rc = gemm_tc_launch(g, st);
-  }
-  if (!rc) {  // (scale | shift) = SiLU(emb) We^T + be
-    GemmProblem g = linear_problem(embp, B, ewp, 2 * D, E, OP_BF16X2);
-    g.seg[0] = seg_default(2 * D, 0);
-    g.seg[0].bias = emb_b; g.seg[0].out32 = mod; g.seg[0].ld32 = 2 * D;
-    rc = gemm_tc_launch(g, st);
-  }
-  if (!rc) rc = ln_rows_launch(y, rows, D, D, ln_w, ln_b, mod, mod + D, 2 * D, T, true, zop, OP_F16, st);
-  if (!rc) {  // out = x + SiLU(...) Wo^T + bo
-    GemmProblem g = linear_problem(zop, rows, owp, D, D, OP_F16);
-    g.seg[0] = seg_default(D, 0);
-    g.seg[0].bias = out_b; g.seg[0].addend = x; g.seg[0].out32 = out; g.seg[0].ld32 = D;
-    rc = gemm_tc_launch(g, st);
-  }
-  cudaError_t e = cudaStreamSynchronize(st);
-  for (void* q : tmp) cudaFree(q);
-  if (!rc && e != cudaSuccess) {
-    set_error(std::string("mcm_sffn_forward: ") + cudaGetErrorString(e));
-    rc = 1;
-  }
-  return rc;
-}
-
 }  // extern "C"

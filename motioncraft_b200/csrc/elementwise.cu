@@ -556,7 +556,7 @@ axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa,
 // the H x H graph is soft-maxed once per block in shared memory.
 __global__ void __launch_bounds__(256)
 part_mix_kernel(const float* __restrict__ body_weight, const float* __restrict__ v, float* __restrict__ out, size_t rows,
-                int H, int L) {
+                int H, int L, int pitch) {
   __shared__ float w[32 * 32];
   pdl_trigger();
   pdl_wait();
@@ -576,9 +576,9 @@ part_mix_kernel(const float* __restrict__ body_weight, const float* __restrict__
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / L;
     const int d = (int)(i - r * L);
-    const float* src = v + r * (size_t)H * L + d;
+    const float* src = v + r * (size_t)H * pitch + d;      // part l of row r starts at (r * H + l) * pitch
     float x[32];
-    for (int l = 0; l < H; ++l) x[l] = src[(size_t)l * L];
+    for (int l = 0; l < H; ++l) x[l] = src[(size_t)l * pitch];
     for (int h = 0; h < H; ++h) {
       float acc = 0.f;
       for (int l = 0; l < H; ++l) acc = fmaf(w[h * H + l], x[l], acc);
@@ -616,11 +616,13 @@ int axpby_launch(const float* a, const float* b, float wa, float wb, float* out,
   return 0;
 }
 
-int part_mix_launch(const float* body_weight, const float* v, float* out, size_t rows, int H, int L, cudaStream_t stream) {
+int part_mix_launch(const float* body_weight, const float* v, float* out, size_t rows, int H, int L, cudaStream_t stream,
+                    int pitch) {
   MCM_CHECK(H >= 1 && H <= 32 && L >= 1, "part_mix: at most 32 parts");
+  if (pitch <= 0) pitch = L;
   LaunchTimer lt(LK_ROW, stream);
   MCM_CUDA(launch_pdl(part_mix_kernel, dim3(grid_for(rows * (size_t)L, 256)), dim3(256), (size_t)(0), stream, body_weight, v, out,
-                      rows, H, L));
+                      rows, H, L, pitch));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

@@ -61,7 +61,9 @@ int randn_fill_launch(float* out, size_t n, unsigned long long seed, unsigned lo
 int axpby_launch(const float* a, const float* b, float wa, float wb, float* out, size_t n, cudaStream_t stream);
 
 // out[r, h, :] = sum_l softmax(body_weight (H x H), dim=1)[h, l] * v[r, l, :]   (STMA static branch, st_attention.py:123-128)
-int part_mix_launch(const float* body_weight, const float* v, float* out, size_t rows, int H, int L, cudaStream_t stream);
+// `pitch`: elements between consecutive parts of the INPUT (0 = L, dense); the output is dense
+int part_mix_launch(const float* body_weight, const float* v, float* out, size_t rows, int H, int L, cudaStream_t stream,
+                    int pitch = 0);
 
 int elementwise_init();
 unsigned long long elementwise_launch_count();

@@ -12,6 +12,8 @@ What is here runs on the device and is pinned against the unmodified reference (
   SFFN                       stmogen.py:581-607 (+ its StylizationBlock): the twelve per-part Linear -> GELU -> Linear pairs as TWO
       block-diagonal tcgen05 GEMM launches (batch = body part, per-part biases), LayerNorm + AdaLN + SiLU, output Linear with the
       residual in its epilogue -> `mcm_sffn_forward`
+  STMATail                   st_attention.py:105-175 minus the two MoE layers: static + dynamic body branches, the temporal linear
+      attention over text + motion tokens with the reference's masks, StylizationBlock -> `mcm_stma_mix` (MoE outputs are inputs)
   static_body_mix            st_attention.py:123-128 -> `mcm_part_mix`
   cfg_combine / scale_func   stmogen.py:655-659, 755-759 -> `mcm_cfg_combine`
   start_x / fixed_large      diffusion.py (`SamplerTables(model_mean="start_x")`)
@@ -229,10 +231,78 @@ class SFFN(nn.Module):
         return out
 
 
+class _BodyAttention(nn.Module):
+    """Parameter container with the key names of EfficientSelfAttention(latent_dim, 8 heads, time_embed_dim=None)
+    (efficient_attention.py:12-23), the dynamic body branch of STMA (st_attention.py:88-93)."""
+
+    def __init__(self, latent_dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(latent_dim)
+        self.query = nn.Linear(latent_dim, latent_dim)
+        self.key = nn.Linear(latent_dim, latent_dim)
+        self.value = nn.Linear(latent_dim, latent_dim)
+
+
+class STMATail(nn.Module):
+    """Everything of STMA (st_attention.py:65-175) except its two mixture-of-experts layers: the parameters `body_weight`,
+    `body_d_attn.*`, `proj_out.*` under the reference's key names, and `forward` = `mcm_stma_mix` on the MoE OUTPUTS
+    (motion_feat (B, T, H, 4L), text_feat (B, Nt, Ht, 2L)).  With a pinned MoE in front of it this is STMA.forward."""
+
+    def __init__(self, latent_dim, num_heads, num_text_heads, time_embed_dim, static_body=True, dynamic_body=False, **kwargs):
+        super().__init__()
+        self.latent_dim, self.num_heads, self.num_text_heads = latent_dim, num_heads, num_text_heads
+        self.time_embed_dim, self.static_body, self.dynamic_body = time_embed_dim, static_body, dynamic_body
+        self.body_weight = nn.Parameter(torch.randn(num_heads, num_heads))
+        if dynamic_body:
+            self.body_d_attn = _BodyAttention(latent_dim)
+        self.proj_out = _Stylization(latent_dim * num_heads, time_embed_dim)
+        self._stacked = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: setattr(self, "_stacked", None))
+
+    def _apply(self, fn, *a, **k):
+        self._stacked = None
+        return super()._apply(fn, *a, **k)
+
+    def _stack(self, dev):
+        if self._stacked is None or self._stacked[0].device != dev:
+            f = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+            po = self.proj_out
+            dyn = [None] * 4
+            if self.dynamic_body:
+                a = self.body_d_attn
+                dyn = [f(a.norm.weight), f(a.norm.bias), f(torch.cat([a.query.weight, a.key.weight, a.value.weight])),
+                       f(torch.cat([a.query.bias, a.key.bias, a.value.bias]))]
+            self._stacked = (f(self.body_weight), *dyn, f(po.emb_layers[1].weight), f(po.emb_layers[1].bias), f(po.norm.weight),
+                             f(po.norm.bias), f(po.out_layers[2].weight), f(po.out_layers[2].bias))
+        return self._stacked
+
+    def forward(self, x, motion_feat, text_feat, emb, src_mask, cond_type, **kwargs):
+        if x.device.type != "cuda":
+            raise McmError("motioncraft_b200 runs on an sm_100a CUDA device only")
+        B, T, D = x.shape
+        H, L = self.num_heads, self.latent_dim
+        Nt, Ht = text_feat.shape[1], text_feat.shape[2]
+        if D != H * L or tuple(motion_feat.shape) != (B, T, H, 4 * L) or tuple(text_feat.shape) != (B, Nt, Ht, 2 * L):
+            raise McmError("STMATail: x (B, T, H*L), motion_feat (B, T, H, 4L), text_feat (B, Nt, Ht, 2L) expected")
+        f = lambda t: t.detach().to(x.device, torch.float32).contiguous()  # noqa: E731
+        xc, mf, tf, ec = f(x), f(motion_feat), f(text_feat), f(emb)
+        mask = f(src_mask).reshape(B, T)
+        tcond = (cond_type.reshape(B).to(x.device) % 10 > 0).float().contiguous()              # st_attention.py:137
+        out = torch.empty_like(xc)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else None)  # noqa: E731
+        st = self._stack(x.device)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mcm_stma_mix(B, T, H, L, Nt, Ht, self.time_embed_dim, 1 if self.static_body else 0, ptr(xc), ptr(mf), ptr(tf),
+                                        ptr(ec), ptr(mask), ptr(tcond), *[ptr(t) for t in st], ptr(out),
+                                        ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        return out
+
+
 class STMoGenTransformer(nn.Module):
     def __init__(self, *a, **k):
         super().__init__()
         raise McmError("STMoGenTransformer (configs/stmogen/*) is not complete in motioncraft_b200: its STMA blocks route "
                        "through tutel's mixture-of-experts layer, an un-vendored dependency whose semantics cannot be pinned "
-                       "here (SURVEY.md section 8 row b2).  Available pieces: PoseEncoder, PoseDecoder, SFFN, static_body_mix, "
+                       "here (SURVEY.md section 8 row b2).  Available pieces: PoseEncoder, PoseDecoder, SFFN, STMATail (STMA after its MoE layers), static_body_mix, "
                        "cfg_combine, the start_x / fixed_large samplers (motioncraft_b200/pathb.py)")

@@ -259,6 +259,41 @@ def pathb(B=2, T=9, L=128):
         se = synth.synth_tensor("sffn_emb", (B, 256), synth.SEED_XF_PROJ)
         out["sffn_keys"] = np.array(sorted(sf_names.keys()))
         out["sffn_out"] = sf(sx, se).numpy()
+        # STMA.forward (st_attention.py:105-175) with its two mixture-of-experts layers replaced by stubs that return preset
+        # tensors (tutel is un-vendored): everything AFTER the MoE outputs is the reference's own code.
+        import mogen.models.attentions.st_attention as sta
+
+        class _PresetMOE(torch.nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+                self.preset, self.aux_loss = None, 0.0
+
+            def forward(self, x):
+                return self.preset
+
+        real_moe, sta.MOE = sta.MOE, _PresetMOE
+        try:
+            for tag, Ls, dyn, Ht, Tm in (("a", 64, True, 1, 20), ("b", 32, False, 12, 9)):
+                m = sta.STMA(latent_dim=Ls, text_latent_dim=256, num_heads=12, num_text_heads=Ht, num_experts=16, topk=2,
+                             gate_type="cosine_top", gate_noise=1.0, ffn_dim=4 * Ls, time_embed_dim=256, max_seq_len=196,
+                             max_text_seq_len=77, temporal_comb=False, dropout=0.0, static_body=True, dynamic_body=dyn).eval()
+                keep = {k: v for k, v in m.state_dict().items() if not k.startswith(("norm.", "text_norm."))}
+                nm = {f"stma_{tag}." + k: v.shape for k, v in keep.items()}
+                ssd = synth.synth_state_dict(nm)
+                m.load_state_dict({k[len(f"stma_{tag}."):]: v for k, v in ssd.items()}, strict=False)
+                Bs, Nt = 3, 7
+                sx = synth.synth_tensor(f"stma_{tag}_x", (Bs, Tm, 12 * Ls), synth.SEED_XT)
+                m.motion_moe.preset = synth.synth_tensor(f"stma_{tag}_mf", (Bs, Tm, 12, 4 * Ls), synth.SEED_XF_OUT)
+                m.text_moe.preset = synth.synth_tensor(f"stma_{tag}_tf", (Bs, Nt, Ht, 2 * Ls), synth.SEED_C_EMB)
+                semb = synth.synth_tensor(f"stma_{tag}_emb", (Bs, 256), synth.SEED_XF_PROJ)
+                mask = torch.ones(Bs, Tm, 1)
+                mask[1, Tm - 4:] = 0                                   # a padded sample
+                cond = torch.tensor([1, 0, 11]).view(Bs, 1, 1)         # text on / off / on (cond_type % 10 > 0)
+                xf = torch.zeros(Bs, Nt, Ht * 256)                     # only its shape is used once the MoE is preset
+                out[f"stma_{tag}_keys"] = np.array(sorted(nm.keys()))
+                out[f"stma_{tag}_out"] = m(sx, xf, semb, mask, cond, None, None).numpy()
+        finally:
+            sta.MOE = real_moe
     np.savez_compressed(os.path.join(GOLD, "pathb.npz"), **out)
     print("pathb", {k: v.shape for k, v in out.items() if v.dtype.kind == "f"})
 

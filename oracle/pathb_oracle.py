@@ -92,3 +92,63 @@ def sffn(sd, x, emb, num_heads, prefix=""):
     h = F.layer_norm(y, (D,), sd[prefix + "proj_out.norm.weight"], sd[prefix + "proj_out.norm.bias"]) * (1 + scale) + shift
     h = F.linear(F.silu(h), sd[prefix + "proj_out.out_layers.2.weight"], sd[prefix + "proj_out.out_layers.2.bias"])
     return x.reshape(B, T, D) + h
+
+
+def _stylization(sd, prefix, h, emb):
+    """StylizationBlock.forward (stylization_block.py:29-40), inference."""
+    D = h.shape[-1]
+    emb_out = F.linear(F.silu(emb), sd[prefix + "emb_layers.1.weight"], sd[prefix + "emb_layers.1.bias"]).unsqueeze(1)
+    scale, shift = torch.chunk(emb_out, 2, dim=2)
+    h = F.layer_norm(h, (D,), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"]) * (1 + scale) + shift
+    return F.linear(F.silu(h), sd[prefix + "out_layers.2.weight"], sd[prefix + "out_layers.2.bias"])
+
+
+def _body_self_attention(sd, prefix, x, num_heads=8):
+    """EfficientSelfAttention.forward with time_embed_dim=None and an all-ones mask (efficient_attention.py:25-46), as STMA calls
+    it on the (B*T, H, L) part tokens (st_attention.py:130-133)."""
+    B, T, D = x.shape
+    xn = F.layer_norm(x, (D,), sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])
+    query = F.linear(xn, sd[prefix + "query.weight"], sd[prefix + "query.bias"])
+    key = F.linear(xn, sd[prefix + "key.weight"], sd[prefix + "key.bias"]) + (1 - torch.ones(B, T, 1)) * -1000000
+    query = F.softmax(query.view(B, T, num_heads, -1), dim=-1)
+    key = F.softmax(key.view(B, T, num_heads, -1), dim=1)
+    value = (F.linear(xn, sd[prefix + "value.weight"], sd[prefix + "value.bias"]) * torch.ones(B, T, 1)).view(B, T, num_heads, -1)
+    attention = torch.einsum("bnhd,bnhl->bhdl", key, value)
+    y = torch.einsum("bnhd,bhdl->bnhl", query, attention).reshape(B, T, D)
+    return x + y
+
+
+def stma_tail(sd, x, motion_feat, text_feat, emb, src_mask, cond_type, num_heads, latent_dim, static_body=True, dynamic_body=False,
+              prefix=""):
+    """STMA.forward (st_attention.py:105-175) from the point where both mixture-of-experts outputs exist: `motion_feat` =
+    motion_moe(norm(x)) (B, T, H, 4L) and `text_feat` = text_moe(text_norm(xf)) (B, Nt, Ht, 2L) are INPUTS (the tutel MoE is
+    un-vendored: parity unpinned, not restated)."""
+    B, T, D = x.shape
+    H, L = num_heads, latent_dim
+    N = text_feat.shape[1] + T
+    body_weight = F.softmax(sd[prefix + "body_weight"], dim=1)
+    body_value = motion_feat[:, :, :, :L]
+    body_feat = body_value
+    if static_body:
+        body_feat = torch.einsum("hl,bnld->bnhd", body_weight, body_value)
+    body_feat = body_feat.reshape(B, T, D)
+    if dynamic_body:
+        body_feat = body_feat + _body_self_attention(sd, prefix + "body_d_attn.", body_value.reshape(B * T, H, -1)).reshape(B, T, D)
+    text_cond_type = (cond_type % 10 > 0).float().unsqueeze(-1)
+    src_mask = src_mask.view(B, T, 1, 1)
+    key_text = text_feat[:, :, :, :L].contiguous()
+    key_text = key_text + (1 - text_cond_type) * -1000000
+    if text_feat.shape[2] == 1:
+        key_text = key_text.repeat(1, 1, H, 1)
+    key_motion = motion_feat[:, :, :, L:2 * L].contiguous()
+    key_motion = key_motion + (1 - src_mask) * -1000000
+    key = F.softmax(torch.cat((key_text, key_motion), dim=1).view(B, N, H, -1), dim=1)
+    value_text = text_feat[:, :, :, L:].contiguous() * text_cond_type
+    if text_feat.shape[2] == 1:
+        value_text = value_text.repeat(1, 1, H, 1)
+    value_motion = motion_feat[:, :, :, 2 * L:3 * L].contiguous() * src_mask
+    value = torch.cat((value_text, value_motion), dim=1).view(B, N, H, -1)
+    query = F.softmax(motion_feat[:, :, :, 3 * L:].contiguous().view(B, T, H, -1), dim=-1)
+    attention = torch.einsum("bnhd,bnhl->bhdl", key, value)
+    y_t = torch.einsum("bnhd,bhdl->bnhl", query, attention).reshape(B, T, D)
+    return x.reshape(B, T, D) + _stylization(sd, prefix + "proj_out.", body_feat + y_t, emb)

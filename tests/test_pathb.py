@@ -166,3 +166,71 @@ def test_gpu_sffn_vs_reference_golden(golden_dir):
         wb = P.sffn(sd, xb, eb, 12, prefix="ffn.")
     gb = mod(xb.cuda(), eb.cuda())
     assert C.rel_l2(gb, wb) < TOL_FAST and C.rel_l2(gb.cpu() - xb, wb - xb) < 2 * TOL_FAST
+
+
+_STMA_CASES = (("a", 64, True, 1, 20), ("b", 32, False, 12, 9))     # tag, latent_dim, dynamic_body, num_text_heads, T
+
+
+def _stma_setup(g, tag, Ls, dyn, Ht, Tm):
+    from motioncraft_b200 import pathb
+    mod = pathb.STMATail(latent_dim=Ls, num_heads=12, num_text_heads=Ht, time_embed_dim=256, static_body=True, dynamic_body=dyn)
+    names = {f"stma_{tag}." + k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    assert sorted(names) == list(g[f"stma_{tag}_keys"])        # the reference STMA's parameters minus its MoE / pre-MoE norms
+    sd = synth.synth_state_dict(names)
+    Bs, Nt = 3, 7
+    x = synth.synth_tensor(f"stma_{tag}_x", (Bs, Tm, 12 * Ls), synth.SEED_XT)
+    mf = synth.synth_tensor(f"stma_{tag}_mf", (Bs, Tm, 12, 4 * Ls), synth.SEED_XF_OUT)
+    tf = synth.synth_tensor(f"stma_{tag}_tf", (Bs, Nt, Ht, 2 * Ls), synth.SEED_C_EMB)
+    emb = synth.synth_tensor(f"stma_{tag}_emb", (Bs, 256), synth.SEED_XF_PROJ)
+    mask = torch.ones(Bs, Tm, 1)
+    mask[1, Tm - 4:] = 0
+    cond = torch.tensor([1, 0, 11]).view(Bs, 1, 1)
+    return mod, sd, (x, mf, tf, emb, mask, cond)
+
+
+@pytest.mark.parametrize("tag,Ls,dyn,Ht,Tm", _STMA_CASES)
+def test_stma_tail_oracle_matches_reference_golden(golden_dir, tag, Ls, dyn, Ht, Tm):
+    """STMA.forward after its MoE layers (static + dynamic body, masked temporal linear attention over text + motion tokens,
+    StylizationBlock): the restatement against the unmodified reference class run with preset MoE outputs, bit for bit."""
+    g = _gold(golden_dir)
+    _, sd, (x, mf, tf, emb, mask, cond) = _stma_setup(g, tag, Ls, dyn, Ht, Tm)
+    with torch.no_grad():
+        got = P.stma_tail(sd, x, mf, tf, emb, mask, cond, 12, Ls, True, dyn, prefix=f"stma_{tag}.")
+    assert torch.equal(got, torch.from_numpy(g[f"stma_{tag}_out"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,Ls,dyn,Ht,Tm", _STMA_CASES)
+def test_gpu_stma_tail_vs_reference_golden(golden_dir, tag, Ls, dyn, Ht, Tm):
+    g = _gold(golden_dir)
+    mod, sd, (x, mf, tf, emb, mask, cond) = _stma_setup(g, tag, Ls, dyn, Ht, Tm)
+    mod.load_state_dict({k[len(f"stma_{tag}."):]: v for k, v in sd.items()})
+    mod = mod.cuda()
+    got = mod(x.cuda(), mf.cuda(), tf.cuda(), emb.cuda(), mask.cuda(), cond.cuda()).cpu()
+    want = torch.from_numpy(g[f"stma_{tag}_out"])
+    assert torch.isfinite(got).all()
+    assert C.rel_l2(got, want) < TOL_FAST, C.rel_l2(got, want)
+    assert C.rel_l2(got - x, want - x) < 2 * TOL_FAST, C.rel_l2(got - x, want - x)      # the attention branch without the residual
+
+
+@pytest.mark.gpu
+def test_gpu_stma_tail_full_size_vs_oracle():
+    """The latent_dim = 64 configuration at T = 196, 77 text tokens, B = 4 (several GEMM tiles per contraction), against the
+    oracle; a text-off sample and a padded sample included."""
+    from motioncraft_b200 import pathb
+    Ls, Tm, Nt, Bs = 64, 196, 77, 4
+    mod = pathb.STMATail(latent_dim=Ls, num_heads=12, num_text_heads=1, time_embed_dim=2048, static_body=True, dynamic_body=True)
+    names = {"stma_f." + k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    sd = synth.synth_state_dict(names)
+    mod.load_state_dict({k[len("stma_f."):]: v for k, v in sd.items()})
+    x = synth.synth_tensor("stma_f_x", (Bs, Tm, 12 * Ls), synth.SEED_XT)
+    mf = synth.synth_tensor("stma_f_mf", (Bs, Tm, 12, 4 * Ls), synth.SEED_XF_OUT)
+    tf = synth.synth_tensor("stma_f_tf", (Bs, Nt, 1, 2 * Ls), synth.SEED_C_EMB)
+    emb = synth.synth_tensor("stma_f_emb", (Bs, 2048), synth.SEED_XF_PROJ)
+    mask = torch.ones(Bs, Tm, 1)
+    mask[2, 150:] = 0
+    cond = torch.tensor([1, 1, 0, 21]).view(Bs, 1, 1)
+    with torch.no_grad():
+        want = P.stma_tail(sd, x, mf, tf, emb, mask, cond, 12, Ls, True, True, prefix="stma_f.")
+    got = mod.cuda()(x.cuda(), mf.cuda(), tf.cuda(), emb.cuda(), mask.cuda(), cond.cuda()).cpu()
+    assert C.rel_l2(got, want) < TOL_FAST and C.rel_l2(got - x, want - x) < 2 * TOL_FAST, (C.rel_l2(got, want), C.rel_l2(got - x, want - x))

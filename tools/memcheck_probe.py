@@ -24,4 +24,14 @@ for T, B, fused in ((196, 12, 1), (196, 2, 0), (300, 2, 0), (1024, 2, 0), (1024,
     torch.cuda.synchronize()
     print(T, B, fused, bool(torch.isfinite(out).all()), flush=True)
     eng.close()
+
+# Path-B pieces (SFFN, STMA after its MoE layers)
+from motioncraft_b200 import pathb
+sf = pathb.SFFN(latent_dim=64, ffn_dim=128, dropout=0.0, time_embed_dim=256, num_heads=12).cuda()
+print("sffn", bool(torch.isfinite(sf(torch.randn(2, 9, 768).cuda(), torch.randn(2, 256).cuda())).all()), flush=True)
+for L, dyn, Ht in ((64, True, 1), (32, False, 12)):
+    tm = pathb.STMATail(latent_dim=L, num_heads=12, num_text_heads=Ht, time_embed_dim=256, dynamic_body=dyn).cuda()
+    o = tm(torch.randn(3, 20, 12 * L).cuda(), torch.randn(3, 20, 12, 4 * L).cuda(), torch.randn(3, 7, Ht, 2 * L).cuda(),
+           torch.randn(3, 256).cuda(), torch.ones(3, 20, 1).cuda(), torch.tensor([1, 0, 11]).view(3, 1, 1).cuda())
+    print("stma", L, dyn, bool(torch.isfinite(o).all()), flush=True)
 print("done")
