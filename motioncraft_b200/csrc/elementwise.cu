@@ -102,7 +102,7 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
   for (int i = 0; i < MAXV; ++i) {
     const int q = i * 32 + lane;
     if (q < nv) {
-      v[i] = *reinterpret_cast<const float4*>(x + 4 * q);
+      v[i] = __ldcs(reinterpret_cast<const float4*>(x + 4 * q));     // streamed once: keep L1 for the parameter vectors
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
