@@ -69,9 +69,18 @@ def test_pathb_modules_fail_loudly_without_gpu_and_for_moe():
     from motioncraft_b200._lib import McmError
     with pytest.raises(McmError):
         pathb.STMoGenTransformer()
-    if not torch.cuda.is_available():
-        with pytest.raises(McmError):
-            pathb.PoseEncoder()(torch.zeros(1, 2, 322))
+    # CPU tensors never reach a fallback: every Path-B module refuses them (the library is CUDA-only)
+    with pytest.raises(McmError):
+        pathb.PoseEncoder()(torch.zeros(1, 2, 322))
+    with pytest.raises(McmError):
+        pathb.SFFN(latent_dim=64, ffn_dim=128, dropout=0.0, time_embed_dim=256, num_heads=12)(torch.zeros(1, 2, 768), torch.zeros(1, 256))
+    tail = pathb.STMATail(latent_dim=32, num_heads=12, num_text_heads=1, time_embed_dim=256, dynamic_body=True)
+    with pytest.raises(McmError):
+        tail(torch.zeros(1, 2, 384), torch.zeros(1, 2, 12, 128), torch.zeros(1, 3, 1, 64), torch.zeros(1, 256), torch.ones(1, 2, 1),
+             torch.ones(1, 1, 1))
+    # the reference's parameter names (st_attention.py:79-99 minus the MoE layers and the pre-MoE norms)
+    assert {"body_weight", "body_d_attn.norm.weight", "body_d_attn.query.weight", "proj_out.emb_layers.1.weight",
+            "proj_out.out_layers.2.bias"} <= set(tail.state_dict())
 
 
 @pytest.mark.gpu
