@@ -118,8 +118,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (p.cs > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts / arrives remotely
   tc_fence_after();
-  pdl_wait();                                         // prologue done; from here on global memory is touched
-  if (warp == 0) MCM_STAMP(1);
+  // griddepcontrol.wait is issued by each role as LATE as possible (with programmatic dependent launch the kernel typically
+  // starts tens of microseconds before its inputs exist): the producer right before its first TMA load, after the tile
+  // decode and every parameter fetch -- cold constant-bank / instruction-cache misses cost ~2.5 k cycles there, which the
+  // time line showed between the wait and the first load; the epilogue warps after their first accumulator arrives (their
+  // bias prefetch reads parameters only); the MMA warp touches no global memory at all.
   const uint32_t tmem_base = tmem_slot;
   const int crank = p.cs > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / p.cs;
@@ -134,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
+      bool pdl_done = false;
       long long pr_wait = 0, pr_kb = 0, pr_t0 = (p.debug == 3) ? clock64() : 0;
       const uint32_t tx = p.stage_bytes;
       for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
@@ -150,6 +154,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b_k0 = inner * p.b_k_inner;
         const int a_z = p.a_batched ? batch : outer;
         const int b_z = p.b_batched ? batch : 0;
+        if (p.prefetch && !pdl_done) {           // (experiment switch) the prefetches below read activations
+          pdl_wait();
+          pdl_done = true;
+        }
         if (p.prefetch && lane == 0) {
           // pull the NEXT work item's A rows (activations, usually DRAM-resident) into L2 while this one is loaded
           const int nt = tile + n_clusters;
@@ -223,6 +231,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (stages < 2) r1 = 0u;
           if (!r0) mbar_wait(empty0 + (uint32_t)s0 * 8u, ph0 ^ 1u);
           if (dbg3) { const long long n = clock64(); pr_wait += n - tp0; pr_kb += two ? 2 : 1; }
+          if (!pdl_done) {                       // first load of this CTA: the inputs must exist from here on
+            pdl_wait();
+            pdl_done = true;
+            MCM_STAMP(1);
+          }
           load_kb(s0, kb);
           if (two) {
             if (!r1) {
@@ -410,6 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
+      if (it == 0) pdl_wait();                 // returns at once: the accumulator exists, so the producer's wait has passed
       if (ew == 0 && it == 0) MCM_STAMP(4);
       MCM_TICK(0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
