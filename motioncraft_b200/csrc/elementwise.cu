@@ -90,14 +90,19 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
                int mod_ld, int rows_per_batch, int act_silu, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo,
                int out_ld) {
   pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* x = in + (size_t)row * ld_in;
   const int nv = d >> 2;                       // float4 count (d % 4 == 0)
+  const int batch = row / rows_per_batch;
+  const float* sc = scale ? scale + (size_t)batch * mod_ld : nullptr;
+  const float* sh = shift ? shift + (size_t)batch * mod_ld : nullptr;
+  const int nvo = out_ld >> 2;
+  const size_t obase = (size_t)row * out_ld;
   float4 v[MAXV];
   float s = 0.f;
+  pdl_wait();                                  // as late as possible: every kernel parameter has been fetched by now
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int q = i * 32 + lane;
@@ -119,11 +124,6 @@ ln_rows_kernel(const float* __restrict__ in, int rows, int d, int ld_in, const f
     }
   }
   const float rstd = rsqrtf(warp_sum(ss) / (float)d + 1e-5f);
-  const int batch = row / rows_per_batch;
-  const float* sc = scale ? scale + (size_t)batch * mod_ld : nullptr;
-  const float* sh = shift ? shift + (size_t)batch * mod_ld : nullptr;
-  const int nvo = out_ld >> 2;
-  const size_t obase = (size_t)row * out_ld;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int q = i * 32 + lane;
@@ -160,7 +160,6 @@ __global__ void __launch_bounds__(256)
 softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols, int ld_in, int seg, int nseg,
                    uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
   pdl_trigger();
-  pdl_wait();
   constexpr int SPW = 32 / LPS;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -170,8 +169,10 @@ softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols
   const long long row = active ? gs / nseg : 0;
   const int sidx = active ? (int)(gs - row * nseg) : 0;
   const float* x = in + (size_t)row * ld_in + (size_t)sidx * seg + sub;
+  const size_t obase = (size_t)row * out_ld + (size_t)sidx * seg + sub;
   float v[EPL];
   float m = -INFINITY;
+  pdl_wait();                                  // after the index arithmetic (which fetches every kernel parameter)
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
     v[i] = (active && i * LPS + sub < seg) ? x[i * LPS] : -INFINITY;
@@ -189,7 +190,6 @@ softmax_seg_kernel(const float* __restrict__ in, long long total_segs, int ncols
   for (int o = LPS / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (!active) return;
   const float inv = 1.f / s;
-  const size_t obase = (size_t)row * out_ld + (size_t)sidx * seg + sub;
 #pragma unroll
   for (int i = 0; i < EPL; ++i)
     if (i * LPS + sub < seg) st1<FMT>(ohi, olo, obase + i * LPS, v[i] * inv);
@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(32 * NW)
 ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __restrict__ w,
                     const float* __restrict__ b, uint16_t* __restrict__ ohi, uint16_t* __restrict__ olo, int out_ld) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float tile[];            // T * 33
   __shared__ float red[NW][33];
   __shared__ float mean_s[32], rstd_s[32];
@@ -216,6 +215,7 @@ ln_transpose_kernel(const float* __restrict__ h, int T, int D, const float* __re
   const int bidx = blockIdx.y;
   const float* src = h + (size_t)bidx * T * D + d0 + tx;
   float s = 0.f;
+  pdl_wait();
 #pragma unroll 8
   for (int t = ty; t < T; t += NW) {
     const float val = src[(size_t)t * D];
@@ -328,8 +328,8 @@ ln_transpose16_kernel(const float* __restrict__ h, int T, int D, const float* __
 __global__ void __launch_bounds__(256)
 pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, int act_silu, OpPtr out, int out_fmt) {
   pdl_trigger();
-  pdl_wait();
   const size_t total = rows * (size_t)out.ld;
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / out.ld;
     const int c = (int)(i - r * out.ld);
@@ -346,9 +346,9 @@ pack_op_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, i
 __global__ void __launch_bounds__(256)
 pack_op8_kernel(const float* __restrict__ in, size_t rows, int cols, int ld_in, int act_silu, OpPtr out, int out_fmt) {
   pdl_trigger();
-  pdl_wait();
   const int gpr = out.ld >> 3;
   const size_t total = rows * (size_t)gpr;
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / gpr;
     const int c = (int)(i - r * gpr) * 8;
