@@ -103,9 +103,20 @@ struct mcm_ctx {
   static constexpr size_t MAX_GRAPHS = 8;
   unsigned long long graph_clock = 0;
   float* noise_buf = nullptr;            // [Bmax*T*IN] per-step sampler noise staged / generated on the device (lazy)
+  // Hoisted AdaLN modulation (run_sampler): emb = time_embed(t) + xf_proj and mod = emb_layers(SiLU(emb)) depend on the step only
+  // through t, so for small batches all steps' modulation vectors are computed by ONE batched pass before the loop
+  // (3 GEMMs + 2 row kernels per run instead of per step) and each step's graph just gathers its slice.
+  int hoist_mod = 1;                     // MCM_HOIST_MOD=0 / set_option("hoist_mod", 0): per-step modulation always
+  float* mod_all = nullptr;              // [steps * B, mod_total]
+  float* emb_all = nullptr;              // [steps * B, E]
+  long long* t_all = nullptr;            // [steps * B]
+  long long* step_buf = nullptr;         // device scalar: index of the current step's slice
+  OpPtr te_all, t1_all, embop_all;
+  size_t hoist_rows = 0;                 // capacity of the buffers above in rows
+  bool hoist_active = false;             // the current sampling run uses mod_all
   // every scheduling option that changes the captured launch sequence is part of the graph key
   long long graph_key() const {
-    return (long long)fused + 2ll * fused_sa + 16ll * (dual ? 1 : 0) + 32ll * fused_stop + 256ll * (split_sms ? 1 : 0) + 512ll * (long long)chunk +
+    return (long long)fused + 2ll * fused_sa + 4ll * (hoist_active ? 1 : 0) + 16ll * (dual ? 1 : 0) + 32ll * fused_stop + 256ll * (split_sms ? 1 : 0) + 512ll * (long long)chunk +
            (1ll << 24) * (long long)fused_min_rows + (1ll << 44) * (long long)(fused_sa_min_rows >= 0 ? 1 + fused_sa_min_rows / 64 : 0);
   }
   void drop_graphs() {
@@ -578,6 +589,10 @@ int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float
   const int D = c->D, E = c->E;
   const int fp = c->fmt_prec();
   MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first (for at least this batch)");
+  if (c->hoist_active) {
+    // this step's modulation vectors were computed before the loop (precompute_mod_all): pick the slice
+    MCM_TRY(gather_slice_launch(c->mod_all, c->step_buf, c->mod32, (size_t)B * c->mod_total, st));
+  } else {
   // emb = time_embed(sinusoid(t)) + xf_proj                      (diffusion_transformer.py:206-213)
   MCM_TRY(timestep_embedding_launch(t_dev, t_uniform, B, D, c->te_op, fp, st));
   {
@@ -593,6 +608,7 @@ int run_denoiser(mcm_ctx* c, int B, const long long* t_dev, int t_uniform, float
     MCM_TRY(gemm_tc_launch(g, st));
   }
   MCM_TRY(run_mod(c, B, c->emb32, 0, (int)c->blocks.size(), st));
+  }   // per-step modulation
   // Layer stack, in chunks of `chunk` samples: every op is per-sample, so a chunk runs the whole stack on
   // chunk-local activations (h, operands and fp32 scratch reuse the SAME addresses for every chunk) which then stay
   // resident in the 126 MB L2 instead of bouncing through HBM between kernels.
@@ -722,13 +738,68 @@ int step_noise_ptr(mcm_ctx* c, const NoiseSource& ns, long long index, size_t n,
   return 0;
 }
 
+// All steps' AdaLN modulation vectors in one batched pass (row r = step * B + sample): the arithmetic per row is that of the
+// per-step path (same kernels, same K order), so the sampled result does not depend on whether the hoist is taken.
+int precompute_mod_all(mcm_ctx* c, const mcm_sampler* s, int B, cudaStream_t st) {
+  const int S = s->n_steps, D = c->D, E = c->E, fp = c->fmt_prec();
+  const size_t R = (size_t)S * B;
+  MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first (for at least this batch)");
+  if (R > c->hoist_rows) {
+    MCM_TRY(alloc_f32(c, &c->mod_all, R * c->mod_total));
+    MCM_TRY(alloc_f32(c, &c->emb_all, R * E));
+    MCM_TRY(dev_alloc(c, reinterpret_cast<void**>(&c->t_all), R * sizeof(long long)));
+    if (c->step_buf == nullptr) MCM_TRY(dev_alloc(c, reinterpret_cast<void**>(&c->step_buf), 256));
+    MCM_TRY(alloc_op(c, &c->te_all, R * D, D, true));
+    MCM_TRY(alloc_op(c, &c->t1_all, R * E, E, true));
+    MCM_TRY(alloc_op(c, &c->embop_all, R * E, E, true));
+    c->hoist_rows = R;
+  }
+  std::vector<long long> th(R);
+  for (int i = 0; i < S; ++i)
+    for (int b = 0; b < B; ++b) th[(size_t)i * B + b] = s->timestep_map[i];
+  MCM_CUDA(cudaMemcpyAsync(c->t_all, th.data(), R * sizeof(long long), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+  MCM_TRY(timestep_embedding_launch(c->t_all, 0, (int)R, D, c->te_all, fp, st));
+  {
+    GemmProblem g = linear_problem(c->te_all, (int)R, c->w_te0, E, D, fp);
+    g.seg[0] = seg_default(E, 0);
+    g.seg[0].bias = c->b_te0; g.seg[0].flags = EPI_SILU; g.seg[0].op = c->t1_all; g.seg[0].op_fmt = fp;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  {  // + xf_proj[sample]: one GEMM batch per step, the addend indexed by the row within the batch
+    GemmProblem g = linear_problem(c->t1_all, B, c->w_te2, E, E, fp);
+    g.a_batches = S; g.batches = S; g.out_rows_per_outer = B;
+    g.seg[0] = seg_default(E, 0);
+    g.seg[0].bias = c->b_te2; g.seg[0].addend = c->xfproj32; g.seg[0].out32 = c->emb_all; g.seg[0].ld32 = E;
+    g.seg[0].flags = EPI_ADDEND_BCAST;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  MCM_TRY(pack_op_launch(c->emb_all, (int)R, E, E, true, c->embop_all, fp, st));
+  {
+    GemmProblem g = linear_problem(c->embop_all, (int)R, c->w_mod, c->mod_total, E, fp);
+    g.seg[0] = seg_default(c->mod_total, 0);
+    g.seg[0].bias = c->b_mod; g.seg[0].out32 = c->mod_all; g.seg[0].ld32 = c->mod_total;
+    MCM_TRY(gemm_tc_launch(g, st));
+  }
+  return 0;
+}
+
 int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const NoiseSource& ns, float* x_io, cudaStream_t st) {
   const size_t rows = (size_t)B * c->T;
   const size_t n = rows * c->IN;
   const bool stochastic = s->mode == 1 || s->eta != 0.f;
   if (stochastic && !ns.dev) MCM_TRY(ensure_noise_buf(c));
+  // hoist the timestep-conditioned modulation out of the loop while the table of all steps stays small (<= 256 MB)
+  static const size_t hoist_cap = [] { const char* e = getenv("MCM_HOIST_MOD_MB"); return (size_t)(e ? atoi(e) : 256) << 20; }();
+  c->hoist_active = c->hoist_mod && !timing_enabled() && c->mod_total % 4 == 0 &&
+                    (size_t)s->n_steps * B * c->mod_total * 4 <= hoist_cap;
+  if (c->hoist_active) {
+    const int rc = precompute_mod_all(c, s, B, st);
+    if (rc != 0) { c->hoist_active = false; return rc; }
+  }
+  struct HoistOff { mcm_ctx* c; ~HoistOff() { c->hoist_active = false; } } hoist_off{c};
   // x_io holds x_T on entry and x_0 on exit; xop must already hold the operand copy of x_T
   for (int i = s->n_steps - 1; i >= 0; --i) {
+    if (c->hoist_active) MCM_TRY(fill_timesteps_launch(c->step_buf, (long long)i, 1, st));
     MCM_TRY(run_denoiser_step(c, B, s->timestep_map[i], st));
     const float* noise = nullptr;
     if (stochastic && i != 0) MCM_TRY(step_noise_ptr(c, ns, i, n, st, &noise));
@@ -873,6 +944,7 @@ int mcm_create(const mcm_config* cfg, mcm_ctx** out) {
   if (const char* e = getenv("MCM_DUAL")) dual_env = atoi(e);
   if (const char* e = getenv("MCM_GRAPH")) c->use_graph = atoi(e);
   if (const char* e = getenv("MCM_SPLIT_SMS")) c->split_sms = atoi(e);
+  if (const char* e = getenv("MCM_HOIST_MOD")) c->hoist_mod = atoi(e);
   if (dev_alloc(c, reinterpret_cast<void**>(&c->t_buf), (size_t)c->Bmax * sizeof(long long))) return fail(0);
   if (cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
@@ -924,6 +996,8 @@ int mcm_set_option(mcm_ctx* c, const char* name, int value) {
     c->use_graph = value;
   } else if (n == "split_sms") {
     c->split_sms = value;
+  } else if (n == "hoist_mod") {
+    c->hoist_mod = value;
   } else if (n == "chunk") {
     c->chunk = value;
   } else if (n == "fused") {

@@ -594,6 +594,17 @@ __global__ void fill_timesteps_kernel(long long* __restrict__ t_buf, long long t
   if (i < B) t_buf[i] = t;
 }
 
+// out[0..n) = src[idx[0] * n + (0..n)): one slice of a per-step table picked by a DEVICE index, so that the node can live in a
+// CUDA graph that is replayed for every step
+__global__ void __launch_bounds__(256)
+gather_slice_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ out, size_t n4) {
+  pdl_trigger();
+  pdl_wait();
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (size_t)idx[0] * n4;
+  float4* o4 = reinterpret_cast<float4*>(out);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) o4[i] = s4[i];
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   return (int)std::min<size_t>(g, 148 * 16);
@@ -603,6 +614,15 @@ inline int grid_for(size_t total, int block) {
 int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream) {
   LaunchTimer lt(LK_ROW, stream);
   MCM_CUDA(launch_pdl(fill_timesteps_kernel, dim3((B + 255) / 256), dim3(256), (size_t)(0), stream, t_buf, t, B));
+  MCM_CUDA(cudaGetLastError());
+  g_ew_launches.fetch_add(1);
+  return 0;
+}
+
+int gather_slice_launch(const float* src, const long long* idx_dev, float* out, size_t n, cudaStream_t stream) {
+  MCM_CHECK(n % 4 == 0, "gather_slice: slice length must be a multiple of 4");
+  LaunchTimer lt(LK_ROW, stream);
+  MCM_CUDA(launch_pdl(gather_slice_kernel, dim3(grid_for(n / 4, 256)), dim3(256), (size_t)(0), stream, src, idx_dev, out, n / 4));
   MCM_CUDA(cudaGetLastError());
   g_ew_launches.fetch_add(1);
   return 0;

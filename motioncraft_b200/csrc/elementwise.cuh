@@ -52,6 +52,8 @@ int undo_launch(float* x, const float* noise, size_t rows, int cols, float a, fl
 
 // t_buf[0..B) = t  (the timestep of the current sampler step, read by the graph-captured timestep embedding)
 int fill_timesteps_launch(long long* t_buf, long long t, int B, cudaStream_t stream);
+// out[0..n) = src[idx_dev[0] * n + (0..n)) (n % 4 == 0): a per-step table slice selected by a device-resident index
+int gather_slice_launch(const float* src, const long long* idx_dev, float* out, size_t n, cudaStream_t stream);
 
 // out[0..n) ~ N(0, 1): Philox4x32-10 keyed by (seed, sub) + Box-Muller; `sub` numbers the draw (sampler step / RePaint draw)
 int randn_fill_launch(float* out, size_t n, unsigned long long seed, unsigned long long sub, cudaStream_t stream);
