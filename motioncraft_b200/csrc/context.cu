@@ -788,8 +788,8 @@ int run_sampler(mcm_ctx* c, const mcm_sampler* s, int B, const NoiseSource& ns, 
   const size_t n = rows * c->IN;
   const bool stochastic = s->mode == 1 || s->eta != 0.f;
   if (stochastic && !ns.dev) MCM_TRY(ensure_noise_buf(c));
-  // hoist the timestep-conditioned modulation out of the loop while the table of all steps stays small (<= 256 MB)
-  static const size_t hoist_cap = [] { const char* e = getenv("MCM_HOIST_MOD_MB"); return (size_t)(e ? atoi(e) : 256) << 20; }();
+  // hoist the timestep-conditioned modulation out of the loop while the table of all steps stays small (<= 2 GB: t2m B = 256 x 50 steps = 1 GB)
+  static const size_t hoist_cap = [] { const char* e = getenv("MCM_HOIST_MOD_MB"); return (size_t)(e ? atoi(e) : 2048) << 20; }();
   c->hoist_active = c->hoist_mod && !timing_enabled() && c->mod_total % 4 == 0 &&
                     (size_t)s->n_steps * B * c->mod_total * 4 <= hoist_cap;
   if (c->hoist_active) {
