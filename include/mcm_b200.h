@@ -79,7 +79,10 @@ void mcm_destroy(mcm_ctx* ctx);
  *   "fused_min_rows" n = use the persistent fused kernels only for launches of at least n rows (B*T, per
  *               stream: half the batch with "dual"); default 2048.  Results of the two schedules agree to ~2e-4, not bit for bit
  *   "fused_sa_min_rows" n = a separate threshold for the fused channel-attention kernels; default -1 = fused_min_rows
- *   "split_sms" 1 = with "dual", every persistent kernel takes half the SMs so the halves run side by side (default 0: slower) */
+ *   "split_sms" 1 = with "dual", every persistent kernel takes half the SMs so the halves run side by side (default 0: slower)
+ *   "hoist_mod" 1 (default) = mcm_sample / mcm_sample_host compute the timestep-conditioned AdaLN modulation of ALL steps in one
+ *               batched pass before the loop while that table stays below 2 GB (env MCM_HOIST_MOD_MB); 0 = per step always.
+ *               Scheduling only: x_0 does not depend on it. */
 int mcm_set_option(mcm_ctx* ctx, const char* name, int value);
 
 /* replaces: load_checkpoint / nn.Module.load_state_dict.  `name` is the reference state_dict key
