@@ -745,6 +745,7 @@ int precompute_mod_all(mcm_ctx* c, const mcm_sampler* s, int B, cudaStream_t st)
   const size_t R = (size_t)S * B;
   MCM_CHECK(c->cond_ready && c->cond_batch >= B, "mcm_prepare_conditions must be called first (for at least this batch)");
   if (R > c->hoist_rows) {
+    c->drop_graphs();            // captured steps gather from the OLD table address
     MCM_TRY(alloc_f32(c, &c->mod_all, R * c->mod_total));
     MCM_TRY(alloc_f32(c, &c->emb_all, R * E));
     MCM_TRY(dev_alloc(c, reinterpret_cast<void**>(&c->t_all), R * sizeof(long long)));

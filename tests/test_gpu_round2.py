@@ -439,3 +439,31 @@ def test_per_head_channel_attention_contractions_match_the_masked_product(tmp_pa
         assert torch.isfinite(base[k]).all()
     assert torch.equal(full["196"], base["196"]) and torch.equal(full["300"], base["300"])
     assert C.rel_l2(base["1024"], full["1024"]) < 1e-6
+
+
+def test_hoisted_modulation_is_scheduling_only_and_survives_a_longer_schedule():
+    """The sampler computes the timestep-conditioned AdaLN modulation of ALL steps before the loop (hoist_mod, default on) and
+    every captured step gathers its slice from that table.  (1) x_0 is bit-identical with the hoist off; (2) a LONGER schedule
+    on the same engine re-allocates the table -- captured step graphs must not keep gathering from the old one: the result
+    equals a fresh engine's; (3) going back to the short schedule still reproduces the first result."""
+    T, B = 60, 3
+    x, xf_out, xf_proj = C.inputs(B, T)
+    sd = C.hot(C.base_state(T, 2))
+
+    def tables(respace):
+        tb, tmap = O.spaced_tables(1000, respace)
+        return SamplerTables(tb, tmap, "ddim")
+
+    eng = DenoiserEngine(sd, seq_len=T, max_batch=B, num_layers=2)
+    eng.prepare_conditions(xf_out.cuda(), xf_proj.cuda())
+    short = eng.sample(tables("10"), x.cuda())
+    long_ = eng.sample(tables("25"), x.cuda())                  # 25 x B rows > 10 x B: the table grows
+    assert torch.equal(eng.sample(tables("10"), x.cuda()), short)
+    eng.set_option("hoist_mod", 0)
+    assert torch.equal(eng.sample(tables("10"), x.cuda()), short)
+    assert torch.equal(eng.sample(tables("25"), x.cuda()), long_)
+    eng.close()
+    fresh = DenoiserEngine(sd, seq_len=T, max_batch=B, num_layers=2)
+    fresh.prepare_conditions(xf_out.cuda(), xf_proj.cuda())
+    assert torch.equal(fresh.sample(tables("25"), x.cuda()), long_)
+    fresh.close()
